@@ -1,0 +1,273 @@
+"""
+ORACLE (test infrastructure only -- never imported by the product path).
+
+Plain-PyTorch fp32 restatement of the YOLOv5-P6 `DetectionModel` forward that the reference executes at
+/root/reference/megadetector/detection/pytorch_detector.py:1313 (`self.model(batch_tensor)[0]`) after
+`.float().fuse().eval()` (:957).
+
+The module graph lives in the un-vendored dependency `ultralytics-yolov5 == 0.1.1`
+(/root/reference/pyproject.toml:70; imports at pytorch_detector.py:333-338); neither it nor MDv5 weights
+exist offline.  PARITY UNPINNED for this file: the topology follows the public `yolov5x6.yaml`
+ and is checked only through invariants (139.99 M fused parameters at nc=3,
+140.73 M at nc=80, 249.49 GMAC at 768x1280).  Everything the GPU engine is compared with is THIS
+restatement, run in fp32.
+
+Weight naming follows the fused yolov5 state dict so a real checkpoint maps 1:1:
+    model.{i}.conv.{weight,bias}                     plain Conv
+    model.{i}.cv{1,2,3}.conv.*, model.{i}.m.{j}.cv{1,2}.conv.*      C3
+    model.11.cv{1,2}.conv.*                           SPPF
+    model.33.m.{l}.{weight,bias}                      Detect 1x1 heads
+"""
+
+from dataclasses import dataclass, field
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+DEFAULT_ANCHORS_PX = [
+    [19, 27, 44, 40, 38, 94],
+    [96, 68, 86, 152, 180, 137],
+    [140, 301, 303, 264, 238, 542],
+    [436, 615, 739, 380, 925, 792],
+]
+STRIDES = [8, 16, 32, 64]
+
+
+@dataclass
+class Arch:
+    """YOLOv5-P6 family member.  Defaults = yolov5x6 (depth 1.33, width 1.25) with MegaDetector's nc=3."""
+    ch: list = field(default_factory=lambda: [80, 160, 320, 640, 960, 1280])
+    n_backbone: list = field(default_factory=lambda: [4, 8, 12, 4, 4])  # C3 repeats at idx 2,4,6,8,10
+    n_head: int = 4
+    nc: int = 3
+    anchors_px: list = field(default_factory=lambda: [list(a) for a in DEFAULT_ANCHORS_PX])
+
+    @property
+    def no(self):
+        return self.nc + 5
+
+
+def tiny_arch():
+    """Same topology, quarter the width and shallow: used by fast tests."""
+    return Arch(ch=[32, 64, 128, 256, 384, 512], n_backbone=[1, 2, 2, 1, 1], n_head=1, nc=3)
+
+
+def conv_specs(arch):
+    """
+    Ordered list of every fused conv: (name, c_in, c_out, k, s, p, act).  This order is also the
+    canonical execution order used by the engine's plan.
+    """
+    c = arch.ch
+    specs = []
+
+    def conv(name, ci, co, k, s, p=None, act=True):
+        specs.append((name, ci, co, k, s, k // 2 if p is None else p, act))
+
+    def c3(i, ci, co, n):
+        h = co // 2
+        conv('model.%d.cv1.conv' % i, ci, h, 1, 1)
+        conv('model.%d.cv2.conv' % i, ci, h, 1, 1)
+        for j in range(n):
+            conv('model.%d.m.%d.cv1.conv' % (i, j), h, h, 1, 1)
+            conv('model.%d.m.%d.cv2.conv' % (i, j), h, h, 3, 1)
+        conv('model.%d.cv3.conv' % i, 2 * h, co, 1, 1)
+
+    nb = arch.n_backbone
+    conv('model.0.conv', 3, c[0], 6, 2, 2)
+    conv('model.1.conv', c[0], c[1], 3, 2)
+    c3(2, c[1], c[1], nb[0])
+    conv('model.3.conv', c[1], c[2], 3, 2)
+    c3(4, c[2], c[2], nb[1])
+    conv('model.5.conv', c[2], c[3], 3, 2)
+    c3(6, c[3], c[3], nb[2])
+    conv('model.7.conv', c[3], c[4], 3, 2)
+    c3(8, c[4], c[4], nb[3])
+    conv('model.9.conv', c[4], c[5], 3, 2)
+    c3(10, c[5], c[5], nb[4])
+    conv('model.11.cv1.conv', c[5], c[5] // 2, 1, 1)
+    conv('model.11.cv2.conv', c[5] * 2, c[5], 1, 1)
+    nh = arch.n_head
+    conv('model.12.conv', c[5], c[4], 1, 1)
+    c3(15, 2 * c[4], c[4], nh)
+    conv('model.16.conv', c[4], c[3], 1, 1)
+    c3(19, 2 * c[3], c[3], nh)
+    conv('model.20.conv', c[3], c[2], 1, 1)
+    c3(23, 2 * c[2], c[2], nh)
+    conv('model.24.conv', c[2], c[2], 3, 2)
+    c3(26, 2 * c[2], c[3], nh)
+    conv('model.27.conv', c[3], c[3], 3, 2)
+    c3(29, 2 * c[3], c[4], nh)
+    conv('model.30.conv', c[4], c[4], 3, 2)
+    c3(32, 2 * c[4], c[5], nh)
+    for l, ci in enumerate([c[2], c[3], c[4], c[5]]):
+        specs.append(('model.33.m.%d' % l, ci, 3 * arch.no, 1, 1, 0, False))
+    return specs
+
+
+def count_params_and_macs(arch, h, w):
+    """Fused parameter count and conv multiply-accumulates for one h x w input."""
+    params, macs = 0, 0
+    # spatial size per conv: follow the graph
+    sizes = {}
+    H, W = h, w
+    res = {}
+    for name, ci, co, k, s, p, act in conv_specs(arch):
+        params += co * ci * k * k + co
+    # MACs: walk by stage resolution
+    lvl = {0: 2, 1: 4, 2: 4, 3: 8, 4: 8, 5: 16, 6: 16, 7: 32, 8: 32, 9: 64, 10: 64, 11: 64, 12: 64, 15: 32, 16: 32,
+           19: 16, 20: 16, 23: 8, 24: 16, 26: 16, 27: 32, 29: 32, 30: 64, 32: 64}
+    det_lvl = [8, 16, 32, 64]
+    for name, ci, co, k, s, p, act in conv_specs(arch):
+        idx = int(name.split('.')[1])
+        if idx == 33:
+            st = det_lvl[int(name.split('.')[3])]
+        else:
+            st = lvl[idx]
+        macs += (h // st) * (w // st) * co * ci * k * k
+    return params, macs
+
+
+_CALIB = None  # set only inside calibrated_random_weights()
+
+
+def default_calibration_input(h=1080, w=1920, index=100000):
+    """One synthetic benchmark-style image (never part of a test pool), letterboxed, as model input."""
+    from megadetector_b200.synth import synth_image
+    from oracle.letterbox import letterbox, to_model_input
+    img, _, _ = letterbox(synth_image(index, h, w))
+    return torch.from_numpy(to_model_input(img))[None]
+
+
+def calibrated_random_weights(arch, seed=0, calib_input=None, obj_logit=(-13.0, 2.5)):
+    """
+    "Calibrated random init" (SURVEY.md par. 8d): with plain random weights the activations of a
+    ~100-conv-deep residual network explode or die, every anchor gets the same score and the
+    threshold/NMS stages degenerate into pure tie-breaking.  So: draw N(0, 1/fan_in) weights, then walk
+    the graph once on a letterboxed synthetic benchmark image and rescale each conv so its pre-activation std is 1
+    (0.7 on the residual branches), fused bias ~ N(0, 0.1^2).  The Detect heads are scaled so that the
+    objectness logit is ~N(obj_logit) (a few 10^3..10^4 anchors above the 1e-5 batch-path threshold, a
+    few 10^1..10^2 above 0.005), box logits ~N(0,1), class logits ~N(0,1.5).
+    Deterministic for a given (arch, seed, calib_input) on a given machine; the weights are generated once
+    per test/bench process and handed to both the oracle and the engine.
+    """
+    global _CALIB
+    g = torch.Generator().manual_seed(seed)
+    w = {}
+    for name, ci, co, k, s, p, act in conv_specs(arch):
+        fan_in = ci * k * k
+        w[name + '.weight'] = torch.randn(co, ci, k, k, generator=g) / fan_in ** 0.5
+        w[name + '.bias'] = torch.randn(co, generator=g) * 0.1
+    if calib_input is None:
+        calib_input = default_calibration_input()
+    x = calib_input
+    _CALIB = {'obj_logit': obj_logit, 'no': arch.no}
+    try:
+        forward(x, w, arch)
+    finally:
+        _CALIB = None
+    return w
+
+
+def _calibrate(x, w, name, s, p):
+    y = F.conv2d(x, w[name + '.weight'], None, stride=s, padding=p)
+    if name.startswith('model.33.'):
+        no = _CALIB['no']
+        wt = w[name + '.weight'].view(3, no, -1)
+        b = w[name + '.bias'].view(3, no)
+        yy = y.view(y.shape[0], 3, no, -1)
+        for a in range(3):
+            for c in range(no):
+                tgt_std = 1.0 if c < 4 else (_CALIB['obj_logit'][1] if c == 4 else 1.5)
+                tgt_mean = 0.0 if c != 4 else _CALIB['obj_logit'][0]
+                v = yy[:, a, c]
+                sc = tgt_std / float(v.std() + 1e-12)
+                wt[a, c] *= sc
+                b[a, c] = tgt_mean - float(v.mean()) * sc
+    else:
+        tgt = 0.7 if ('.m.' in name and name.endswith('cv2.conv')) else 1.0
+        w[name + '.weight'] *= tgt / float(y.std() + 1e-12)
+
+
+def _conv(x, w, name, s=1, p=0, act=True, trace=None):
+    if _CALIB is not None:
+        _calibrate(x, w, name, s, p)
+    y = F.conv2d(x, w[name + '.weight'], w[name + '.bias'], stride=s, padding=p)
+    if act:
+        y = F.silu(y)
+    if trace is not None:
+        trace[name] = y
+    return y
+
+
+def _c3(x, w, i, n, shortcut, trace):
+    pre = 'model.%d' % i
+    a = _conv(x, w, pre + '.cv1.conv', trace=trace)
+    for j in range(n):
+        b = _conv(a, w, '%s.m.%d.cv1.conv' % (pre, j), trace=trace)
+        b = _conv(b, w, '%s.m.%d.cv2.conv' % (pre, j), p=1, trace=trace)
+        a = a + b if shortcut else b
+        if trace is not None:
+            trace['%s.m.%d' % (pre, j)] = a
+    c = _conv(x, w, pre + '.cv2.conv', trace=trace)
+    return _conv(torch.cat((a, c), 1), w, pre + '.cv3.conv', trace=trace)
+
+
+def decode_level(raw, level, arch):
+    """
+    yolov5 (v7.0 era, = ultralytics-yolov5 0.1.1) `Detect.forward` inference branch for one level.
+    raw: [B, na*no, ny, nx] conv output -> [B, na*ny*nx, no] rows ordered (anchor, y, x).
+    """
+    B, _, ny, nx = raw.shape
+    na, no = 3, arch.no
+    x = raw.view(B, na, no, ny, nx).permute(0, 1, 3, 4, 2).contiguous()
+    y = x.sigmoid()
+    yv, xv = torch.meshgrid(torch.arange(ny, dtype=torch.float32), torch.arange(nx, dtype=torch.float32), indexing='ij')
+    grid = torch.stack((xv, yv), 2).expand(1, na, ny, nx, 2) - 0.5
+    anchor_grid = torch.tensor(arch.anchors_px[level], dtype=torch.float32).view(1, na, 1, 1, 2)
+    xy = (y[..., 0:2] * 2 + grid) * float(STRIDES[level])
+    wh = (y[..., 2:4] * 2) ** 2 * anchor_grid
+    out = torch.cat((xy, wh, y[..., 4:]), 4)
+    return out.view(B, na * ny * nx, no)
+
+
+@torch.no_grad()
+def forward(x, w, arch=None, trace=None):
+    """x: float32 [B,3,H,W] in [0,1].  Returns pred [B, n_anchors, 5+nc] (and fills `trace` if given)."""
+    arch = arch or Arch()
+    nb, nh = arch.n_backbone, arch.n_head
+    x0 = _conv(x, w, 'model.0.conv', s=2, p=2, trace=trace)
+    x1 = _conv(x0, w, 'model.1.conv', s=2, p=1, trace=trace)
+    x2 = _c3(x1, w, 2, nb[0], True, trace)
+    x3 = _conv(x2, w, 'model.3.conv', s=2, p=1, trace=trace)
+    x4 = _c3(x3, w, 4, nb[1], True, trace)
+    x5 = _conv(x4, w, 'model.5.conv', s=2, p=1, trace=trace)
+    x6 = _c3(x5, w, 6, nb[2], True, trace)
+    x7 = _conv(x6, w, 'model.7.conv', s=2, p=1, trace=trace)
+    x8 = _c3(x7, w, 8, nb[3], True, trace)
+    x9 = _conv(x8, w, 'model.9.conv', s=2, p=1, trace=trace)
+    x10 = _c3(x9, w, 10, nb[4], True, trace)
+    # SPPF
+    s1 = _conv(x10, w, 'model.11.cv1.conv', trace=trace)
+    p1 = F.max_pool2d(s1, 5, 1, 2)
+    p2 = F.max_pool2d(p1, 5, 1, 2)
+    p3 = F.max_pool2d(p2, 5, 1, 2)
+    x11 = _conv(torch.cat((s1, p1, p2, p3), 1), w, 'model.11.cv2.conv', trace=trace)
+    # head
+    x12 = _conv(x11, w, 'model.12.conv', trace=trace)
+    x15 = _c3(torch.cat((F.interpolate(x12, scale_factor=2, mode='nearest'), x8), 1), w, 15, nh, False, trace)
+    x16 = _conv(x15, w, 'model.16.conv', trace=trace)
+    x19 = _c3(torch.cat((F.interpolate(x16, scale_factor=2, mode='nearest'), x6), 1), w, 19, nh, False, trace)
+    x20 = _conv(x19, w, 'model.20.conv', trace=trace)
+    x23 = _c3(torch.cat((F.interpolate(x20, scale_factor=2, mode='nearest'), x4), 1), w, 23, nh, False, trace)
+    x24 = _conv(x23, w, 'model.24.conv', s=2, p=1, trace=trace)
+    x26 = _c3(torch.cat((x24, x20), 1), w, 26, nh, False, trace)
+    x27 = _conv(x26, w, 'model.27.conv', s=2, p=1, trace=trace)
+    x29 = _c3(torch.cat((x27, x16), 1), w, 29, nh, False, trace)
+    x30 = _conv(x29, w, 'model.30.conv', s=2, p=1, trace=trace)
+    x32 = _c3(torch.cat((x30, x12), 1), w, 32, nh, False, trace)
+    z = []
+    for l, f in enumerate([x23, x26, x29, x32]):
+        raw = _conv(f, w, 'model.33.m.%d' % l, act=False, trace=trace)
+        z.append(decode_level(raw, l, arch))
+    return torch.cat(z, 1)
