@@ -1,0 +1,147 @@
+/*
+ * mdb200.h -- C ABI of libmdb200.so, the B200-native batch detection engine that drops in behind
+ * MegaDetector's PyTorch detector.
+ *
+ * The reference has no FFI: its seam is the Python duck type returned by
+ *   run_detector.load_detector()                      megadetector/detection/run_detector.py:601-681
+ * i.e. PTDetector                                      megadetector/detection/pytorch_detector.py:739-1482
+ * The Python mirror of that class (megadetector_b200/detector.py) binds exactly the entry points declared
+ * here through ctypes; INTEGRATION.md shows the reference-side hook.  Each function cites the reference
+ * code it replaces.
+ *
+ * Conventions: every function returns MDB_OK (0) or a negative error; no exception crosses the
+ * boundary; the caller owns all host buffers; the library owns device memory inside the opaque handle;
+ * one handle per GPU; a handle is not thread-safe, different handles are independent.  There is no CPU
+ * fallback: without a CUDA device mdb_create() fails with MDB_ERR_CUDA.
+ */
+#ifndef MDB200_H_
+#define MDB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define MDB_API __attribute__((visibility("default")))
+#else
+#define MDB_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MDB_OK 0
+#define MDB_ERR_CUDA (-1)
+#define MDB_ERR_ARG (-2)
+#define MDB_ERR_STATE (-3)
+#define MDB_ERR_NOMEM (-4)
+
+/* per-image status written by the infer calls */
+#define MDB_IMG_OK 0
+#define MDB_IMG_BAD_INPUT 1   /* maps to FAILURE_IMAGE_OPEN, run_detector.py:55 */
+#define MDB_IMG_INFER_FAILED 2 /* maps to FAILURE_INFER,      run_detector.py:56 */
+
+#define MDB_MAX_DET_CAP 300 /* nms(max_det=300), pytorch_detector.py:502 */
+
+typedef struct mdb_engine mdb_engine;
+
+/* YOLOv5-P6 family member.  yolov5x6 / MDv5: ch={80,160,320,640,960,1280},
+ * n_backbone={4,8,12,4,4}, n_head=4, nc=3. */
+typedef struct mdb_arch {
+  int32_t ch[6];
+  int32_t n_backbone[5];
+  int32_t n_head;
+  int32_t nc;
+  float anchors_px[4][3][2]; /* Detect.anchors * stride, (w,h) in letterbox pixels */
+} mdb_arch;
+
+typedef struct mdb_config {
+  int32_t struct_size; /* sizeof(mdb_config), checked */
+  int32_t device;      /* CUDA ordinal ("cuda:0" hard-coded at pytorch_detector.py:863-864) */
+  int32_t max_batch;   /* images per forward pass */
+  int32_t img_size;    /* 1280: default_image_size, pytorch_detector.py:798-810 */
+  int32_t stride;      /* 64:   letterbox_stride,   pytorch_detector.py:826-843 */
+  int32_t letterbox_auto;    /* 1 in "classic" mode, pytorch_detector.py:1064-1068 */
+  int32_t letterbox_scaleup; /* 1 in "classic" mode */
+  float iou_thres;     /* 0.45 classic / 0.6 otherwise, pytorch_detector.py:1318-1321 */
+  int32_t max_det;     /* 300 */
+  mdb_arch arch;
+} mdb_config;
+
+/* A named fp32 tensor in the fused-yolov5 state-dict naming and PyTorch layout
+ * (conv weight [Cout][Cin][kh][kw], bias [Cout]); see oracle/yolov5.py for the names. */
+typedef struct mdb_tensor_desc {
+  const char* name;
+  const float* data;
+  int32_t ndim;
+  int64_t shape[4];
+} mdb_tensor_desc;
+
+/* ---- life cycle: replaces PTDetector.__init__/_load_model, pytorch_detector.py:745-959 ---- */
+MDB_API int mdb_create(mdb_engine** out, const mdb_config* cfg);
+MDB_API int mdb_load_weights(mdb_engine* e, const mdb_tensor_desc* tensors, int32_t n);
+MDB_API void mdb_destroy(mdb_engine* e);
+/* last error text of this handle (or of the failed mdb_create when e == NULL) */
+MDB_API const char* mdb_last_error(const mdb_engine* e);
+
+/* ---- the hot path: replaces PTDetector.generate_detections_one_batch for raw images,
+ *      pytorch_detector.py:1124-1252 = preprocess_image (:964) + _process_batch_group (:1257-1424)
+ *      up to and including scale_coords(...).round() (:1379).
+ * rgb_hwc[i]   : uint8 RGB, h[i] x w[i] x 3, row_stride[i] bytes between rows (pageable or pinned host memory)
+ * conf_thres   : detection_threshold (1e-5 on the batch path, run_detector_batch.py:751-754)
+ * det_out      : [n][max_det][6] = x1,y1,x2,y2 (original-image pixels, rounded half-to-even), conf, class(0-based)
+ *                rows sorted by conf descending (ties: anchor index ascending)
+ * det_count    : [n]
+ * kept_anchor  : [n][max_det] row index into the model's prediction tensor (for bit-exact index parity); may be NULL
+ * status       : [n] MDB_IMG_*
+ * Images are grouped by letterboxed shape internally (pytorch_detector.py:1226-1233). */
+MDB_API int mdb_infer_batch(mdb_engine* e, const uint8_t* const* rgb_hwc, const int32_t* h, const int32_t* w,
+                    const int64_t* row_stride, int32_t n, float conf_thres, float* det_out, int32_t* det_count,
+                    int32_t* kept_anchor, int32_t* status);
+
+/* Same, for images already letterboxed by a producer worker (dict inputs, run_detector_batch.py:175-183):
+ * lb_hwc[i] is lh[i] x lw[i] x 3 (dense), src_h/src_w the original size used by scale_coords. */
+MDB_API int mdb_infer_preprocessed(mdb_engine* e, const uint8_t* const* lb_hwc, const int32_t* lh, const int32_t* lw,
+                           const int32_t* src_h, const int32_t* src_w, int32_t n, float conf_thres, float* det_out,
+                           int32_t* det_count, int32_t* kept_anchor, int32_t* status);
+
+/* Letterbox geometry exactly as the reference computes it (pytorch_detector.py:434-452,1104-1109):
+ * out[0..7] = new_unpad_w, new_unpad_h, top, bottom, left, right, out_h, out_w ; ratio_pad[0..2] = r, dw, dh */
+MDB_API int mdb_letterbox_geometry(const mdb_config* cfg, int32_t h, int32_t w, int32_t* out8, double* ratio_pad3);
+
+/* ---- parity / profiling hooks (not used by the product path) ---- */
+#define MDB_FETCH_STEM_INPUT 1 /* K1 output of the last batch: fp16 [n][H/2][W/2][16]            */
+#define MDB_FETCH_PRED 2       /* decoded predictions of the last batch: fp32 [n][anchors][5+nc]  */
+#define MDB_FETCH_LAYER 3      /* fp16 NHWC output of conv #index (order of oracle.yolov5.conv_specs) */
+MDB_API int mdb_debug_fetch(mdb_engine* e, int32_t what, int32_t index, void* host_dst, size_t bytes, int64_t* shape4);
+
+/* device timing of the last infer call, milliseconds: [0]=h2d+preprocess [1]=network [2]=decode+nms [3]=total */
+MDB_API int mdb_last_timing(mdb_engine* e, float* ms4);
+/* number of kernels the engine launched since creation (bench.py's gpu_launches) */
+MDB_API int64_t mdb_launch_count(const mdb_engine* e);
+
+/* ---- single-kernel entry points on HOST buffers, for the parity tests (tests/ -m gpu) ---- */
+/* K1: letterbox + pad(114) + /255 + space-to-depth NHWC fp16.  dst: [out_h/2][out_w/2][16] fp16. */
+MDB_API int mdb_op_letterbox(mdb_engine* e, const uint8_t* rgb_hwc, int32_t h, int32_t w, int64_t row_stride, void* dst_fp16,
+                     int32_t* out_hw2);
+/* K2: one convolution.  x: fp16 NHWC [n][h][w][cin]; wgt: fp32 [cout][cin][k][k]; bias fp32 [cout];
+ * residual (may be NULL): fp16 NHWC [n][ho][wo][cout]; y: fp16 (or fp32 when out_fp32) NHWC [n][ho][wo][cout].
+ * iters>1 repeats the launch and reports the mean device time in *ms (may be NULL). */
+MDB_API int mdb_op_conv2d(mdb_engine* e, const void* x_fp16, int32_t n, int32_t h, int32_t w, int32_t cin, const float* wgt,
+                  const float* bias, int32_t cout, int32_t k, int32_t s, int32_t pad, int32_t act,
+                  const void* residual_fp16, int32_t out_fp32, void* y, int32_t iters, float* ms);
+/* K5-K8: threshold + per-class NMS + top-k on a prediction tensor fp32 [n][anchors][5+nc] (the reference's
+ * nms(), pytorch_detector.py:502-610).  det_out boxes stay in letterbox pixels (no rescale). */
+MDB_API int mdb_op_nms(mdb_engine* e, const float* pred, int32_t n, int32_t anchors, int32_t nc, float conf_thres,
+               double iou_thres, int32_t max_det, float* det_out, int32_t* det_count, int32_t* kept_anchor);
+
+/* ---- host memory helpers (page-locked buffers make the H2D copy asynchronous) ---- */
+MDB_API void* mdb_alloc_pinned(size_t bytes);
+MDB_API void mdb_free_pinned(void* p);
+
+MDB_API const char* mdb_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MDB200_H_ */

@@ -1,0 +1,331 @@
+"""
+ctypes binding of include/mdb200.h (libmdb200.so).  This is the only place Python touches the C ABI.
+
+There is no fallback: if the shared library is missing or cannot be loaded, importing an engine raises.
+"""
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libmdb200.so')
+
+MDB_OK = 0
+MDB_IMG_OK, MDB_IMG_BAD_INPUT, MDB_IMG_INFER_FAILED = 0, 1, 2
+MDB_FETCH_STEM_INPUT, MDB_FETCH_PRED, MDB_FETCH_LAYER = 1, 2, 3
+
+EXPORTS = [
+    'mdb_create', 'mdb_load_weights', 'mdb_destroy', 'mdb_last_error', 'mdb_infer_batch', 'mdb_infer_preprocessed',
+    'mdb_letterbox_geometry', 'mdb_debug_fetch', 'mdb_last_timing', 'mdb_launch_count', 'mdb_op_letterbox',
+    'mdb_op_conv2d', 'mdb_op_nms', 'mdb_alloc_pinned', 'mdb_free_pinned', 'mdb_version',
+]
+
+
+class MdbArch(C.Structure):
+    _fields_ = [('ch', C.c_int32 * 6), ('n_backbone', C.c_int32 * 5), ('n_head', C.c_int32), ('nc', C.c_int32),
+                ('anchors_px', (C.c_float * 2) * 3 * 4)]
+
+
+class MdbConfig(C.Structure):
+    _fields_ = [('struct_size', C.c_int32), ('device', C.c_int32), ('max_batch', C.c_int32), ('img_size', C.c_int32),
+                ('stride', C.c_int32), ('letterbox_auto', C.c_int32), ('letterbox_scaleup', C.c_int32),
+                ('iou_thres', C.c_float), ('max_det', C.c_int32), ('arch', MdbArch)]
+
+
+class MdbTensorDesc(C.Structure):
+    _fields_ = [('name', C.c_char_p), ('data', C.POINTER(C.c_float)), ('ndim', C.c_int32), ('shape', C.c_int64 * 4)]
+
+
+_lib = None
+
+
+def load_library():
+    """dlopen libmdb200.so (building it first if nvcc is here and the sources changed)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            'libmdb200.so is missing ({}): build it with `python -m megadetector_b200.build`. '
+            'megadetector_b200 has no CPU / PyTorch fallback.'.format(LIB_PATH))
+    lib = C.CDLL(LIB_PATH)
+    P = C.POINTER
+    vp = C.c_void_p
+    lib.mdb_create.argtypes = [P(vp), P(MdbConfig)]
+    lib.mdb_create.restype = C.c_int
+    lib.mdb_load_weights.argtypes = [vp, P(MdbTensorDesc), C.c_int32]
+    lib.mdb_load_weights.restype = C.c_int
+    lib.mdb_destroy.argtypes = [vp]
+    lib.mdb_destroy.restype = None
+    lib.mdb_last_error.argtypes = [vp]
+    lib.mdb_last_error.restype = C.c_char_p
+    lib.mdb_infer_batch.argtypes = [vp, P(vp), P(C.c_int32), P(C.c_int32), P(C.c_int64), C.c_int32, C.c_float,
+                                    vp, vp, vp, vp]
+    lib.mdb_infer_batch.restype = C.c_int
+    lib.mdb_infer_preprocessed.argtypes = [vp, P(vp), P(C.c_int32), P(C.c_int32), P(C.c_int32), P(C.c_int32),
+                                           C.c_int32, C.c_float, vp, vp, vp, vp]
+    lib.mdb_infer_preprocessed.restype = C.c_int
+    lib.mdb_letterbox_geometry.argtypes = [P(MdbConfig), C.c_int32, C.c_int32, P(C.c_int32), P(C.c_double)]
+    lib.mdb_letterbox_geometry.restype = C.c_int
+    lib.mdb_debug_fetch.argtypes = [vp, C.c_int32, C.c_int32, vp, C.c_size_t, P(C.c_int64)]
+    lib.mdb_debug_fetch.restype = C.c_int
+    lib.mdb_last_timing.argtypes = [vp, P(C.c_float)]
+    lib.mdb_last_timing.restype = C.c_int
+    lib.mdb_launch_count.argtypes = [vp]
+    lib.mdb_launch_count.restype = C.c_int64
+    lib.mdb_op_letterbox.argtypes = [vp, vp, C.c_int32, C.c_int32, C.c_int64, vp, P(C.c_int32)]
+    lib.mdb_op_letterbox.restype = C.c_int
+    lib.mdb_op_conv2d.argtypes = [vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp, vp, C.c_int32, C.c_int32,
+                                  C.c_int32, C.c_int32, C.c_int32, vp, C.c_int32, vp, C.c_int32, P(C.c_float)]
+    lib.mdb_op_conv2d.restype = C.c_int
+    lib.mdb_op_nms.argtypes = [vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_double, C.c_int32, vp, vp, vp]
+    lib.mdb_op_nms.restype = C.c_int
+    lib.mdb_alloc_pinned.argtypes = [C.c_size_t]
+    lib.mdb_alloc_pinned.restype = vp
+    lib.mdb_free_pinned.argtypes = [vp]
+    lib.mdb_free_pinned.restype = None
+    lib.mdb_version.argtypes = []
+    lib.mdb_version.restype = C.c_char_p
+    _lib = lib
+    return lib
+
+
+DEFAULT_ANCHORS_PX = [
+    [19, 27, 44, 40, 38, 94],
+    [96, 68, 86, 152, 180, 137],
+    [140, 301, 303, 264, 238, 542],
+    [436, 615, 739, 380, 925, 792],
+]
+
+
+def make_config(device=0, max_batch=8, img_size=1280, stride=64, letterbox_auto=True, letterbox_scaleup=True,
+                iou_thres=0.45, max_det=300, ch=(80, 160, 320, 640, 960, 1280), n_backbone=(4, 8, 12, 4, 4), n_head=4,
+                nc=3, anchors_px=None):
+    cfg = MdbConfig()
+    cfg.struct_size = C.sizeof(MdbConfig)
+    cfg.device = device
+    cfg.max_batch = max_batch
+    cfg.img_size = img_size
+    cfg.stride = stride
+    cfg.letterbox_auto = int(bool(letterbox_auto))
+    cfg.letterbox_scaleup = int(bool(letterbox_scaleup))
+    cfg.iou_thres = iou_thres
+    cfg.max_det = max_det
+    for i in range(6):
+        cfg.arch.ch[i] = int(ch[i])
+    for i in range(5):
+        cfg.arch.n_backbone[i] = int(n_backbone[i])
+    cfg.arch.n_head = int(n_head)
+    cfg.arch.nc = int(nc)
+    anchors_px = anchors_px or DEFAULT_ANCHORS_PX
+    for l in range(4):
+        for a in range(3):
+            cfg.arch.anchors_px[l][a][0] = float(anchors_px[l][2 * a])
+            cfg.arch.anchors_px[l][a][1] = float(anchors_px[l][2 * a + 1])
+    return cfg
+
+
+def letterbox_geometry(cfg, h, w):
+    """Pure host arithmetic (works without a GPU): dict mirroring yolov5 letterbox() geometry."""
+    lib = load_library()
+    out = (C.c_int32 * 8)()
+    rp = (C.c_double * 3)()
+    rc = lib.mdb_letterbox_geometry(C.byref(cfg), h, w, out, rp)
+    if rc != MDB_OK:
+        raise ValueError('mdb_letterbox_geometry failed ({})'.format(rc))
+    return {'new_unpad': (out[0], out[1]), 'top': out[2], 'bottom': out[3], 'left': out[4], 'right': out[5],
+            'out_hw': (out[6], out[7]), 'ratio': (rp[0], rp[0]), 'pad': (rp[1], rp[2])}
+
+
+class PinnedArray:
+    """numpy view over page-locked host memory owned by libmdb200."""
+
+    def __init__(self, shape, dtype=np.uint8):
+        lib = load_library()
+        self.nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        self._ptr = lib.mdb_alloc_pinned(self.nbytes)
+        if not self._ptr:
+            raise MemoryError('mdb_alloc_pinned({}) failed'.format(self.nbytes))
+        buf = (C.c_uint8 * self.nbytes).from_address(self._ptr)
+        self.array = np.frombuffer(buf, dtype=dtype).reshape(shape)
+
+    def __del__(self):
+        try:
+            if getattr(self, '_ptr', None):
+                load_library().mdb_free_pinned(self._ptr)
+                self._ptr = None
+        except Exception:
+            pass
+
+
+class Engine:
+    """One mdb_engine handle (one GPU)."""
+
+    def __init__(self, cfg):
+        self.lib = load_library()
+        self.cfg = cfg
+        self.max_det = cfg.max_det
+        self.no = cfg.arch.nc + 5
+        h = C.c_void_p()
+        rc = self.lib.mdb_create(C.byref(h), C.byref(cfg))
+        if rc != MDB_OK:
+            raise RuntimeError('mdb_create failed ({}): {}'.format(rc, (self.lib.mdb_last_error(None) or b'').decode()))
+        self.h = h
+        self._keep = []
+
+    def close(self):
+        if getattr(self, 'h', None):
+            self.lib.mdb_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc != MDB_OK:
+            raise RuntimeError('{} failed ({}): {}'.format(what, rc, (self.lib.mdb_last_error(self.h) or b'').decode()))
+
+    def last_error(self):
+        return (self.lib.mdb_last_error(self.h) or b'').decode()
+
+    def load_weights(self, weights):
+        """weights: dict name -> float32 array-like (numpy or torch CPU tensor), fused-yolov5 naming."""
+        descs = (MdbTensorDesc * len(weights))()
+        keep = []
+        for i, (name, t) in enumerate(weights.items()):
+            a = np.ascontiguousarray(t.detach().cpu().numpy() if hasattr(t, 'detach') else t, dtype=np.float32)
+            keep.append(a)
+            descs[i].name = name.encode()
+            descs[i].data = a.ctypes.data_as(C.POINTER(C.c_float))
+            descs[i].ndim = a.ndim
+            for d in range(a.ndim):
+                descs[i].shape[d] = a.shape[d]
+        self._check(self.lib.mdb_load_weights(self.h, descs, len(weights)), 'mdb_load_weights')
+
+    def infer_batch(self, images, conf_thres, want_anchors=True):
+        """
+        images: list of HxWx3 uint8 arrays (C-contiguous rows; row stride taken from .strides).
+        Returns (det [n,max_det,6] float32, count [n] int32, anchors [n,max_det] int32 or None, status [n] int32).
+        """
+        n = len(images)
+        ptrs = (C.c_void_p * n)()
+        hs = (C.c_int32 * n)()
+        ws = (C.c_int32 * n)()
+        st = (C.c_int64 * n)()
+        for i, im in enumerate(images):
+            ok = isinstance(im, np.ndarray) and im.dtype == np.uint8 and im.ndim == 3 and im.shape[2] == 3 and \
+                im.strides[2] == 1 and im.strides[1] == 3
+            if not ok:
+                ptrs[i] = None
+                hs[i] = ws[i] = 0
+                continue
+            ptrs[i] = im.ctypes.data
+            hs[i], ws[i] = im.shape[0], im.shape[1]
+            st[i] = im.strides[0]
+        det = np.zeros((n, self.max_det, 6), np.float32)
+        cnt = np.zeros((n,), np.int32)
+        anc = np.full((n, self.max_det), -1, np.int32) if want_anchors else None
+        status = np.zeros((n,), np.int32)
+        rc = self.lib.mdb_infer_batch(self.h, ptrs, hs, ws, st, n, float(conf_thres), det.ctypes.data, cnt.ctypes.data,
+                                      anc.ctypes.data if anc is not None else None, status.ctypes.data)
+        self._check(rc, 'mdb_infer_batch')
+        return det, cnt, anc, status
+
+    def infer_preprocessed(self, images, src_shapes, conf_thres, want_anchors=True):
+        n = len(images)
+        ptrs = (C.c_void_p * n)()
+        lh = (C.c_int32 * n)()
+        lw = (C.c_int32 * n)()
+        sh = (C.c_int32 * n)()
+        sw = (C.c_int32 * n)()
+        keep = []
+        for i, im in enumerate(images):
+            a = np.ascontiguousarray(im, dtype=np.uint8)
+            keep.append(a)
+            ptrs[i] = a.ctypes.data
+            lh[i], lw[i] = a.shape[0], a.shape[1]
+            sh[i], sw[i] = int(src_shapes[i][0]), int(src_shapes[i][1])
+        det = np.zeros((n, self.max_det, 6), np.float32)
+        cnt = np.zeros((n,), np.int32)
+        anc = np.full((n, self.max_det), -1, np.int32) if want_anchors else None
+        status = np.zeros((n,), np.int32)
+        rc = self.lib.mdb_infer_preprocessed(self.h, ptrs, lh, lw, sh, sw, n, float(conf_thres), det.ctypes.data,
+                                             cnt.ctypes.data, anc.ctypes.data if anc is not None else None,
+                                             status.ctypes.data)
+        self._check(rc, 'mdb_infer_preprocessed')
+        return det, cnt, anc, status
+
+    def last_timing(self):
+        ms = (C.c_float * 4)()
+        self._check(self.lib.mdb_last_timing(self.h, ms), 'mdb_last_timing')
+        return {'preprocess_ms': ms[0], 'network_ms': ms[1], 'postprocess_ms': ms[2], 'total_ms': ms[3]}
+
+    def launch_count(self):
+        return int(self.lib.mdb_launch_count(self.h))
+
+    def fetch(self, what, index=0):
+        shp = (C.c_int64 * 4)()
+        self._check(self.lib.mdb_debug_fetch(self.h, what, index, None, 0, shp), 'mdb_debug_fetch')
+        shp = [int(x) for x in shp]
+        if what == MDB_FETCH_STEM_INPUT:
+            out = np.empty(shp, np.float16)
+        elif what == MDB_FETCH_PRED:
+            out = np.empty(shp[:3], np.float32)
+        else:
+            out = np.empty((shp[0], shp[1]), np.float16)
+        self._check(self.lib.mdb_debug_fetch(self.h, what, index, out.ctypes.data, out.nbytes, shp_arr(shp)),
+                    'mdb_debug_fetch')
+        if what == MDB_FETCH_LAYER:
+            return out[:, shp[2]:shp[2] + shp[3]]
+        return out
+
+    # ---- single-kernel entry points (parity tests) ----
+    def op_letterbox(self, img):
+        g = letterbox_geometry(self.cfg, img.shape[0], img.shape[1])
+        oh, ow = g['out_hw']
+        out = np.empty((oh // 2, ow // 2, 16), np.float16)
+        hw = (C.c_int32 * 2)()
+        img = np.ascontiguousarray(img)
+        self._check(self.lib.mdb_op_letterbox(self.h, img.ctypes.data, img.shape[0], img.shape[1], img.strides[0],
+                                              out.ctypes.data, hw), 'mdb_op_letterbox')
+        return out
+
+    def op_conv2d(self, x, w, b, k, s, pad, act=True, residual=None, out_fp32=False, iters=1):
+        """x: fp16 NHWC; w: fp32 [co][ci][k][k]; b: fp32 [co]; returns (y NHWC, ms)."""
+        x = np.ascontiguousarray(x, np.float16)
+        w = np.ascontiguousarray(w, np.float32)
+        b = np.ascontiguousarray(b, np.float32)
+        n, h, wd, ci = x.shape
+        co = w.shape[0]
+        ho, wo = (h + 2 * pad - k) // s + 1, (wd + 2 * pad - k) // s + 1
+        y = np.empty((n, ho, wo, co), np.float32 if out_fp32 else np.float16)
+        r = None
+        if residual is not None:
+            r = np.ascontiguousarray(residual, np.float16)
+        ms = C.c_float(0)
+        self._check(self.lib.mdb_op_conv2d(self.h, x.ctypes.data, n, h, wd, ci, w.ctypes.data, b.ctypes.data, co, k, s,
+                                           pad, int(bool(act)), r.ctypes.data if r is not None else None,
+                                           int(bool(out_fp32)), y.ctypes.data, iters, C.byref(ms)), 'mdb_op_conv2d')
+        return y, float(ms.value)
+
+    def op_nms(self, pred, conf_thres, iou_thres=0.45, max_det=300):
+        pred = np.ascontiguousarray(pred, np.float32)
+        n, a, no = pred.shape
+        det = np.zeros((n, max_det, 6), np.float32)
+        cnt = np.zeros((n,), np.int32)
+        anc = np.full((n, max_det), -1, np.int32)
+        self._check(self.lib.mdb_op_nms(self.h, pred.ctypes.data, n, a, no - 5, float(conf_thres), float(iou_thres),
+                                        max_det, det.ctypes.data, cnt.ctypes.data, anc.ctypes.data), 'mdb_op_nms')
+        return det, cnt, anc
+
+
+def shp_arr(shp):
+    a = (C.c_int64 * 4)()
+    for i in range(4):
+        a[i] = shp[i]
+    return a

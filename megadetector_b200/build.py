@@ -1,0 +1,73 @@
+"""
+Builds megadetector_b200/libmdb200.so (hand-written sm_100a CUDA + the C ABI of include/mdb200.h) in-tree with
+nvcc.  No GPU is needed to build (nvcc cross-compiles); the .so is git-ignored but travels to the GPU box.
+
+    python -m megadetector_b200.build [--force] [--verbose]
+"""
+
+import hashlib
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, 'csrc')
+OUT = os.path.join(HERE, 'libmdb200.so')
+OBJ_DIR = os.path.join(HERE, 'csrc', 'build')
+SOURCES = ['tmap.cu', 'conv_host.cu', 'preprocess.cu', 'aux.cu', 'nms.cu', 'engine.cu']
+NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
+ARCH_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a']
+CFLAGS = ['-O3', '-std=c++17', '-lineinfo', '-Xcompiler', '-fPIC', '-Xcompiler', '-fvisibility=hidden',
+          '--expt-relaxed-constexpr']
+
+
+def _stamp():
+    h = hashlib.sha256()
+    names = sorted(os.listdir(CSRC)) + ['../../include/mdb200.h']
+    for n in names:
+        p = os.path.join(CSRC, n)
+        if os.path.isfile(p) and n.endswith(('.cu', '.cuh', '.h')):
+            with open(p, 'rb') as f:
+                h.update(n.encode())
+                h.update(f.read())
+    h.update(' '.join(ARCH_FLAGS + CFLAGS).encode())
+    return h.hexdigest()
+
+
+def build(force=False, verbose=False):
+    """Compile every .cu for sm_100a and link the shared library.  Returns the path of the .so."""
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    stamp_file = os.path.join(OBJ_DIR, 'stamp')
+    stamp = _stamp()
+    if not force and os.path.exists(OUT) and os.path.exists(stamp_file) and open(stamp_file).read() == stamp:
+        return OUT
+    if not os.path.exists(NVCC):
+        raise RuntimeError('nvcc not found at {} and no up-to-date prebuilt libmdb200.so'.format(NVCC))
+    objs = []
+    procs = []
+    for src in SOURCES:
+        obj = os.path.join(OBJ_DIR, src.replace('.cu', '.o'))
+        cmd = [NVCC] + ARCH_FLAGS + CFLAGS + (['-Xptxas', '-v'] if verbose else []) + \
+              ['-c', os.path.join(CSRC, src), '-o', obj]
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        objs.append(obj)
+    failed = False
+    for src, p in procs:
+        out, _ = p.communicate()
+        if p.returncode != 0 or verbose:
+            sys.stderr.write('---- {} ----\n{}\n'.format(src, out))
+        failed = failed or p.returncode != 0
+    if failed:
+        raise RuntimeError('nvcc failed')
+    cmd = [NVCC] + ARCH_FLAGS + ['-shared', '-cudart', 'static', '-Xcompiler', '-fPIC', '-o', OUT] + objs + ['-ldl', '-lpthread', '-lrt']
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout)
+        raise RuntimeError('link failed')
+    with open(stamp_file, 'w') as f:
+        f.write(stamp)
+    return OUT
+
+
+if __name__ == '__main__':
+    print(build(force='--force' in sys.argv, verbose='--verbose' in sys.argv))

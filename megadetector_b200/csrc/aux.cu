@@ -1,0 +1,153 @@
+// K3 nearest-2x upsample into a concat buffer, K4 SPPF max-pools, K5 Detect decode.
+// All three are pure data movement / elementwise work on NHWC tensors: HBM-bound, 16-byte vector accesses,
+// one thread per (pixel, 8-channel group).
+#include <cfloat>
+
+#include "common.h"
+
+namespace mdb {
+
+// ---------------------------------------------------------------------------------------------
+// K3: nn.Upsample(scale_factor=2, mode='nearest') (yolov5x6.yaml idx 13/17/21), written
+// straight into channels [c_off, c_off+C) of the following Concat's buffer.
+// ---------------------------------------------------------------------------------------------
+__global__ void upsample2x_kernel(const __half* __restrict__ src, long long src_px, int src_coff,
+                                  __half* __restrict__ dst, long long dst_px, int dst_coff, int Hs, int Ws, int C8,
+                                  long long total) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c8 = static_cast<int>(i % C8);
+  long long p = i / C8;
+  const int Wd = Ws * 2, Hd = Hs * 2;
+  const int x = static_cast<int>(p % Wd);
+  p /= Wd;
+  const int y = static_cast<int>(p % Hd);
+  const long long n = p / Hd;
+  const long long sp = (n * Hs + (y >> 1)) * Ws + (x >> 1);
+  const long long dp = (n * Hd + y) * Wd + x;
+  const uint4 v = __ldg(reinterpret_cast<const uint4*>(src + sp * src_px + src_coff) + c8);
+  reinterpret_cast<uint4*>(dst + dp * dst_px + dst_coff)[c8] = v;
+}
+
+void upsample2x_launch(const View& src, const View& dst, int n_img, cudaStream_t st) {
+  MDB_REQUIRE(src.C == dst.C && src.C % 8 == 0 && dst.H == 2 * src.H && dst.W == 2 * src.W, "upsample view mismatch");
+  const int C8 = src.C / 8;
+  const long long total = static_cast<long long>(n_img) * dst.H * dst.W * C8;
+  if (total == 0) return;
+  const int threads = 256;
+  upsample2x_kernel<<<static_cast<unsigned>((total + threads - 1) / threads), threads, 0, st>>>(
+      static_cast<const __half*>(src.base), src.Ctot, src.c_off, static_cast<__half*>(dst.base), dst.Ctot, dst.c_off,
+      src.H, src.W, C8, total);
+  MDB_CUDA(cudaGetLastError());
+}
+
+// ---------------------------------------------------------------------------------------------
+// K4: SPPF (yolov5 models/common.py SPPF, k=5): p1 = maxpool5(s1), p2 = maxpool5(p1), p3 = maxpool5(p2),
+// all stride 1 / pad 2 (-inf padding), i.e. 5x5, 9x9 and 13x13 window maxima of s1.  One pass.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void hmax8(uint4& a, const uint4& b) {
+  __half2* pa = reinterpret_cast<__half2*>(&a);
+  const __half2* pb = reinterpret_cast<const __half2*>(&b);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) pa[i] = __hmax2(pa[i], pb[i]);
+}
+
+__global__ void sppf_pool_kernel(const __half* __restrict__ s1, long long px, int c_s1, __half* __restrict__ out,
+                                 int c_p1, int c_p2, int c_p3, int H, int W, int C8, long long total) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c8 = static_cast<int>(i % C8);
+  long long p = i / C8;
+  const int x = static_cast<int>(p % W);
+  p /= W;
+  const int y = static_cast<int>(p % H);
+  const long long n = p / H;
+  const __half2 ninf = __float2half2_rn(-INFINITY);
+  uint4 m5, m9, m13;
+  *reinterpret_cast<__half2*>(&m5.x) = ninf; *reinterpret_cast<__half2*>(&m5.y) = ninf;
+  *reinterpret_cast<__half2*>(&m5.z) = ninf; *reinterpret_cast<__half2*>(&m5.w) = ninf;
+  m9 = m5;
+  m13 = m5;
+  for (int dy = -6; dy <= 6; ++dy) {
+    const int yy = y + dy;
+    if (yy < 0 || yy >= H) continue;
+    for (int dx = -6; dx <= 6; ++dx) {
+      const int xx = x + dx;
+      if (xx < 0 || xx >= W) continue;
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(s1 + ((n * H + yy) * W + xx) * px + c_s1) + c8);
+      hmax8(m13, v);
+      const int ady = dy < 0 ? -dy : dy, adx = dx < 0 ? -dx : dx;
+      if (ady <= 4 && adx <= 4) hmax8(m9, v);
+      if (ady <= 2 && adx <= 2) hmax8(m5, v);
+    }
+  }
+  __half* o = out + ((n * H + y) * W + x) * px;
+  reinterpret_cast<uint4*>(o + c_p1)[c8] = m5;
+  reinterpret_cast<uint4*>(o + c_p2)[c8] = m9;
+  reinterpret_cast<uint4*>(o + c_p3)[c8] = m13;
+}
+
+void sppf_pool_launch(const View& s1, const View& p1, const View& p2, const View& p3, int n_img, cudaStream_t st) {
+  MDB_REQUIRE(s1.base == p1.base && s1.base == p2.base && s1.base == p3.base, "SPPF views must share the concat buffer");
+  MDB_REQUIRE(s1.C % 8 == 0, "SPPF channels must be a multiple of 8");
+  const int C8 = s1.C / 8;
+  const long long total = static_cast<long long>(n_img) * s1.H * s1.W * C8;
+  if (total == 0) return;
+  const int threads = 128;
+  sppf_pool_kernel<<<static_cast<unsigned>((total + threads - 1) / threads), threads, 0, st>>>(
+      static_cast<const __half*>(s1.base), s1.Ctot, s1.c_off, static_cast<__half*>(s1.base), p1.c_off, p2.c_off,
+      p3.c_off, s1.H, s1.W, C8, total);
+  MDB_CUDA(cudaGetLastError());
+}
+
+// ---------------------------------------------------------------------------------------------
+// K5: Detect inference decode (yolov5 models/yolo.py Detect.forward, v7.0 era = ultralytics-yolov5 0.1.1;
+// restated in oracle/yolov5.py::decode_level):   y = sigmoid(raw)
+//     xy = (y*2 + (grid - 0.5)) * stride        wh = (y*2)^2 * anchor_px        rest = y
+// row of pred = level_off + (a*ny + iy)*nx + ix.  Every product/sum is rounded separately (no FMA
+// contraction) so the op order is the reference's.
+// ---------------------------------------------------------------------------------------------
+struct DecodeArgs {
+  DecodeLevel lv[4];
+};
+
+__device__ __forceinline__ float sigmoid_acc(float x) { return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x))); }
+
+__global__ void decode_kernel(const DecodeArgs args, int no, int rows_per_img, float* __restrict__ pred,
+                              long long total_rows) {
+  const long long r = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (r >= total_rows) return;
+  const int n = static_cast<int>(r / rows_per_img);
+  const int row = static_cast<int>(r - static_cast<long long>(n) * rows_per_img);
+  int l = 0;
+#pragma unroll
+  for (int i = 1; i < 4; ++i)
+    if (row >= args.lv[i].row_off) l = i;
+  const DecodeLevel& L = args.lv[l];
+  const int local = row - L.row_off;
+  const int ix = local % L.nx;
+  const int iy = (local / L.nx) % L.ny;
+  const int a = local / (L.nx * L.ny);
+  const float* src = L.raw + ((static_cast<long long>(n) * L.ny + iy) * L.nx + ix) * L.c_stride + a * no;
+  float* dst = pred + r * no;
+  const float s0 = sigmoid_acc(src[0]), s1 = sigmoid_acc(src[1]), s2 = sigmoid_acc(src[2]), s3 = sigmoid_acc(src[3]);
+  dst[0] = __fmul_rn(__fadd_rn(__fmul_rn(s0, 2.0f), static_cast<float>(ix) - 0.5f), L.stride);
+  dst[1] = __fmul_rn(__fadd_rn(__fmul_rn(s1, 2.0f), static_cast<float>(iy) - 0.5f), L.stride);
+  const float w2 = __fmul_rn(s2, 2.0f), h2 = __fmul_rn(s3, 2.0f);
+  dst[2] = __fmul_rn(__fmul_rn(w2, w2), L.anchors[a][0]);
+  dst[3] = __fmul_rn(__fmul_rn(h2, h2), L.anchors[a][1]);
+  for (int c = 4; c < no; ++c) dst[c] = sigmoid_acc(src[c]);
+}
+
+void decode_launch(const DecodeLevel* lv4, int n_img, int no, int rows_per_img, float* pred, cudaStream_t st) {
+  DecodeArgs args;
+  for (int i = 0; i < 4; ++i) args.lv[i] = lv4[i];
+  const long long total = static_cast<long long>(n_img) * rows_per_img;
+  if (total == 0) return;
+  const int threads = 256;
+  decode_kernel<<<static_cast<unsigned>((total + threads - 1) / threads), threads, 0, st>>>(args, no, rows_per_img,
+                                                                                          pred, total);
+  MDB_CUDA(cudaGetLastError());
+}
+
+}  // namespace mdb

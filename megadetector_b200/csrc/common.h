@@ -1,0 +1,148 @@
+// Host-side shared declarations for libmdb200 (engine internals; the public ABI is include/mdb200.h).
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdio>
+#include <string>
+#include <vector>
+
+namespace mdb {
+
+constexpr int kMaxDetCap = 300;  // nms(max_det=300), pytorch_detector.py:502
+
+struct CudaError {
+  std::string msg;
+};
+
+#define MDB_CUDA(expr)                                                                                    \
+  do {                                                                                                    \
+    cudaError_t _e = (expr);                                                                              \
+    if (_e != cudaSuccess) {                                                                              \
+      char _b[512];                                                                                       \
+      snprintf(_b, sizeof(_b), "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      throw mdb::CudaError{_b};                                                                           \
+    }                                                                                                     \
+  } while (0)
+
+#define MDB_REQUIRE(cond, text)                                                          \
+  do {                                                                                   \
+    if (!(cond)) {                                                                       \
+      char _b[512];                                                                      \
+      snprintf(_b, sizeof(_b), "%s (%s) (%s:%d)", text, #cond, __FILE__, __LINE__);      \
+      throw mdb::CudaError{_b};                                                          \
+    }                                                                                    \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// A channel slice of an NHWC fp16 (or fp32) buffer.
+// ---------------------------------------------------------------------------------------------
+struct View {
+  void* base = nullptr;  // start of the underlying buffer
+  int N = 0, H = 0, W = 0;
+  int Ctot = 0;   // channels of the underlying buffer (pixel stride in elements)
+  int c_off = 0;  // first channel of this view
+  int C = 0;      // channels of this view
+  bool fp32 = false;
+  size_t elem() const { return fp32 ? 4 : 2; }
+  void* ptr() const { return static_cast<char*>(base) + static_cast<size_t>(c_off) * elem(); }
+};
+
+// ---------------------------------------------------------------------------------------------
+// TMA descriptors (tmap.cu)
+// ---------------------------------------------------------------------------------------------
+// 4-D {C, W, H, N} fp16 activation map over a View; par_y/par_x < 0: dense, else the (par_y, par_x)
+// parity sub-lattice of a stride-2 convolution (dims W/2, H/2).  box = {kc, tw, th, 1}.
+void make_act_tmap(CUtensorMap* m, const View& v, int kc, int tw, int th, int par_y, int par_x);
+// flattened variant for 1x1 convolutions: dims {C, N*H*W, 1, 1}, box {kc, 128, 1, 1}
+void make_act_tmap_flat(CUtensorMap* m, const View& v, int kc);
+// 2-D {K, Cout_pad} fp16 weight map, box {kc, bn}
+void make_wgt_tmap(CUtensorMap* m, const void* w, int K, int cout_pad, int kc, int bn);
+
+// ---------------------------------------------------------------------------------------------
+// K2 convolution (conv_host.cu)
+// ---------------------------------------------------------------------------------------------
+struct ConvOp;  // opaque here
+struct ConvDesc {
+  View in, out, res;  // res.base == nullptr: no residual
+  const void* wgt = nullptr;  // device fp16 [cout_pad][k][k][cin]
+  const float* bias = nullptr;  // device fp32 [cout_pad]
+  int cout = 0, cout_pad = 0;
+  int k = 1, s = 1, pad = 0, act = 1;
+};
+ConvOp* conv_build(const ConvDesc& d, int num_sms);
+void conv_launch(ConvOp* op, int n_img, cudaStream_t st);
+void conv_free(ConvOp* op);
+double conv_macs_per_image(const ConvOp* op);
+int conv_pick_bn(int cout_pad);
+
+// weight re-layout helpers (host): PyTorch [co][ci][k][k] fp32 -> [co_pad][k][k][ci_pad] fp16
+void pack_weights_khwc(const float* w, int co, int ci, int k, int co_pad, int ci_pad, std::vector<__half>& out);
+// stem: [co][3][6][6] -> 3x3 conv over the 2x2 space-to-depth input with 16 (12 used) channels
+void pack_weights_stem_s2d(const float* w, int co, int co_pad, std::vector<__half>& out);
+
+// ---------------------------------------------------------------------------------------------
+// K1 letterbox / preprocess (preprocess.cu)
+// ---------------------------------------------------------------------------------------------
+struct LetterboxGeom {
+  int src_h, src_w;
+  int new_w, new_h;  // new_unpad
+  int top, bottom, left, right;
+  int out_h, out_w;
+  double ratio, dw, dh;
+};
+LetterboxGeom letterbox_geometry(int h, int w, int img_size, int stride, bool autopad, bool scaleup);
+// coefficient tables of cv::resize(INTER_LINEAR) for u8: ofs[d], coef[2*d], coef[2*d+1]
+void linear_tables(int ssize, int dsize, bool vertical, std::vector<int32_t>& ofs, std::vector<int16_t>& coef);
+
+struct PreImage {  // one per image, lives in device memory
+  const uint8_t* src;  // device, rows dense or strided
+  long long src_stride;
+  int src_h, src_w;
+  int new_w, new_h, top, left;
+  const int32_t* xofs;
+  const int16_t* xcoef;
+  const int32_t* yofs;
+  const int16_t* ycoef;
+};
+void preprocess_launch(const PreImage* d_imgs, int n, int out_h, int out_w, __half* dst, float max_scale,
+                       cudaStream_t st);
+void preprocess_init_constants();
+
+// ---------------------------------------------------------------------------------------------
+// K3/K4/K5 (aux.cu)
+// ---------------------------------------------------------------------------------------------
+void upsample2x_launch(const View& src, const View& dst, int n_img, cudaStream_t st);
+void sppf_pool_launch(const View& s1, const View& p1, const View& p2, const View& p3, int n_img, cudaStream_t st);
+struct DecodeLevel {
+  const float* raw;  // fp32 [n][ny][nx][c_stride]
+  int ny, nx, c_stride;
+  float stride;
+  float anchors[3][2];
+  int row_off;
+};
+void decode_launch(const DecodeLevel* lv4, int n_img, int no, int rows_per_img, float* pred, cudaStream_t st);
+
+// ---------------------------------------------------------------------------------------------
+// K6-K8 (nms.cu)
+// ---------------------------------------------------------------------------------------------
+struct NmsImageParams {  // scale_coords inputs, one per image (device array); gain == 0: no rescale
+  float gain, pad_x, pad_y, max_x, max_y;
+};
+struct NmsScratch {
+  // per image: candidate arrays of `cap` entries, double-buffered for the radix passes
+  uint32_t* key[2];
+  int32_t* idx[2];
+  int cap;
+};
+size_t nms_scratch_bytes(int n_img, int anchors);
+void nms_bind_scratch(NmsScratch* s, void* mem, int n_img, int anchors);
+void nms_launch(const float* pred, int n_img, int anchors, int no, float conf_thres, float iou_thres_floor,
+                int max_det, const NmsImageParams* d_params, const NmsScratch& scratch, float* det_out,
+                int32_t* det_count, int32_t* kept_anchor, cudaStream_t st);
+// largest float <= t  (the CPU torchvision kernel compares float IoU against a double threshold)
+float float_floor_of_double(double t);
+
+}  // namespace mdb

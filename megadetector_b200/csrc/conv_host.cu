@@ -1,0 +1,196 @@
+// Host side of K2: tile-shape selection, TMA descriptors, launch.
+#include <algorithm>
+#include <cmath>
+
+#include "common.h"
+#include "conv_tcgen05.cuh"
+
+namespace mdb {
+
+struct ConvOp {
+  CUtensorMap tmA[4];
+  CUtensorMap tmB;
+  ConvParams p;
+  int kc = 64;
+  bool flat = false;
+  int HW_out = 0;  // output pixels per image
+  size_t smem = 0;
+  int num_sms = 148;
+  double macs_per_image = 0;
+};
+
+int conv_pick_bn(int cout_pad) {
+  // largest multiple of 16 that divides cout_pad and fits one TMEM accumulator stage (256 columns)
+  for (int bn = 256; bn >= 16; bn -= 16)
+    if (cout_pad % bn == 0) return bn;
+  return 16;
+}
+
+static void pick_tile(int H, int W, int* tw, int* th) {
+  // maximise useful rows per 128-row MMA tile; prefer wide tiles (longer contiguous TMA rows)
+  double best = -1;
+  int bw = 1, bh = 1;
+  for (int w = std::min(W, 128); w >= 1; --w) {
+    int h = std::min(H, 128 / w);
+    if (h < 1) continue;
+    if (w > 256 || h > 256) continue;
+    const long tiles = static_cast<long>((W + w - 1) / w) * ((H + h - 1) / h);
+    const double eff = static_cast<double>(H) * W / (static_cast<double>(tiles) * 128.0);
+    if (eff > best + 1e-9) {
+      best = eff;
+      bw = w;
+      bh = h;
+    }
+  }
+  *tw = bw;
+  *th = bh;
+}
+
+template <int KC>
+static void set_smem_attr(size_t bytes) {
+  static size_t current = 0;
+  if (bytes > current) {
+    MDB_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(bytes)));
+    current = bytes;
+  }
+}
+
+ConvOp* conv_build(const ConvDesc& d, int num_sms) {
+  ConvOp* op = new ConvOp();
+  try {
+    const View& in = d.in;
+    const View& out = d.out;
+    MDB_REQUIRE(in.C % 16 == 0, "conv input channels must be a multiple of 16");
+    MDB_REQUIRE(d.cout_pad % 16 == 0 && d.cout_pad >= d.cout, "bad cout_pad");
+    MDB_REQUIRE(d.s == 1 || d.s == 2, "stride must be 1 or 2");
+    MDB_REQUIRE(out.C >= d.cout, "output view too narrow");
+    const int kc = in.C % 64 == 0 ? 64 : (in.C % 32 == 0 ? 32 : 16);
+    op->kc = kc;
+    op->num_sms = num_sms;
+    ConvParams& p = op->p;
+    const int Ho = (in.H + 2 * d.pad - d.k) / d.s + 1;
+    const int Wo = (in.W + 2 * d.pad - d.k) / d.s + 1;
+    MDB_REQUIRE(Ho == out.H && Wo == out.W && out.N == in.N, "conv output view has the wrong shape");
+    op->HW_out = Ho * Wo;
+    p.H_out = Ho;
+    p.W_out = Wo;
+    op->macs_per_image = static_cast<double>(Ho) * Wo * d.cout * in.C * d.k * d.k;
+    op->flat = (d.k == 1 && d.s == 1 && d.pad == 0);
+
+    p.BN = conv_pick_bn(d.cout_pad);
+    p.n_tiles = d.cout_pad / p.BN;
+    p.Cout = d.cout;
+    p.KH = p.KW = d.k;
+    p.stride = d.s;
+    p.pad = d.pad;
+    p.Cin = in.C;
+    p.chunks = in.C / kc;
+    p.bias = d.bias;
+    p.out = out.base;
+    p.out_pix_stride = out.Ctot;
+    p.out_c_off = out.c_off;
+    p.out_fp32 = out.fp32 ? 1 : 0;
+    p.res = d.res.base ? static_cast<const __half*>(d.res.base) : nullptr;
+    p.res_pix_stride = d.res.Ctot;
+    p.res_c_off = d.res.c_off;
+    p.act = d.act;
+    p.idesc = make_idesc_f16(kTileM, static_cast<uint32_t>(p.BN));
+    if (d.res.base) {
+      MDB_REQUIRE(d.res.H == Ho && d.res.W == Wo && d.res.N == in.N && !d.res.fp32, "residual view mismatch");
+      MDB_REQUIRE(d.res.Ctot % 8 == 0 && d.res.c_off % 8 == 0, "residual view must be 16-byte aligned per pixel");
+    }
+    MDB_REQUIRE(out.fp32 ? (out.Ctot % 4 == 0 && out.c_off % 4 == 0) : (out.Ctot % 8 == 0 && out.c_off % 8 == 0),
+                "output view must be 16-byte aligned per pixel");
+
+    if (op->flat) {
+      p.tw = 128;
+      p.th = 1;
+      make_act_tmap_flat(&op->tmA[0], in, kc);
+      op->tmA[1] = op->tmA[2] = op->tmA[3] = op->tmA[0];
+    } else {
+      pick_tile(Ho, Wo, &p.tw, &p.th);
+      if (d.s == 1) {
+        make_act_tmap(&op->tmA[0], in, kc, p.tw, p.th, -1, -1);
+        op->tmA[1] = op->tmA[2] = op->tmA[3] = op->tmA[0];
+      } else {
+        for (int py = 0; py < 2; ++py)
+          for (int px = 0; px < 2; ++px) make_act_tmap(&op->tmA[py * 2 + px], in, kc, p.tw, p.th, py, px);
+      }
+    }
+    make_wgt_tmap(&op->tmB, d.wgt, d.k * d.k * in.C, d.cout_pad, kc, p.BN);
+
+    const size_t a_bytes = static_cast<size_t>(kTileM) * kc * 2;
+    const size_t b_bytes = (static_cast<size_t>(p.BN) * kc * 2 + 1023) & ~static_cast<size_t>(1023);
+    const size_t stage = a_bytes + b_bytes;
+    const size_t budget = 227 * 1024 - 2048;  // static barriers + alignment slack
+    int stages = static_cast<int>(std::min<size_t>(kConvMaxStages, (budget - 1024) / stage));
+    const int k_iters = d.k * d.k * p.chunks;
+    stages = std::max(2, std::min(stages, std::max(2, k_iters * 2)));
+    p.stages = stages;
+    op->smem = stage * stages + 1024;
+    if (kc == 64) set_smem_attr<64>(op->smem);
+    else if (kc == 32) set_smem_attr<32>(op->smem);
+    else set_smem_attr<16>(op->smem);
+  } catch (...) {
+    delete op;
+    throw;
+  }
+  return op;
+}
+
+void conv_launch(ConvOp* op, int n_img, cudaStream_t st) {
+  ConvParams p = op->p;
+  if (op->flat) {
+    const long long npix = static_cast<long long>(n_img) * op->HW_out;
+    p.n_img = 1;
+    p.H_out = 1;
+    p.W_out = static_cast<int>(npix);
+    p.tiles_x = static_cast<int>((npix + 127) / 128);
+    p.tiles_y = 1;
+  } else {
+    p.n_img = n_img;
+    p.tiles_x = (p.W_out + p.tw - 1) / p.tw;
+    p.tiles_y = (p.H_out + p.th - 1) / p.th;
+  }
+  p.m_tiles = p.n_img * p.tiles_x * p.tiles_y;
+  const long long total = static_cast<long long>(p.m_tiles) * p.n_tiles;
+  const int grid = static_cast<int>(std::min<long long>(total, op->num_sms));
+  if (grid <= 0) return;
+  if (op->kc == 64)
+    conv_igemm_kernel<64><<<grid, kConvThreads, op->smem, st>>>(op->tmA[0], op->tmA[1], op->tmA[2], op->tmA[3], op->tmB, p);
+  else if (op->kc == 32)
+    conv_igemm_kernel<32><<<grid, kConvThreads, op->smem, st>>>(op->tmA[0], op->tmA[1], op->tmA[2], op->tmA[3], op->tmB, p);
+  else
+    conv_igemm_kernel<16><<<grid, kConvThreads, op->smem, st>>>(op->tmA[0], op->tmA[1], op->tmA[2], op->tmA[3], op->tmB, p);
+  MDB_CUDA(cudaGetLastError());
+}
+
+void conv_free(ConvOp* op) { delete op; }
+double conv_macs_per_image(const ConvOp* op) { return op->macs_per_image; }
+
+void pack_weights_khwc(const float* w, int co, int ci, int k, int co_pad, int ci_pad, std::vector<__half>& out) {
+  out.assign(static_cast<size_t>(co_pad) * k * k * ci_pad, __float2half(0.f));
+  for (int o = 0; o < co; ++o)
+    for (int c = 0; c < ci; ++c)
+      for (int y = 0; y < k; ++y)
+        for (int x = 0; x < k; ++x)
+          out[((static_cast<size_t>(o) * k + y) * k + x) * ci_pad + c] =
+              __float2half_rn(w[((static_cast<size_t>(o) * ci + c) * k + y) * k + x]);
+}
+
+void pack_weights_stem_s2d(const float* w, int co, int co_pad, std::vector<__half>& out) {
+  // 6x6 stride-2 pad-2 conv over RGB == 3x3 stride-1 pad-1 conv over the 2x2 space-to-depth image whose
+  // channel is (py*2+px)*3+c:  W'[o][a][b][(py*2+px)*3+c] = W[o][c][2a+py][2b+px]
+  out.assign(static_cast<size_t>(co_pad) * 9 * 16, __float2half(0.f));
+  for (int o = 0; o < co; ++o)
+    for (int c = 0; c < 3; ++c)
+      for (int ky = 0; ky < 6; ++ky)
+        for (int kx = 0; kx < 6; ++kx) {
+          const int a = ky / 2, py = ky % 2, b = kx / 2, px = kx % 2;
+          out[((static_cast<size_t>(o) * 3 + a) * 3 + b) * 16 + (py * 2 + px) * 3 + c] =
+              __float2half_rn(w[((static_cast<size_t>(o) * 3 + c) * 6 + ky) * 6 + kx]);
+        }
+}
+
+}  // namespace mdb

@@ -1,0 +1,946 @@
+// libmdb200 engine: weights, per-shape execution plans (static graph + liveness-packed activation arena),
+// the batch pipeline and the C ABI of include/mdb200.h.
+//
+// Host-side mirror of what `PTDetector` does around the model
+// (megadetector/detection/pytorch_detector.py:745-1424): letterbox geometry, grouping by processed shape
+// (:1226-1233), one forward per group (:1257-1313), nms (:1342), scale_coords + round (:1379).
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/mdb200.h"
+#include "common.h"
+
+using namespace mdb;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct ConvWeights {
+  __half* w = nullptr;  // device [cout_pad][k][k][cin_pad]
+  float* b = nullptr;   // device [cout_pad]
+  int cout = 0, cout_pad = 0, cin = 0, cin_pad = 0, k = 0;
+};
+
+// ------------------------------------------------------------------------------------------
+// graph description with virtual buffers
+// ------------------------------------------------------------------------------------------
+struct VBuf {
+  int H, W, C;
+  bool fp32 = false;
+  int first = 1 << 30, last = -1;
+  size_t offset = 0, bytes = 0;
+};
+struct VView {
+  int buf = -1, c_off = 0, C = 0;
+};
+enum StepKind { STEP_CONV, STEP_UPSAMPLE, STEP_SPPF };
+struct Step {
+  StepKind kind = STEP_CONV;
+  std::string name;
+  VView in, out, res;
+  int cout = 0, k = 1, s = 1, pad = 0, act = 1;
+  ConvOp* op = nullptr;
+};
+
+struct Plan {
+  int H = 0, W = 0, nb = 0;
+  std::vector<VBuf> bufs;
+  std::vector<Step> steps;
+  void* arena = nullptr;
+  size_t arena_bytes = 0;
+  int stem_buf = -1;
+  int raw_buf[4] = {-1, -1, -1, -1};
+  float* pred = nullptr;
+  int anchors = 0;
+  DecodeLevel lv[4];
+  void* nms_mem = nullptr;
+  NmsScratch nms_scratch{};
+  double macs_per_image = 0;
+  ~Plan() {
+    for (auto& s : steps)
+      if (s.op) conv_free(s.op);
+    if (arena) cudaFree(arena);
+    if (pred) cudaFree(pred);
+    if (nms_mem) cudaFree(nms_mem);
+  }
+  View view(const VView& v) const {
+    const VBuf& b = bufs[v.buf];
+    View r;
+    r.base = static_cast<char*>(arena) + b.offset;
+    r.N = nb; r.H = b.H; r.W = b.W; r.Ctot = b.C; r.c_off = v.c_off; r.C = v.C; r.fp32 = b.fp32;
+    return r;
+  }
+};
+
+struct TableKey {
+  int ssize, dsize, vertical;
+  bool operator<(const TableKey& o) const {
+    return std::tie(ssize, dsize, vertical) < std::tie(o.ssize, o.dsize, o.vertical);
+  }
+};
+struct DevTable {
+  int32_t* ofs = nullptr;
+  int16_t* coef = nullptr;
+};
+
+}  // namespace
+
+struct mdb_engine {
+  mdb_config cfg{};
+  int num_sms = 148;
+  cudaStream_t st_compute = nullptr, st_copy = nullptr;
+  cudaEvent_t ev_copy_done[2] = {nullptr, nullptr}, ev_compute_done[2] = {nullptr, nullptr};
+  cudaEvent_t ev_t[4] = {nullptr, nullptr, nullptr, nullptr};
+  std::map<std::string, ConvWeights> weights;
+  bool weights_loaded = false;
+  std::map<std::pair<int, int>, std::unique_ptr<Plan>> plans;
+  std::map<TableKey, DevTable> tables;
+  // staging (double-buffered across chunks)
+  uint8_t* d_src[2] = {nullptr, nullptr};
+  size_t d_src_bytes[2] = {0, 0};
+  PreImage* h_pre[2] = {nullptr, nullptr};  // pinned
+  PreImage* d_pre[2] = {nullptr, nullptr};
+  NmsImageParams* h_nmsp[2] = {nullptr, nullptr};  // pinned
+  NmsImageParams* d_nmsp[2] = {nullptr, nullptr};
+  float* d_det = nullptr;  // [max_batch][max_det][6]
+  int32_t* d_cnt = nullptr;
+  int32_t* d_anchor = nullptr;
+  float* h_det = nullptr;  // pinned mirrors
+  int32_t* h_cnt = nullptr;
+  int32_t* h_anchor = nullptr;
+  // last-run bookkeeping for debug fetch
+  Plan* last_plan = nullptr;
+  int last_n = 0;
+  float last_ms[4] = {0, 0, 0, 0};
+  int64_t launches = 0;
+  std::string err;
+};
+
+namespace {
+
+int fail(mdb_engine* e, int code, const std::string& msg) {
+  if (e) e->err = msg; else g_create_error = msg;
+  return code;
+}
+
+// ------------------------------------------------------------------------------------------
+// graph builder (order == oracle/yolov5.py::conv_specs)
+// ------------------------------------------------------------------------------------------
+struct Builder {
+  Plan& P;
+  const mdb_arch& A;
+  explicit Builder(Plan& p, const mdb_arch& a) : P(p), A(a) {}
+  int newbuf(int H, int W, int C, bool fp32 = false) {
+    VBuf b; b.H = H; b.W = W; b.C = C; b.fp32 = fp32;
+    P.bufs.push_back(b);
+    return static_cast<int>(P.bufs.size()) - 1;
+  }
+  VView whole(int buf) { return VView{buf, 0, P.bufs[buf].C}; }
+  VView slice(int buf, int off, int C) { return VView{buf, off, C}; }
+  void touch(const VView& v) {
+    if (v.buf < 0) return;
+    const int i = static_cast<int>(P.steps.size());
+    P.bufs[v.buf].first = std::min(P.bufs[v.buf].first, i);
+    P.bufs[v.buf].last = std::max(P.bufs[v.buf].last, i);
+  }
+  void conv(const std::string& name, VView in, VView out, int cout, int k, int s, int pad, int act = 1, VView res = VView{}) {
+    Step st; st.kind = STEP_CONV; st.name = name; st.in = in; st.out = out; st.res = res;
+    st.cout = cout; st.k = k; st.s = s; st.pad = pad; st.act = act;
+    touch(in); touch(out); touch(res);
+    P.steps.push_back(st);
+  }
+  void upsample(VView in, VView out) {
+    Step st; st.kind = STEP_UPSAMPLE; st.name = "upsample"; st.in = in; st.out = out;
+    touch(in); touch(out);
+    P.steps.push_back(st);
+  }
+  void sppf(VView cat) {
+    Step st; st.kind = STEP_SPPF; st.name = "sppf_pool"; st.in = cat; st.out = cat;
+    touch(cat);
+    P.steps.push_back(st);
+  }
+  // C3(c1 -> c2, n bottlenecks): returns nothing, writes `out`
+  void c3(int idx, VView in, VView out, int c2, int n, bool shortcut) {
+    const int h = c2 / 2;
+    const VBuf& ib = P.bufs[in.buf];
+    const int H = ib.H, W = ib.W;
+    const std::string pre = "model." + std::to_string(idx);
+    const int cat = newbuf(H, W, 2 * h);
+    int cur = (n == 0) ? -1 : newbuf(H, W, h);
+    VView a = (n == 0) ? slice(cat, 0, h) : whole(cur);
+    conv(pre + ".cv1.conv", in, a, h, 1, 1, 0);
+    conv(pre + ".cv2.conv", in, slice(cat, h, h), h, 1, 1, 0);
+    const int tmp = n > 0 ? newbuf(H, W, h) : -1;
+    for (int j = 0; j < n; ++j) {
+      const std::string m = pre + ".m." + std::to_string(j);
+      conv(m + ".cv1.conv", a, whole(tmp), h, 1, 1, 0);
+      VView nxt = (j == n - 1) ? slice(cat, 0, h) : whole(newbuf(H, W, h));
+      conv(m + ".cv2.conv", whole(tmp), nxt, h, 3, 1, 1, 1, shortcut ? a : VView{});
+      a = nxt;
+    }
+    conv(pre + ".cv3.conv", whole(cat), out, c2, 1, 1, 0);
+  }
+};
+
+void build_graph(Plan& P, const mdb_arch& A) {
+  Builder B(P, A);
+  const int* c = A.ch;
+  const int* nb = A.n_backbone;
+  const int nh = A.n_head;
+  const int H = P.H, W = P.W;
+  auto dim = [&](int s, int* h, int* w) { *h = H / s; *w = W / s; };
+  int h2, w2, h4, w4, h8, w8, h16, w16, h32, w32, h64, w64;
+  dim(2, &h2, &w2); dim(4, &h4, &w4); dim(8, &h8, &w8); dim(16, &h16, &w16); dim(32, &h32, &w32); dim(64, &h64, &w64);
+
+  P.stem_buf = B.newbuf(h2, w2, 16);
+  // concat buffers that several producers write into
+  const int cat22 = B.newbuf(h8, w8, 2 * c[2]);    // [up(x20), x4]
+  const int cat18 = B.newbuf(h16, w16, 2 * c[3]);  // [up(x16), x6]
+  const int cat14 = B.newbuf(h32, w32, 2 * c[4]);  // [up(x12), x8]
+  const int cat25 = B.newbuf(h16, w16, 2 * c[2]);  // [x24, x20]
+  const int cat28 = B.newbuf(h32, w32, 2 * c[3]);  // [x27, x16]
+  const int cat31 = B.newbuf(h64, w64, 2 * c[4]);  // [x30, x12]
+  const int sppf_cat = B.newbuf(h64, w64, 2 * c[5]);  // [s1, p1, p2, p3], each c5/2
+
+  // NB: the stem consumes K1's space-to-depth image: 3x3 / s1 / p1 over 16 channels (see preprocess.cu)
+  const int x0 = B.newbuf(h2, w2, c[0]);
+  B.conv("model.0.conv", B.whole(P.stem_buf), B.whole(x0), c[0], 3, 1, 1);
+  const int x1 = B.newbuf(h4, w4, c[1]);
+  B.conv("model.1.conv", B.whole(x0), B.whole(x1), c[1], 3, 2, 1);
+  const int x2 = B.newbuf(h4, w4, c[1]);
+  B.c3(2, B.whole(x1), B.whole(x2), c[1], nb[0], true);
+  const int x3 = B.newbuf(h8, w8, c[2]);
+  B.conv("model.3.conv", B.whole(x2), B.whole(x3), c[2], 3, 2, 1);
+  B.c3(4, B.whole(x3), B.slice(cat22, c[2], c[2]), c[2], nb[1], true);  // x4
+  const int x5 = B.newbuf(h16, w16, c[3]);
+  B.conv("model.5.conv", B.slice(cat22, c[2], c[2]), B.whole(x5), c[3], 3, 2, 1);
+  B.c3(6, B.whole(x5), B.slice(cat18, c[3], c[3]), c[3], nb[2], true);  // x6
+  const int x7 = B.newbuf(h32, w32, c[4]);
+  B.conv("model.7.conv", B.slice(cat18, c[3], c[3]), B.whole(x7), c[4], 3, 2, 1);
+  B.c3(8, B.whole(x7), B.slice(cat14, c[4], c[4]), c[4], nb[3], true);  // x8
+  const int x9 = B.newbuf(h64, w64, c[5]);
+  B.conv("model.9.conv", B.slice(cat14, c[4], c[4]), B.whole(x9), c[5], 3, 2, 1);
+  const int x10 = B.newbuf(h64, w64, c[5]);
+  B.c3(10, B.whole(x9), B.whole(x10), c[5], nb[4], true);
+  // SPPF
+  const int hs = c[5] / 2;
+  B.conv("model.11.cv1.conv", B.whole(x10), B.slice(sppf_cat, 0, hs), hs, 1, 1, 0);
+  B.sppf(B.whole(sppf_cat));
+  const int x11 = B.newbuf(h64, w64, c[5]);
+  B.conv("model.11.cv2.conv", B.whole(sppf_cat), B.whole(x11), c[5], 1, 1, 0);
+  // head
+  B.conv("model.12.conv", B.whole(x11), B.slice(cat31, c[4], c[4]), c[4], 1, 1, 0);  // x12
+  B.upsample(B.slice(cat31, c[4], c[4]), B.slice(cat14, 0, c[4]));
+  const int x15 = B.newbuf(h32, w32, c[4]);
+  B.c3(15, B.whole(cat14), B.whole(x15), c[4], nh, false);
+  B.conv("model.16.conv", B.whole(x15), B.slice(cat28, c[3], c[3]), c[3], 1, 1, 0);  // x16
+  B.upsample(B.slice(cat28, c[3], c[3]), B.slice(cat18, 0, c[3]));
+  const int x19 = B.newbuf(h16, w16, c[3]);
+  B.c3(19, B.whole(cat18), B.whole(x19), c[3], nh, false);
+  B.conv("model.20.conv", B.whole(x19), B.slice(cat25, c[2], c[2]), c[2], 1, 1, 0);  // x20
+  B.upsample(B.slice(cat25, c[2], c[2]), B.slice(cat22, 0, c[2]));
+  const int x23 = B.newbuf(h8, w8, c[2]);
+  B.c3(23, B.whole(cat22), B.whole(x23), c[2], nh, false);
+  B.conv("model.24.conv", B.whole(x23), B.slice(cat25, 0, c[2]), c[2], 3, 2, 1);  // x24
+  const int x26 = B.newbuf(h16, w16, c[3]);
+  B.c3(26, B.whole(cat25), B.whole(x26), c[3], nh, false);
+  B.conv("model.27.conv", B.whole(x26), B.slice(cat28, 0, c[3]), c[3], 3, 2, 1);  // x27
+  const int x29 = B.newbuf(h32, w32, c[4]);
+  B.c3(29, B.whole(cat28), B.whole(x29), c[4], nh, false);
+  B.conv("model.30.conv", B.whole(x29), B.slice(cat31, 0, c[4]), c[4], 3, 2, 1);  // x30
+  const int x32 = B.newbuf(h64, w64, c[5]);
+  B.c3(32, B.whole(cat31), B.whole(x32), c[5], nh, false);
+  // Detect heads: fp32 raw outputs, decoded by K5
+  const int no = A.nc + 5;
+  const int feats[4] = {x23, x26, x29, x32};
+  const int fh[4] = {h8, h16, h32, h64}, fw[4] = {w8, w16, w32, w64};
+  for (int l = 0; l < 4; ++l) {
+    const int craw = ((3 * no + 3) / 4) * 4;
+    P.raw_buf[l] = B.newbuf(fh[l], fw[l], craw, true);
+    B.conv("model.33.m." + std::to_string(l), B.whole(feats[l]), B.slice(P.raw_buf[l], 0, 3 * no), 3 * no, 1, 1, 0, 0);
+  }
+  // keep the stem input and the raw heads alive to the end (debug fetch / decode)
+  const int last = static_cast<int>(P.steps.size());
+  P.bufs[P.stem_buf].first = 0;
+  P.bufs[P.stem_buf].last = std::max(P.bufs[P.stem_buf].last, 0);
+  for (int l = 0; l < 4; ++l) P.bufs[P.raw_buf[l]].last = last;
+}
+
+void assign_offsets(Plan& P, bool reuse) {
+  const int n = static_cast<int>(P.bufs.size());
+  std::vector<int> order(n);
+  for (int i = 0; i < n; ++i) {
+    order[i] = i;
+    VBuf& b = P.bufs[i];
+    b.bytes = ((static_cast<size_t>(P.nb) * b.H * b.W * b.C * (b.fp32 ? 4 : 2) + 1023) / 1024) * 1024 + 1024;
+  }
+  std::sort(order.begin(), order.end(), [&](int a, int b) {
+    if (P.bufs[a].bytes != P.bufs[b].bytes) return P.bufs[a].bytes > P.bufs[b].bytes;
+    return a < b;
+  });
+  std::vector<int> placed;
+  size_t total = 0;
+  for (int id : order) {
+    VBuf& b = P.bufs[id];
+    if (b.last < 0) { b.offset = 0; continue; }  // never used
+    size_t off = 0;
+    if (reuse) {
+      // lowest offset that does not collide with any lifetime-overlapping, already placed buffer
+      bool moved = true;
+      while (moved) {
+        moved = false;
+        for (int q : placed) {
+          const VBuf& o = P.bufs[q];
+          const bool life = !(o.last < b.first || b.last < o.first);
+          const bool addr = !(o.offset + o.bytes <= off || off + b.bytes <= o.offset);
+          if (life && addr) { off = o.offset + o.bytes; moved = true; }
+        }
+      }
+    } else {
+      off = total;
+    }
+    b.offset = off;
+    total = std::max(total, off + b.bytes);
+    placed.push_back(id);
+  }
+  P.arena_bytes = total;
+}
+
+Plan* get_plan(mdb_engine* e, int H, int W) {
+  auto key = std::make_pair(H, W);
+  auto it = e->plans.find(key);
+  if (it != e->plans.end()) return it->second.get();
+  MDB_REQUIRE(e->weights_loaded, "mdb_load_weights must be called before inference");
+  MDB_REQUIRE(H % 64 == 0 && W % 64 == 0 && H >= 64 && W >= 64, "letterboxed shape must be a multiple of 64");
+  std::unique_ptr<Plan> P(new Plan());
+  P->H = H; P->W = W; P->nb = e->cfg.max_batch;
+  build_graph(*P, e->cfg.arch);
+  assign_offsets(*P, true);
+  MDB_CUDA(cudaMalloc(&P->arena, P->arena_bytes));
+  MDB_CUDA(cudaMemsetAsync(P->arena, 0, P->arena_bytes, e->st_compute));
+  const int no = e->cfg.arch.nc + 5;
+  // conv ops
+  for (auto& s : P->steps) {
+    if (s.kind != STEP_CONV) continue;
+    auto wi = e->weights.find(s.name);
+    MDB_REQUIRE(wi != e->weights.end(), ("missing weights for " + s.name).c_str());
+    const ConvWeights& cw = wi->second;
+    ConvDesc d;
+    d.in = P->view(s.in);
+    d.out = P->view(s.out);
+    if (s.res.buf >= 0) d.res = P->view(s.res);
+    d.wgt = cw.w; d.bias = cw.b; d.cout = cw.cout; d.cout_pad = cw.cout_pad;
+    d.k = s.k; d.s = s.s; d.pad = s.pad; d.act = s.act;
+    MDB_REQUIRE(cw.cin_pad == d.in.C && cw.k == s.k && cw.cout == s.cout, ("weight shape mismatch for " + s.name).c_str());
+    s.op = conv_build(d, e->num_sms);
+    P->macs_per_image += conv_macs_per_image(s.op);
+  }
+  // decode levels + pred
+  int off = 0;
+  const float strides[4] = {8.f, 16.f, 32.f, 64.f};
+  for (int l = 0; l < 4; ++l) {
+    const VBuf& b = P->bufs[P->raw_buf[l]];
+    DecodeLevel& L = P->lv[l];
+    L.raw = reinterpret_cast<const float*>(static_cast<char*>(P->arena) + b.offset);
+    L.ny = b.H; L.nx = b.W; L.c_stride = b.C; L.stride = strides[l]; L.row_off = off;
+    for (int a = 0; a < 3; ++a) { L.anchors[a][0] = e->cfg.arch.anchors_px[l][a][0]; L.anchors[a][1] = e->cfg.arch.anchors_px[l][a][1]; }
+    off += 3 * b.H * b.W;
+  }
+  P->anchors = off;
+  MDB_CUDA(cudaMalloc(&P->pred, static_cast<size_t>(P->nb) * P->anchors * no * sizeof(float)));
+  MDB_CUDA(cudaMalloc(&P->nms_mem, nms_scratch_bytes(P->nb, P->anchors)));
+  nms_bind_scratch(&P->nms_scratch, P->nms_mem, P->nb, P->anchors);
+  Plan* raw = P.get();
+  e->plans[key] = std::move(P);
+  return raw;
+}
+
+void run_network(mdb_engine* e, Plan* P, int n, cudaStream_t st) {
+  for (auto& s : P->steps) {
+    switch (s.kind) {
+      case STEP_CONV: conv_launch(s.op, n, st); break;
+      case STEP_UPSAMPLE: upsample2x_launch(P->view(s.in), P->view(s.out), n, st); break;
+      case STEP_SPPF: {
+        const VBuf& b = P->bufs[s.in.buf];
+        const int hs = b.C / 4;
+        View cat = P->view(s.in);
+        View s1 = cat, p1 = cat, p2 = cat, p3 = cat;
+        s1.c_off = 0; p1.c_off = hs; p2.c_off = 2 * hs; p3.c_off = 3 * hs;
+        s1.C = p1.C = p2.C = p3.C = hs;
+        sppf_pool_launch(s1, p1, p2, p3, n, st);
+        break;
+      }
+    }
+    e->launches++;
+  }
+}
+
+const DevTable& get_table(mdb_engine* e, int ssize, int dsize, bool vertical) {
+  TableKey k{ssize, dsize, vertical ? 1 : 0};
+  auto it = e->tables.find(k);
+  if (it != e->tables.end()) return it->second;
+  std::vector<int32_t> ofs;
+  std::vector<int16_t> coef;
+  linear_tables(ssize, dsize, vertical, ofs, coef);
+  DevTable t;
+  MDB_CUDA(cudaMalloc(&t.ofs, ofs.size() * sizeof(int32_t)));
+  MDB_CUDA(cudaMalloc(&t.coef, coef.size() * sizeof(int16_t)));
+  // tables are tiny and built once per (size pair): a synchronous copy keeps lifetime handling trivial
+  MDB_CUDA(cudaMemcpy(t.ofs, ofs.data(), ofs.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+  MDB_CUDA(cudaMemcpy(t.coef, coef.data(), coef.size() * sizeof(int16_t), cudaMemcpyHostToDevice));
+  return e->tables.emplace(k, t).first->second;
+}
+
+void ensure_src(mdb_engine* e, int slot, size_t bytes) {
+  if (e->d_src_bytes[slot] >= bytes) return;
+  if (e->d_src[slot]) MDB_CUDA(cudaFree(e->d_src[slot]));
+  e->d_src[slot] = nullptr;
+  const size_t want = bytes + bytes / 4 + 4096;
+  MDB_CUDA(cudaMalloc(&e->d_src[slot], want));
+  e->d_src_bytes[slot] = want;
+}
+
+struct ImgIn {
+  const uint8_t* ptr;
+  int h, w;
+  long long stride;
+  int src_h, src_w;  // original size for scale_coords
+  int index;         // position in the caller's arrays
+};
+
+// One chunk (<= max_batch images of one letterboxed shape): H2D on the copy stream, everything else on
+// the compute stream; two staging slots so that the copy of chunk i+1 overlaps the compute of chunk i.
+void run_chunk(mdb_engine* e, Plan* P, const std::vector<ImgIn>& imgs, const std::vector<LetterboxGeom>& geoms,
+               bool preprocessed, float conf_thres, int slot, float* det_out, int32_t* det_count,
+               int32_t* kept_anchor, bool record_timing) {
+  const int n = static_cast<int>(imgs.size());
+  const int max_det = e->cfg.max_det;
+  // ---- stage sources ----
+  size_t total = 0;
+  std::vector<size_t> offs(n);
+  for (int i = 0; i < n; ++i) {
+    offs[i] = total;
+    total += ((static_cast<size_t>(imgs[i].h) * imgs[i].w * 3 + 255) / 256) * 256;
+  }
+  // the previous user of this slot must be done with its staging buffers before we overwrite them
+  MDB_CUDA(cudaEventSynchronize(e->ev_compute_done[slot]));
+  ensure_src(e, slot, total + 64);
+  float max_scale = 1.0f;
+  for (int i = 0; i < n; ++i) {
+    const ImgIn& im = imgs[i];
+    uint8_t* d = e->d_src[slot] + offs[i];
+    const size_t row = static_cast<size_t>(im.w) * 3;
+    if (im.stride == static_cast<long long>(row)) {
+      MDB_CUDA(cudaMemcpyAsync(d, im.ptr, row * im.h, cudaMemcpyHostToDevice, e->st_copy));
+    } else {
+      MDB_CUDA(cudaMemcpy2DAsync(d, row, im.ptr, static_cast<size_t>(im.stride), row, im.h, cudaMemcpyHostToDevice,
+                                 e->st_copy));
+    }
+    const LetterboxGeom& g = geoms[i];
+    PreImage& pi = e->h_pre[slot][i];
+    pi.src = d; pi.src_stride = static_cast<long long>(row); pi.src_h = im.h; pi.src_w = im.w;
+    pi.new_w = g.new_w; pi.new_h = g.new_h; pi.top = g.top; pi.left = g.left;
+    const DevTable& tx = get_table(e, im.w, g.new_w, false);
+    const DevTable& ty = get_table(e, im.h, g.new_h, true);
+    pi.xofs = tx.ofs; pi.xcoef = tx.coef; pi.yofs = ty.ofs; pi.ycoef = ty.coef;
+    max_scale = std::max(max_scale, std::max(static_cast<float>(im.w) / g.new_w, static_cast<float>(im.h) / g.new_h));
+    // scale_coords(img1_shape=(H,W), coords, img0_shape) -- yolov5 utils.general, ratio_pad=None ("classic")
+    NmsImageParams& np = e->h_nmsp[slot][i];
+    const double gain = std::min(static_cast<double>(P->H) / im.src_h, static_cast<double>(P->W) / im.src_w);
+    const double padx = (P->W - im.src_w * gain) / 2, pady = (P->H - im.src_h * gain) / 2;
+    np.gain = static_cast<float>(gain); np.pad_x = static_cast<float>(padx); np.pad_y = static_cast<float>(pady);
+    np.max_x = static_cast<float>(im.src_w); np.max_y = static_cast<float>(im.src_h);
+  }
+  (void)preprocessed;
+  MDB_CUDA(cudaMemcpyAsync(e->d_pre[slot], e->h_pre[slot], sizeof(PreImage) * n, cudaMemcpyHostToDevice, e->st_copy));
+  MDB_CUDA(cudaMemcpyAsync(e->d_nmsp[slot], e->h_nmsp[slot], sizeof(NmsImageParams) * n, cudaMemcpyHostToDevice, e->st_copy));
+  MDB_CUDA(cudaEventRecord(e->ev_copy_done[slot], e->st_copy));
+
+  // ---- compute ----
+  cudaStream_t st = e->st_compute;
+  if (record_timing) MDB_CUDA(cudaEventRecord(e->ev_t[0], st));
+  MDB_CUDA(cudaStreamWaitEvent(st, e->ev_copy_done[slot], 0));
+  View stem = P->view(VView{P->stem_buf, 0, 16});
+  preprocess_launch(e->d_pre[slot], n, P->H, P->W, static_cast<__half*>(stem.base), max_scale, st);
+  e->launches++;
+  if (record_timing) MDB_CUDA(cudaEventRecord(e->ev_t[1], st));
+  run_network(e, P, n, st);
+  if (record_timing) MDB_CUDA(cudaEventRecord(e->ev_t[2], st));
+  const int no = e->cfg.arch.nc + 5;
+  decode_launch(P->lv, n, no, P->anchors, P->pred, st);
+  nms_launch(P->pred, n, P->anchors, no, conf_thres, float_floor_of_double(static_cast<double>(e->cfg.iou_thres)),
+             max_det, e->d_nmsp[slot], P->nms_scratch, e->d_det, e->d_cnt, e->d_anchor, st);
+  e->launches += 2;
+  MDB_CUDA(cudaMemcpyAsync(e->h_det, e->d_det, sizeof(float) * n * max_det * 6, cudaMemcpyDeviceToHost, st));
+  MDB_CUDA(cudaMemcpyAsync(e->h_cnt, e->d_cnt, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
+  MDB_CUDA(cudaMemcpyAsync(e->h_anchor, e->d_anchor, sizeof(int32_t) * n * max_det, cudaMemcpyDeviceToHost, st));
+  if (record_timing) MDB_CUDA(cudaEventRecord(e->ev_t[3], st));
+  MDB_CUDA(cudaEventRecord(e->ev_compute_done[slot], st));
+  // results of this chunk are consumed before the next chunk reuses the pinned mirrors
+  MDB_CUDA(cudaStreamSynchronize(st));
+  for (int i = 0; i < n; ++i) {
+    const int dst = imgs[i].index;
+    det_count[dst] = e->h_cnt[i];
+    memcpy(det_out + static_cast<size_t>(dst) * max_det * 6, e->h_det + static_cast<size_t>(i) * max_det * 6,
+           sizeof(float) * max_det * 6);
+    if (kept_anchor)
+      memcpy(kept_anchor + static_cast<size_t>(dst) * max_det, e->h_anchor + static_cast<size_t>(i) * max_det,
+             sizeof(int32_t) * max_det);
+  }
+  if (record_timing) {
+    float a = 0, b = 0, c = 0, d = 0;
+    cudaEventElapsedTime(&a, e->ev_t[0], e->ev_t[1]);
+    cudaEventElapsedTime(&b, e->ev_t[1], e->ev_t[2]);
+    cudaEventElapsedTime(&c, e->ev_t[2], e->ev_t[3]);
+    cudaEventElapsedTime(&d, e->ev_t[0], e->ev_t[3]);
+    e->last_ms[0] += a; e->last_ms[1] += b; e->last_ms[2] += c; e->last_ms[3] += d;
+  }
+  e->last_plan = P;
+  e->last_n = n;
+}
+
+int infer_common(mdb_engine* e, std::vector<ImgIn>& all, bool preprocessed, float conf_thres, float* det_out,
+                 int32_t* det_count, int32_t* kept_anchor, int32_t* status, int n) {
+  const mdb_config& cfg = e->cfg;
+  memset(e->last_ms, 0, sizeof(e->last_ms));
+  // group by letterboxed shape, keeping input order inside a group (pytorch_detector.py:1226-1233)
+  std::map<std::pair<int, int>, std::vector<int>> groups;
+  std::vector<LetterboxGeom> geom(all.size());
+  for (size_t i = 0; i < all.size(); ++i) {
+    ImgIn& im = all[i];
+    if (im.ptr == nullptr || im.h <= 0 || im.w <= 0) { status[im.index] = MDB_IMG_BAD_INPUT; det_count[im.index] = 0; continue; }
+    LetterboxGeom g;
+    if (preprocessed) {
+      g = LetterboxGeom{}; g.src_h = im.h; g.src_w = im.w; g.new_w = im.w; g.new_h = im.h; g.out_h = im.h; g.out_w = im.w;
+    } else {
+      g = letterbox_geometry(im.h, im.w, cfg.img_size, cfg.stride, cfg.letterbox_auto != 0, cfg.letterbox_scaleup != 0);
+    }
+    if (g.out_h % 64 != 0 || g.out_w % 64 != 0 || g.new_w < 1 || g.new_h < 1) {
+      status[im.index] = MDB_IMG_INFER_FAILED; det_count[im.index] = 0; continue;
+    }
+    geom[i] = g;
+    groups[std::make_pair(g.out_h, g.out_w)].push_back(static_cast<int>(i));
+    status[im.index] = MDB_IMG_OK;
+  }
+  int slot = 0;
+  for (auto& kv : groups) {
+    Plan* P = nullptr;
+    try {
+      P = get_plan(e, kv.first.first, kv.first.second);
+      const std::vector<int>& ids = kv.second;
+      for (size_t b = 0; b < ids.size(); b += cfg.max_batch) {
+        std::vector<ImgIn> chunk;
+        std::vector<LetterboxGeom> cg;
+        for (size_t j = b; j < std::min(ids.size(), b + static_cast<size_t>(cfg.max_batch)); ++j) {
+          chunk.push_back(all[ids[j]]);
+          cg.push_back(geom[ids[j]]);
+        }
+        run_chunk(e, P, chunk, cg, preprocessed, conf_thres, slot, det_out, det_count, kept_anchor, true);
+        slot ^= 1;
+      }
+    } catch (const CudaError& ex) {
+      // a whole shape group fails together (pytorch_detector.py:1236-1249)
+      e->err = ex.msg;
+      for (int id : kv.second) { status[all[id].index] = MDB_IMG_INFER_FAILED; det_count[all[id].index] = 0; }
+      cudaError_t sticky = cudaGetLastError();
+      if (sticky != cudaSuccess && cudaDeviceSynchronize() != cudaSuccess) return MDB_ERR_CUDA;
+    }
+  }
+  (void)n;
+  return MDB_OK;
+}
+
+}  // namespace
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+extern "C" {
+
+const char* mdb_version(void) { return "mdb200 0.1 (sm_100a)"; }
+
+const char* mdb_last_error(const mdb_engine* e) { return e ? e->err.c_str() : g_create_error.c_str(); }
+
+int mdb_letterbox_geometry(const mdb_config* cfg, int32_t h, int32_t w, int32_t* out8, double* ratio_pad3) {
+  if (!cfg || !out8 || h <= 0 || w <= 0) return MDB_ERR_ARG;
+  const LetterboxGeom g = letterbox_geometry(h, w, cfg->img_size, cfg->stride, cfg->letterbox_auto != 0, cfg->letterbox_scaleup != 0);
+  out8[0] = g.new_w; out8[1] = g.new_h; out8[2] = g.top; out8[3] = g.bottom; out8[4] = g.left; out8[5] = g.right;
+  out8[6] = g.out_h; out8[7] = g.out_w;
+  if (ratio_pad3) { ratio_pad3[0] = g.ratio; ratio_pad3[1] = g.dw; ratio_pad3[2] = g.dh; }
+  return MDB_OK;
+}
+
+void* mdb_alloc_pinned(size_t bytes) {
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  return p;
+}
+void mdb_free_pinned(void* p) { if (p) cudaFreeHost(p); }
+
+int mdb_create(mdb_engine** out, const mdb_config* cfg) {
+  if (!out || !cfg) return fail(nullptr, MDB_ERR_ARG, "null argument");
+  *out = nullptr;
+  if (cfg->struct_size != static_cast<int32_t>(sizeof(mdb_config))) return fail(nullptr, MDB_ERR_ARG, "mdb_config size mismatch");
+  if (cfg->max_batch < 1 || cfg->max_det < 1 || cfg->max_det > kMaxDetCap) return fail(nullptr, MDB_ERR_ARG, "bad max_batch / max_det");
+  // every conv needs C_in % 16 == 0; C3 hidden width is ch/2 for ch[1..5]
+  if (cfg->arch.ch[0] < 16 || cfg->arch.ch[0] % 16 != 0) return fail(nullptr, MDB_ERR_ARG, "arch.ch[0] must be a multiple of 16");
+  for (int i = 1; i < 6; ++i)
+    if (cfg->arch.ch[i] < 32 || cfg->arch.ch[i] % 32 != 0) return fail(nullptr, MDB_ERR_ARG, "arch.ch[1..5] must be multiples of 32");
+  if (cfg->arch.nc < 1 || cfg->arch.nc > 251) return fail(nullptr, MDB_ERR_ARG, "arch.nc out of range");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+    cudaGetLastError();
+    return fail(nullptr, MDB_ERR_CUDA, "no CUDA device: libmdb200 has no CPU fallback");
+  }
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, MDB_ERR_ARG, "device ordinal out of range");
+  mdb_engine* e = new mdb_engine();
+  try {
+    e->cfg = *cfg;
+    MDB_CUDA(cudaSetDevice(cfg->device));
+    cudaDeviceProp prop;
+    MDB_CUDA(cudaGetDeviceProperties(&prop, cfg->device));
+    MDB_REQUIRE(prop.major == 10, "libmdb200 is built for sm_100a (B200) only");
+    e->num_sms = prop.multiProcessorCount;
+    MDB_CUDA(cudaStreamCreateWithFlags(&e->st_compute, cudaStreamNonBlocking));
+    MDB_CUDA(cudaStreamCreateWithFlags(&e->st_copy, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      MDB_CUDA(cudaEventCreateWithFlags(&e->ev_copy_done[i], cudaEventDisableTiming));
+      MDB_CUDA(cudaEventCreateWithFlags(&e->ev_compute_done[i], cudaEventDisableTiming));
+      MDB_CUDA(cudaEventRecord(e->ev_compute_done[i], e->st_compute));
+      MDB_CUDA(cudaHostAlloc(&e->h_pre[i], sizeof(PreImage) * cfg->max_batch, cudaHostAllocDefault));
+      MDB_CUDA(cudaMalloc(&e->d_pre[i], sizeof(PreImage) * cfg->max_batch));
+      MDB_CUDA(cudaHostAlloc(&e->h_nmsp[i], sizeof(NmsImageParams) * cfg->max_batch, cudaHostAllocDefault));
+      MDB_CUDA(cudaMalloc(&e->d_nmsp[i], sizeof(NmsImageParams) * cfg->max_batch));
+    }
+    for (int i = 0; i < 4; ++i) MDB_CUDA(cudaEventCreate(&e->ev_t[i]));
+    const size_t nd = static_cast<size_t>(cfg->max_batch) * cfg->max_det;
+    MDB_CUDA(cudaMalloc(&e->d_det, nd * 6 * sizeof(float)));
+    MDB_CUDA(cudaMalloc(&e->d_cnt, cfg->max_batch * sizeof(int32_t)));
+    MDB_CUDA(cudaMalloc(&e->d_anchor, nd * sizeof(int32_t)));
+    MDB_CUDA(cudaHostAlloc(&e->h_det, nd * 6 * sizeof(float), cudaHostAllocDefault));
+    MDB_CUDA(cudaHostAlloc(&e->h_cnt, cfg->max_batch * sizeof(int32_t), cudaHostAllocDefault));
+    MDB_CUDA(cudaHostAlloc(&e->h_anchor, nd * sizeof(int32_t), cudaHostAllocDefault));
+    preprocess_init_constants();
+  } catch (const CudaError& ex) {
+    g_create_error = ex.msg;
+    mdb_destroy(e);
+    return MDB_ERR_CUDA;
+  }
+  *out = e;
+  return MDB_OK;
+}
+
+void mdb_destroy(mdb_engine* e) {
+  if (!e) return;
+  cudaSetDevice(e->cfg.device);
+  cudaDeviceSynchronize();
+  e->plans.clear();
+  for (auto& kv : e->weights) { cudaFree(kv.second.w); cudaFree(kv.second.b); }
+  for (auto& kv : e->tables) { cudaFree(kv.second.ofs); cudaFree(kv.second.coef); }
+  for (int i = 0; i < 2; ++i) {
+    if (e->d_src[i]) cudaFree(e->d_src[i]);
+    if (e->h_pre[i]) cudaFreeHost(e->h_pre[i]);
+    if (e->d_pre[i]) cudaFree(e->d_pre[i]);
+    if (e->h_nmsp[i]) cudaFreeHost(e->h_nmsp[i]);
+    if (e->d_nmsp[i]) cudaFree(e->d_nmsp[i]);
+    if (e->ev_copy_done[i]) cudaEventDestroy(e->ev_copy_done[i]);
+    if (e->ev_compute_done[i]) cudaEventDestroy(e->ev_compute_done[i]);
+  }
+  for (int i = 0; i < 4; ++i) if (e->ev_t[i]) cudaEventDestroy(e->ev_t[i]);
+  cudaFree(e->d_det); cudaFree(e->d_cnt); cudaFree(e->d_anchor);
+  if (e->h_det) cudaFreeHost(e->h_det);
+  if (e->h_cnt) cudaFreeHost(e->h_cnt);
+  if (e->h_anchor) cudaFreeHost(e->h_anchor);
+  if (e->st_compute) cudaStreamDestroy(e->st_compute);
+  if (e->st_copy) cudaStreamDestroy(e->st_copy);
+  delete e;
+}
+
+int mdb_load_weights(mdb_engine* e, const mdb_tensor_desc* tensors, int32_t n) {
+  if (!e || !tensors || n <= 0) return fail(e, MDB_ERR_ARG, "null argument");
+  try {
+    MDB_CUDA(cudaSetDevice(e->cfg.device));
+    std::map<std::string, const mdb_tensor_desc*> byname;
+    for (int i = 0; i < n; ++i) byname[tensors[i].name] = &tensors[i];
+    for (auto& kv : byname) {
+      const std::string& nm = kv.first;
+      const std::string suffix = ".weight";
+      if (nm.size() <= suffix.size() || nm.compare(nm.size() - suffix.size(), suffix.size(), suffix) != 0) continue;
+      const std::string base = nm.substr(0, nm.size() - suffix.size());
+      const mdb_tensor_desc* tw = kv.second;
+      auto bi = byname.find(base + ".bias");
+      MDB_REQUIRE(bi != byname.end(), ("missing bias for " + base).c_str());
+      MDB_REQUIRE(tw->ndim == 4 && tw->shape[2] == tw->shape[3], "conv weight must be [co][ci][k][k]");
+      const int co = static_cast<int>(tw->shape[0]), ci = static_cast<int>(tw->shape[1]), k = static_cast<int>(tw->shape[2]);
+      MDB_REQUIRE(bi->second->ndim == 1 && bi->second->shape[0] == co, "bias shape mismatch");
+      ConvWeights cw;
+      cw.cout = co;
+      cw.cout_pad = ((co + 15) / 16) * 16;
+      std::vector<__half> packed;
+      if (base == "model.0.conv") {
+        MDB_REQUIRE(ci == 3 && k == 6, "stem must be a 6x6 conv over 3 channels");
+        pack_weights_stem_s2d(tw->data, co, cw.cout_pad, packed);
+        cw.cin = 12; cw.cin_pad = 16; cw.k = 3;
+      } else {
+        MDB_REQUIRE(ci % 16 == 0, "conv input channels must be a multiple of 16");
+        pack_weights_khwc(tw->data, co, ci, k, cw.cout_pad, ci, packed);
+        cw.cin = ci; cw.cin_pad = ci; cw.k = k;
+      }
+      std::vector<float> bias(cw.cout_pad, 0.f);
+      memcpy(bias.data(), bi->second->data, sizeof(float) * co);
+      auto old = e->weights.find(base);
+      if (old != e->weights.end()) { cudaFree(old->second.w); cudaFree(old->second.b); }
+      MDB_CUDA(cudaMalloc(&cw.w, packed.size() * sizeof(__half) + 256));
+      MDB_CUDA(cudaMalloc(&cw.b, bias.size() * sizeof(float)));
+      MDB_CUDA(cudaMemcpy(cw.w, packed.data(), packed.size() * sizeof(__half), cudaMemcpyHostToDevice));
+      MDB_CUDA(cudaMemcpy(cw.b, bias.data(), bias.size() * sizeof(float), cudaMemcpyHostToDevice));
+      e->weights[base] = cw;
+    }
+    e->plans.clear();  // plans hold weight pointers
+    e->last_plan = nullptr;
+    e->weights_loaded = true;
+  } catch (const CudaError& ex) {
+    return fail(e, MDB_ERR_CUDA, ex.msg);
+  }
+  return MDB_OK;
+}
+
+int mdb_infer_batch(mdb_engine* e, const uint8_t* const* rgb_hwc, const int32_t* h, const int32_t* w,
+                    const int64_t* row_stride, int32_t n, float conf_thres, float* det_out, int32_t* det_count,
+                    int32_t* kept_anchor, int32_t* status) {
+  if (!e || !rgb_hwc || !h || !w || !det_out || !det_count || !status || n < 0) return fail(e, MDB_ERR_ARG, "null argument");
+  try {
+    MDB_CUDA(cudaSetDevice(e->cfg.device));
+    std::vector<ImgIn> all(n);
+    for (int i = 0; i < n; ++i)
+      all[i] = ImgIn{rgb_hwc[i], h[i], w[i], row_stride ? row_stride[i] : static_cast<long long>(w[i]) * 3, h[i], w[i], i};
+    return infer_common(e, all, false, conf_thres, det_out, det_count, kept_anchor, status, n);
+  } catch (const CudaError& ex) {
+    return fail(e, MDB_ERR_CUDA, ex.msg);
+  }
+}
+
+int mdb_infer_preprocessed(mdb_engine* e, const uint8_t* const* lb_hwc, const int32_t* lh, const int32_t* lw,
+                           const int32_t* src_h, const int32_t* src_w, int32_t n, float conf_thres, float* det_out,
+                           int32_t* det_count, int32_t* kept_anchor, int32_t* status) {
+  if (!e || !lb_hwc || !lh || !lw || !src_h || !src_w || !det_out || !det_count || !status || n < 0)
+    return fail(e, MDB_ERR_ARG, "null argument");
+  try {
+    MDB_CUDA(cudaSetDevice(e->cfg.device));
+    std::vector<ImgIn> all(n);
+    for (int i = 0; i < n; ++i)
+      all[i] = ImgIn{lb_hwc[i], lh[i], lw[i], static_cast<long long>(lw[i]) * 3, src_h[i], src_w[i], i};
+    return infer_common(e, all, true, conf_thres, det_out, det_count, kept_anchor, status, n);
+  } catch (const CudaError& ex) {
+    return fail(e, MDB_ERR_CUDA, ex.msg);
+  }
+}
+
+int mdb_last_timing(mdb_engine* e, float* ms4) {
+  if (!e || !ms4) return MDB_ERR_ARG;
+  memcpy(ms4, e->last_ms, sizeof(float) * 4);
+  return MDB_OK;
+}
+
+int64_t mdb_launch_count(const mdb_engine* e) { return e ? e->launches : 0; }
+
+int mdb_debug_fetch(mdb_engine* e, int32_t what, int32_t index, void* host_dst, size_t bytes, int64_t* shape4) {
+  if (!e) return MDB_ERR_ARG;
+  if (!e->last_plan) return fail(e, MDB_ERR_STATE, "no batch has been run yet");
+  try {
+    MDB_CUDA(cudaSetDevice(e->cfg.device));
+    Plan* P = e->last_plan;
+    const int n = e->last_n;
+    const void* src = nullptr;
+    size_t need = 0;
+    int64_t shp[4] = {0, 0, 0, 0};
+    if (what == MDB_FETCH_STEM_INPUT) {
+      View v = P->view(VView{P->stem_buf, 0, 16});
+      src = v.base; shp[0] = n; shp[1] = v.H; shp[2] = v.W; shp[3] = 16;
+      need = static_cast<size_t>(n) * v.H * v.W * 16 * 2;
+    } else if (what == MDB_FETCH_PRED) {
+      const int no = e->cfg.arch.nc + 5;
+      src = P->pred; shp[0] = n; shp[1] = P->anchors; shp[2] = no; shp[3] = 1;
+      need = static_cast<size_t>(n) * P->anchors * no * 4;
+    } else if (what == MDB_FETCH_LAYER) {
+      int ci = -1;
+      const Step* st = nullptr;
+      for (auto& s : P->steps) {
+        if (s.kind != STEP_CONV) continue;
+        if (++ci == index) { st = &s; break; }
+      }
+      MDB_REQUIRE(st != nullptr, "layer index out of range");
+      const VBuf& b = P->bufs[st->out.buf];
+      // NB: returns the whole underlying buffer (all channels); valid only while its arena slot has not been
+      // reused by a later layer -- the caller passes c_off/C through shape: {n*H*W, Ctot, c_off, C}
+      src = static_cast<char*>(P->arena) + b.offset;
+      shp[0] = static_cast<int64_t>(n) * b.H * b.W; shp[1] = b.C; shp[2] = st->out.c_off; shp[3] = st->out.C;
+      need = static_cast<size_t>(n) * b.H * b.W * b.C * (b.fp32 ? 4 : 2);
+    } else {
+      return fail(e, MDB_ERR_ARG, "unknown fetch kind");
+    }
+    if (shape4) memcpy(shape4, shp, sizeof(shp));
+    if (host_dst) {
+      if (bytes < need) return fail(e, MDB_ERR_ARG, "destination too small");
+      MDB_CUDA(cudaStreamSynchronize(e->st_compute));
+      MDB_CUDA(cudaMemcpy(host_dst, src, need, cudaMemcpyDeviceToHost));
+    }
+  } catch (const CudaError& ex) {
+    return fail(e, MDB_ERR_CUDA, ex.msg);
+  }
+  return MDB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// single-kernel entry points (parity tests)
+// ---------------------------------------------------------------------------------------------
+int mdb_op_letterbox(mdb_engine* e, const uint8_t* rgb_hwc, int32_t h, int32_t w, int64_t row_stride, void* dst_fp16,
+                     int32_t* out_hw2) {
+  if (!e || !rgb_hwc || !dst_fp16 || h <= 0 || w <= 0) return fail(e, MDB_ERR_ARG, "null argument");
+  try {
+    MDB_CUDA(cudaSetDevice(e->cfg.device));
+    const mdb_config& cfg = e->cfg;
+    const LetterboxGeom g = letterbox_geometry(h, w, cfg.img_size, cfg.stride, cfg.letterbox_auto != 0, cfg.letterbox_scaleup != 0);
+    MDB_REQUIRE(g.out_h % 2 == 0 && g.out_w % 2 == 0, "letterboxed size must be even");
+    cudaStream_t st = e->st_compute;
+    const size_t row = static_cast<size_t>(w) * 3;
+    uint8_t* d_src = nullptr;
+    __half* d_dst = nullptr;
+    PreImage* d_pi = nullptr;
+    const size_t out_elems = static_cast<size_t>(g.out_h / 2) * (g.out_w / 2) * 16;
+    MDB_CUDA(cudaMalloc(&d_src, row * h + 256));
+    MDB_CUDA(cudaMalloc(&d_dst, out_elems * 2));
+    MDB_CUDA(cudaMalloc(&d_pi, sizeof(PreImage)));
+    MDB_CUDA(cudaMemcpy2D(d_src, row, rgb_hwc, row_stride ? static_cast<size_t>(row_stride) : row, row, h, cudaMemcpyHostToDevice));
+    PreImage pi;
+    pi.src = d_src; pi.src_stride = static_cast<long long>(row); pi.src_h = h; pi.src_w = w;
+    pi.new_w = g.new_w; pi.new_h = g.new_h; pi.top = g.top; pi.left = g.left;
+    const DevTable& tx = get_table(e, w, g.new_w, false);
+    const DevTable& ty = get_table(e, h, g.new_h, true);
+    pi.xofs = tx.ofs; pi.xcoef = tx.coef; pi.yofs = ty.ofs; pi.ycoef = ty.coef;
+    MDB_CUDA(cudaMemcpy(d_pi, &pi, sizeof(pi), cudaMemcpyHostToDevice));
+    const float max_scale = std::max(1.0f, std::max(static_cast<float>(w) / g.new_w, static_cast<float>(h) / g.new_h));
+    preprocess_launch(d_pi, 1, g.out_h, g.out_w, d_dst, max_scale, st);
+    e->launches++;
+    MDB_CUDA(cudaStreamSynchronize(st));
+    MDB_CUDA(cudaMemcpy(dst_fp16, d_dst, out_elems * 2, cudaMemcpyDeviceToHost));
+    if (out_hw2) { out_hw2[0] = g.out_h; out_hw2[1] = g.out_w; }
+    cudaFree(d_src); cudaFree(d_dst); cudaFree(d_pi);
+  } catch (const CudaError& ex) {
+    return fail(e, MDB_ERR_CUDA, ex.msg);
+  }
+  return MDB_OK;
+}
+
+int mdb_op_conv2d(mdb_engine* e, const void* x_fp16, int32_t n, int32_t h, int32_t w, int32_t cin, const float* wgt,
+                  const float* bias, int32_t cout, int32_t k, int32_t s, int32_t pad, int32_t act,
+                  const void* residual_fp16, int32_t out_fp32, void* y, int32_t iters, float* ms) {
+  if (!e || !x_fp16 || !wgt || !bias || !y) return fail(e, MDB_ERR_ARG, "null argument");
+  void *d_x = nullptr, *d_y = nullptr, *d_r = nullptr;
+  __half* d_w = nullptr;
+  float* d_b = nullptr;
+  ConvOp* op = nullptr;
+  int rc = MDB_OK;
+  try {
+    MDB_CUDA(cudaSetDevice(e->cfg.device));
+    MDB_REQUIRE(cin % 16 == 0, "cin must be a multiple of 16");
+    cudaStream_t st = e->st_compute;
+    const int ho = (h + 2 * pad - k) / s + 1, wo = (w + 2 * pad - k) / s + 1;
+    const int cout_pad = ((cout + 15) / 16) * 16;
+    const int cstore = out_fp32 ? ((cout + 3) / 4) * 4 : ((cout + 7) / 8) * 8;
+    MDB_REQUIRE(cstore == cout, "cout must be a multiple of 8 (fp16) / 4 (fp32) for this test entry point");
+    std::vector<__half> packed;
+    pack_weights_khwc(wgt, cout, cin, k, cout_pad, cin, packed);
+    std::vector<float> bp(cout_pad, 0.f);
+    memcpy(bp.data(), bias, sizeof(float) * cout);
+    const size_t xb = static_cast<size_t>(n) * h * w * cin * 2;
+    const size_t yb = static_cast<size_t>(n) * ho * wo * cout * (out_fp32 ? 4 : 2);
+    MDB_CUDA(cudaMalloc(&d_x, xb + 256));
+    MDB_CUDA(cudaMalloc(&d_y, yb + 256));
+    MDB_CUDA(cudaMalloc(&d_w, packed.size() * 2 + 256));
+    MDB_CUDA(cudaMalloc(&d_b, bp.size() * 4));
+    MDB_CUDA(cudaMemcpy(d_x, x_fp16, xb, cudaMemcpyHostToDevice));
+    MDB_CUDA(cudaMemcpy(d_w, packed.data(), packed.size() * 2, cudaMemcpyHostToDevice));
+    MDB_CUDA(cudaMemcpy(d_b, bp.data(), bp.size() * 4, cudaMemcpyHostToDevice));
+    MDB_CUDA(cudaMemset(d_y, 0xFF, yb));
+    ConvDesc d;
+    d.in.base = d_x; d.in.N = n; d.in.H = h; d.in.W = w; d.in.Ctot = cin; d.in.C = cin;
+    d.out.base = d_y; d.out.N = n; d.out.H = ho; d.out.W = wo; d.out.Ctot = cout; d.out.C = cout; d.out.fp32 = out_fp32 != 0;
+    if (residual_fp16) {
+      const size_t rb = static_cast<size_t>(n) * ho * wo * cout * 2;
+      MDB_CUDA(cudaMalloc(&d_r, rb + 256));
+      MDB_CUDA(cudaMemcpy(d_r, residual_fp16, rb, cudaMemcpyHostToDevice));
+      d.res.base = d_r; d.res.N = n; d.res.H = ho; d.res.W = wo; d.res.Ctot = cout; d.res.C = cout;
+    }
+    d.wgt = d_w; d.bias = d_b; d.cout = cout; d.cout_pad = cout_pad; d.k = k; d.s = s; d.pad = pad; d.act = act;
+    op = conv_build(d, e->num_sms);
+    conv_launch(op, n, st);
+    e->launches++;
+    MDB_CUDA(cudaStreamSynchronize(st));
+    if (iters > 1) {
+      cudaEvent_t a, b;
+      MDB_CUDA(cudaEventCreate(&a));
+      MDB_CUDA(cudaEventCreate(&b));
+      MDB_CUDA(cudaEventRecord(a, st));
+      for (int i = 0; i < iters; ++i) conv_launch(op, n, st);
+      MDB_CUDA(cudaEventRecord(b, st));
+      MDB_CUDA(cudaEventSynchronize(b));
+      float t = 0;
+      cudaEventElapsedTime(&t, a, b);
+      if (ms) *ms = t / iters;
+      e->launches += iters;
+      cudaEventDestroy(a); cudaEventDestroy(b);
+    } else if (ms) {
+      *ms = 0;
+    }
+    MDB_CUDA(cudaMemcpy(y, d_y, yb, cudaMemcpyDeviceToHost));
+  } catch (const CudaError& ex) {
+    rc = fail(e, MDB_ERR_CUDA, ex.msg);
+  }
+  if (op) conv_free(op);
+  cudaFree(d_x); cudaFree(d_y); cudaFree(d_r); cudaFree(d_w); cudaFree(d_b);
+  return rc;
+}
+
+int mdb_op_nms(mdb_engine* e, const float* pred, int32_t n, int32_t anchors, int32_t nc, float conf_thres,
+               double iou_thres, int32_t max_det, float* det_out, int32_t* det_count, int32_t* kept_anchor) {
+  if (!e || !pred || !det_out || !det_count || n <= 0 || anchors <= 0) return fail(e, MDB_ERR_ARG, "null argument");
+  float* d_pred = nullptr; void* d_scr = nullptr; float* d_det = nullptr; int32_t* d_cnt = nullptr; int32_t* d_anc = nullptr;
+  int rc = MDB_OK;
+  try {
+    MDB_CUDA(cudaSetDevice(e->cfg.device));
+    MDB_REQUIRE(max_det >= 1 && max_det <= kMaxDetCap, "max_det out of range");
+    cudaStream_t st = e->st_compute;
+    const int no = nc + 5;
+    const size_t pb = static_cast<size_t>(n) * anchors * no * 4;
+    MDB_CUDA(cudaMalloc(&d_pred, pb));
+    MDB_CUDA(cudaMalloc(&d_scr, nms_scratch_bytes(n, anchors)));
+    MDB_CUDA(cudaMalloc(&d_det, static_cast<size_t>(n) * max_det * 6 * 4));
+    MDB_CUDA(cudaMalloc(&d_cnt, n * 4));
+    MDB_CUDA(cudaMalloc(&d_anc, static_cast<size_t>(n) * max_det * 4));
+    MDB_CUDA(cudaMemcpy(d_pred, pred, pb, cudaMemcpyHostToDevice));
+    MDB_CUDA(cudaMemset(d_det, 0, static_cast<size_t>(n) * max_det * 6 * 4));
+    MDB_CUDA(cudaMemset(d_anc, 0xFF, static_cast<size_t>(n) * max_det * 4));
+    NmsScratch sc;
+    nms_bind_scratch(&sc, d_scr, n, anchors);
+    nms_launch(d_pred, n, anchors, no, conf_thres, float_floor_of_double(iou_thres), max_det, nullptr, sc, d_det, d_cnt,
+               d_anc, st);
+    e->launches++;
+    MDB_CUDA(cudaStreamSynchronize(st));
+    MDB_CUDA(cudaMemcpy(det_out, d_det, static_cast<size_t>(n) * max_det * 6 * 4, cudaMemcpyDeviceToHost));
+    MDB_CUDA(cudaMemcpy(det_count, d_cnt, n * 4, cudaMemcpyDeviceToHost));
+    if (kept_anchor) MDB_CUDA(cudaMemcpy(kept_anchor, d_anc, static_cast<size_t>(n) * max_det * 4, cudaMemcpyDeviceToHost));
+  } catch (const CudaError& ex) {
+    rc = fail(e, MDB_ERR_CUDA, ex.msg);
+  }
+  cudaFree(d_pred); cudaFree(d_scr); cudaFree(d_det); cudaFree(d_cnt); cudaFree(d_anc);
+  return rc;
+}
+
+}  // extern "C"

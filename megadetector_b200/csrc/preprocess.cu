@@ -1,0 +1,210 @@
+// K1: fused letterbox-resize + pad(114) + /255 + HWC->NHWC(space-to-depth) fp16.
+//
+// Replaces, for one image:
+//   * the third-party yolov5 `letterbox()` (cv2.resize INTER_LINEAR + cv2.copyMakeBorder 114) called at
+//     megadetector/detection/pytorch_detector.py:1104-1109
+//   * HWC->CHW, ascontiguousarray, stack, .float(), /= 255.0 at pytorch_detector.py:1283-1306
+// The arithmetic is OpenCV's 8-bit fixed-point bilinear (11-bit coefficients), reproduced exactly:
+// coefficient tables are built on the host with the same float/double operations cv::resize uses, the
+// kernel is pure integer.  The output is what the first convolution wants to read: the 6x6/s2 stem is run
+// as a 3x3/s1 convolution over the 2x2 space-to-depth image, so K1 writes [H/2][W/2][16] fp16 with channel
+// (py*2+px)*3+c (12 used, 4 zero) -- one 32-byte store per thread, fully coalesced.
+//
+// HBM traffic per 1920x1080 -> 768x1280 image: 6.22 MB read (each source byte once, staged through shared
+// memory with 128-bit loads) + 7.86 MB written.
+#include <algorithm>
+#include <cmath>
+
+#include "common.h"
+
+namespace mdb {
+
+__constant__ __half c_norm_lut[256];  // half(float(v) / 255.0f)
+
+void preprocess_init_constants() {
+  __half lut[256];
+  for (int v = 0; v < 256; ++v) lut[v] = __float2half_rn(static_cast<float>(v) / 255.0f);
+  MDB_CUDA(cudaMemcpyToSymbol(c_norm_lut, lut, sizeof(lut)));
+}
+
+LetterboxGeom letterbox_geometry(int h, int w, int img_size, int stride, bool autopad, bool scaleup) {
+  // pytorch_detector.py:434-452 (the reference's own restatement of yolov5 letterbox geometry).
+  // Python's round() is round-half-to-even on doubles == nearbyint in the default rounding mode.
+  LetterboxGeom g{};
+  g.src_h = h;
+  g.src_w = w;
+  double r = std::min(static_cast<double>(img_size) / h, static_cast<double>(img_size) / w);
+  if (!scaleup) r = std::min(r, 1.0);
+  g.ratio = r;
+  g.new_w = static_cast<int>(std::nearbyint(w * r));
+  g.new_h = static_cast<int>(std::nearbyint(h * r));
+  double dw = img_size - g.new_w, dh = img_size - g.new_h;
+  if (autopad) {
+    dw = std::fmod(dw, stride);
+    dh = std::fmod(dh, stride);
+    if (dw < 0) dw += stride;  // np.mod semantics
+    if (dh < 0) dh += stride;
+  }
+  dw /= 2;
+  dh /= 2;
+  g.dw = dw;
+  g.dh = dh;
+  g.top = static_cast<int>(std::nearbyint(dh - 0.1));
+  g.bottom = static_cast<int>(std::nearbyint(dh + 0.1));
+  g.left = static_cast<int>(std::nearbyint(dw - 0.1));
+  g.right = static_cast<int>(std::nearbyint(dw + 0.1));
+  g.out_h = g.new_h + g.top + g.bottom;
+  g.out_w = g.new_w + g.left + g.right;
+  return g;
+}
+
+void linear_tables(int ssize, int dsize, bool vertical, std::vector<int32_t>& ofs, std::vector<int16_t>& coef) {
+  // cv::resize, INTER_LINEAR, 8-bit: imgproc/src/resize.cpp (coefficient set-up before resizeGeneric_).
+  ofs.resize(dsize);
+  coef.resize(2 * static_cast<size_t>(dsize));
+  const double inv_scale = static_cast<double>(dsize) / ssize;
+  const double scale = 1.0 / inv_scale;
+  for (int d = 0; d < dsize; ++d) {
+    float f = static_cast<float>((d + 0.5) * scale - 0.5);
+    int s = static_cast<int>(std::floor(f));
+    f -= static_cast<float>(s);
+    if (!vertical) {
+      if (s < 0) { s = 0; f = 0.f; }
+      if (s >= ssize - 1) { s = ssize - 1; f = 0.f; }
+    }
+    ofs[d] = s;
+    coef[2 * d] = static_cast<int16_t>(std::lrintf((1.f - f) * 2048.f));
+    coef[2 * d + 1] = static_cast<int16_t>(std::lrintf(f * 2048.f));
+  }
+}
+
+constexpr int kPreThreads = 256;
+constexpr int kTileW2 = 64;  // s2d columns per CTA  (128 output columns)
+constexpr int kTileH2 = 8;   // s2d rows per CTA     (16 output rows)
+
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+// STAGED: the source window of the tile is first copied to shared memory with 16-byte loads.
+template <bool STAGED>
+__global__ void __launch_bounds__(kPreThreads) letterbox_s2d_kernel(const PreImage* __restrict__ imgs, int out_h,
+                                                                   int out_w, __half* __restrict__ dst,
+                                                                   int smem_row_bytes, int smem_rows) {
+  extern __shared__ __align__(16) uint8_t s_src[];
+  const PreImage im = imgs[blockIdx.z];
+  const int W2 = out_w >> 1, H2 = out_h >> 1;
+  const int sx2_0 = blockIdx.x * kTileW2, sy2_0 = blockIdx.y * kTileH2;
+
+  // output-pixel window of this tile that lies inside the resized image
+  const int ox_lo = max(2 * sx2_0, im.left), ox_hi = min(2 * (sx2_0 + kTileW2), im.left + im.new_w) - 1;
+  const int oy_lo = max(2 * sy2_0, im.top), oy_hi = min(2 * (sy2_0 + kTileH2), im.top + im.new_h) - 1;
+  const bool any_src = (ox_lo <= ox_hi) && (oy_lo <= oy_hi);
+
+  int row0 = 0, byte0 = 0;  // source window origin
+  if (STAGED) {
+    if (any_src) {
+      row0 = clampi(im.yofs[oy_lo - im.top], 0, im.src_h - 1);
+      const int row1 = clampi(im.yofs[oy_hi - im.top] + 1, 0, im.src_h - 1);
+      const int col0 = im.xofs[ox_lo - im.left];
+      const int col1 = min(im.xofs[ox_hi - im.left] + 1, im.src_w - 1);
+      byte0 = col0 * 3;
+      const int nbytes = (col1 + 1) * 3 - byte0;
+      const int nrows = row1 - row0 + 1;
+      // each row: 16-byte vectors starting at the aligned-down address of its first needed byte
+      const int vec_per_row = smem_row_bytes >> 4;
+      for (int i = threadIdx.x; i < nrows * vec_per_row; i += kPreThreads) {
+        const int r = i / vec_per_row, v = i - r * vec_per_row;
+        const uint8_t* p = im.src + static_cast<long long>(row0 + r) * im.src_stride + byte0;
+        const uintptr_t a = reinterpret_cast<uintptr_t>(p) & ~static_cast<uintptr_t>(15);
+        const int shift = static_cast<int>(reinterpret_cast<uintptr_t>(p) - a);
+        if (v * 16 < shift + nbytes) {
+          const uint4 q = __ldg(reinterpret_cast<const uint4*>(a) + v);
+          *reinterpret_cast<uint4*>(s_src + static_cast<size_t>(r) * smem_row_bytes + v * 16) = q;
+        }
+      }
+      (void)smem_rows;
+    }
+    __syncthreads();
+  }
+
+  auto fetch = [&](int sy, int sxb) -> int {  // byte sxb of source row sy
+    if (STAGED) {
+      const uint8_t* p = im.src + static_cast<long long>(sy) * im.src_stride + byte0;
+      const int shift = static_cast<int>(reinterpret_cast<uintptr_t>(p) & 15);
+      return s_src[static_cast<size_t>(sy - row0) * smem_row_bytes + shift + (sxb - byte0)];
+    } else {
+      return __ldg(im.src + static_cast<long long>(sy) * im.src_stride + sxb);
+    }
+  };
+
+  for (int t = threadIdx.x; t < kTileW2 * kTileH2; t += kPreThreads) {
+    const int lx = t % kTileW2, ly = t / kTileW2;
+    const int sx2 = sx2_0 + lx, sy2 = sy2_0 + ly;
+    if (sx2 >= W2 || sy2 >= H2) continue;
+    __align__(16) __half px[16];
+#pragma unroll
+    for (int i = 12; i < 16; ++i) px[i] = __ushort_as_half(0);
+#pragma unroll
+    for (int py = 0; py < 2; ++py) {
+      const int oy = 2 * sy2 + py;
+      const int dy = oy - im.top;
+      const bool in_y = dy >= 0 && dy < im.new_h;
+      int sy0 = 0, sy1 = 0, b0 = 0, b1 = 0;
+      if (in_y) {
+        const int s = im.yofs[dy];
+        sy0 = clampi(s, 0, im.src_h - 1);
+        sy1 = clampi(s + 1, 0, im.src_h - 1);
+        b0 = im.ycoef[2 * dy];
+        b1 = im.ycoef[2 * dy + 1];
+      }
+#pragma unroll
+      for (int pxx = 0; pxx < 2; ++pxx) {
+        const int ox = 2 * sx2 + pxx;
+        const int dx = ox - im.left;
+        int v[3] = {114, 114, 114};
+        if (in_y && dx >= 0 && dx < im.new_w) {
+          const int sx0 = im.xofs[dx];
+          const int sx1 = min(sx0 + 1, im.src_w - 1);
+          const int a0 = im.xcoef[2 * dx], a1 = im.xcoef[2 * dx + 1];
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            const int h0 = fetch(sy0, sx0 * 3 + c) * a0 + fetch(sy0, sx1 * 3 + c) * a1;
+            const int h1 = fetch(sy1, sx0 * 3 + c) * a0 + fetch(sy1, sx1 * 3 + c) * a1;
+            v[c] = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) px[(py * 2 + pxx) * 3 + c] = c_norm_lut[v[c] & 255];
+      }
+    }
+    uint4* o = reinterpret_cast<uint4*>(dst + ((static_cast<size_t>(blockIdx.z) * H2 + sy2) * W2 + sx2) * 16);
+    o[0] = reinterpret_cast<const uint4*>(px)[0];
+    o[1] = reinterpret_cast<const uint4*>(px)[1];
+  }
+}
+
+void preprocess_launch(const PreImage* d_imgs, int n, int out_h, int out_w, __half* dst, float max_scale,
+                       cudaStream_t st) {
+  if (n <= 0) return;
+  const int W2 = out_w / 2, H2 = out_h / 2;
+  dim3 grid((W2 + kTileW2 - 1) / kTileW2, (H2 + kTileH2 - 1) / kTileH2, n);
+  // source window of one tile: (2*tile+1)*scale + 2 pixels each way, plus alignment slack
+  const int src_cols = static_cast<int>(std::ceil((2 * kTileW2 + 1) * max_scale)) + 3;
+  const int src_rows = static_cast<int>(std::ceil((2 * kTileH2 + 1) * max_scale)) + 3;
+  const int row_bytes = ((src_cols * 3 + 15 + 15) / 16) * 16;
+  const size_t smem = static_cast<size_t>(row_bytes) * src_rows;
+  static size_t attr = 0;
+  if (smem <= 200 * 1024) {
+    if (smem > 48 * 1024 && smem > attr) {
+      MDB_CUDA(cudaFuncSetAttribute(letterbox_s2d_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    static_cast<int>(smem)));
+      attr = smem;
+    }
+    letterbox_s2d_kernel<true><<<grid, kPreThreads, smem, st>>>(d_imgs, out_h, out_w, dst, row_bytes, src_rows);
+  } else {
+    // extreme down-scales (source window larger than shared memory): read through L1 instead
+    letterbox_s2d_kernel<false><<<grid, kPreThreads, 0, st>>>(d_imgs, out_h, out_w, dst, 0, 0);
+  }
+  MDB_CUDA(cudaGetLastError());
+}
+
+}  // namespace mdb

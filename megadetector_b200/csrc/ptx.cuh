@@ -57,12 +57,13 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Spin on a phase parity.  A watchdog turns a protocol bug into a trap (reported by the host as a
-// launch failure) instead of a hung GPU box.
+// Spin on a phase parity.  A watchdog (~2 s of SM clocks) turns a protocol bug into a trap, which the host
+// sees as a launch failure, instead of a hung GPU box.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t spins = 0;
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 28)) { asm volatile("trap;"); }
+    if (clock64() - t0 > 4000000000LL) { asm volatile("trap;"); }
   }
 }
 

@@ -109,9 +109,6 @@ def count_params_and_macs(arch, h, w):
     """Fused parameter count and conv multiply-accumulates for one h x w input."""
     params, macs = 0, 0
     # spatial size per conv: follow the graph
-    sizes = {}
-    H, W = h, w
-    res = {}
     for name, ci, co, k, s, p, act in conv_specs(arch):
         params += co * ci * k * k + co
     # MACs: walk by stage resolution
@@ -128,70 +125,7 @@ def count_params_and_macs(arch, h, w):
     return params, macs
 
 
-_CALIB = None  # set only inside calibrated_random_weights()
-
-
-def default_calibration_input(h=1080, w=1920, index=100000):
-    """One synthetic benchmark-style image (never part of a test pool), letterboxed, as model input."""
-    from megadetector_b200.synth import synth_image
-    from oracle.letterbox import letterbox, to_model_input
-    img, _, _ = letterbox(synth_image(index, h, w))
-    return torch.from_numpy(to_model_input(img))[None]
-
-
-def calibrated_random_weights(arch, seed=0, calib_input=None, obj_logit=(-13.0, 2.5)):
-    """
-    "Calibrated random init" (SURVEY.md par. 8d): with plain random weights the activations of a
-    ~100-conv-deep residual network explode or die, every anchor gets the same score and the
-    threshold/NMS stages degenerate into pure tie-breaking.  So: draw N(0, 1/fan_in) weights, then walk
-    the graph once on a letterboxed synthetic benchmark image and rescale each conv so its pre-activation std is 1
-    (0.7 on the residual branches), fused bias ~ N(0, 0.1^2).  The Detect heads are scaled so that the
-    objectness logit is ~N(obj_logit) (a few 10^3..10^4 anchors above the 1e-5 batch-path threshold, a
-    few 10^1..10^2 above 0.005), box logits ~N(0,1), class logits ~N(0,1.5).
-    Deterministic for a given (arch, seed, calib_input) on a given machine; the weights are generated once
-    per test/bench process and handed to both the oracle and the engine.
-    """
-    global _CALIB
-    g = torch.Generator().manual_seed(seed)
-    w = {}
-    for name, ci, co, k, s, p, act in conv_specs(arch):
-        fan_in = ci * k * k
-        w[name + '.weight'] = torch.randn(co, ci, k, k, generator=g) / fan_in ** 0.5
-        w[name + '.bias'] = torch.randn(co, generator=g) * 0.1
-    if calib_input is None:
-        calib_input = default_calibration_input()
-    x = calib_input
-    _CALIB = {'obj_logit': obj_logit, 'no': arch.no}
-    try:
-        forward(x, w, arch)
-    finally:
-        _CALIB = None
-    return w
-
-
-def _calibrate(x, w, name, s, p):
-    y = F.conv2d(x, w[name + '.weight'], None, stride=s, padding=p)
-    if name.startswith('model.33.'):
-        no = _CALIB['no']
-        wt = w[name + '.weight'].view(3, no, -1)
-        b = w[name + '.bias'].view(3, no)
-        yy = y.view(y.shape[0], 3, no, -1)
-        for a in range(3):
-            for c in range(no):
-                tgt_std = 1.0 if c < 4 else (_CALIB['obj_logit'][1] if c == 4 else 1.5)
-                tgt_mean = 0.0 if c != 4 else _CALIB['obj_logit'][0]
-                v = yy[:, a, c]
-                sc = tgt_std / float(v.std() + 1e-12)
-                wt[a, c] *= sc
-                b[a, c] = tgt_mean - float(v.mean()) * sc
-    else:
-        tgt = 0.7 if ('.m.' in name and name.endswith('cv2.conv')) else 1.0
-        w[name + '.weight'] *= tgt / float(y.std() + 1e-12)
-
-
 def _conv(x, w, name, s=1, p=0, act=True, trace=None):
-    if _CALIB is not None:
-        _calibrate(x, w, name, s, p)
     y = F.conv2d(x, w[name + '.weight'], w[name + '.bias'], stride=s, padding=p)
     if act:
         y = F.silu(y)
