@@ -105,6 +105,10 @@ MDB_API int mdb_infer_preprocessed(mdb_engine* e, const uint8_t* const* lb_hwc, 
                            const int32_t* src_h, const int32_t* src_w, int32_t n, float conf_thres, float* det_out,
                            int32_t* det_count, int32_t* kept_anchor, int32_t* status);
 
+/* `image_size` argument of generate_detections_one_batch (pytorch_detector.py:1011-1024): long-side target of
+ * the letterbox for subsequent calls (default cfg.img_size). */
+MDB_API int mdb_set_image_size(mdb_engine* e, int32_t img_size);
+
 /* Letterbox geometry exactly as the reference computes it (pytorch_detector.py:434-452,1104-1109):
  * out[0..7] = new_unpad_w, new_unpad_h, top, bottom, left, right, out_h, out_w ; ratio_pad[0..2] = r, dw, dh */
 MDB_API int mdb_letterbox_geometry(const mdb_config* cfg, int32_t h, int32_t w, int32_t* out8, double* ratio_pad3);
@@ -117,6 +121,18 @@ MDB_API int mdb_debug_fetch(mdb_engine* e, int32_t what, int32_t index, void* ho
 
 /* device timing of the last infer call, milliseconds: [0]=h2d+preprocess [1]=network [2]=decode+nms [3]=total */
 MDB_API int mdb_last_timing(mdb_engine* e, float* ms4);
+/* Device-resident throughput measurement (bench.py `value`): re-runs the batch that the last infer call left
+ * staged in HBM `iters` times back to back (stages_mask: 1 = K1 preprocess, 2 = network, 4 = decode+NMS+result
+ * D2H; 7 = everything) and returns the elapsed device time between CUDA events on the compute stream. */
+MDB_API int mdb_bench_resident(mdb_engine* e, int32_t iters, float conf_thres, int32_t stages_mask, float* ms_total);
+/* Per-step device time of the staged batch (each step launched `iters` times back to back): ms_out[i], the
+ * conv multiply-accumulates of the step macs_out[i] (0 for non-conv steps) and a description in
+ * names_out[i * name_stride].  *n_steps receives the number of steps of the plan. */
+MDB_API int mdb_profile_steps(mdb_engine* e, int32_t iters, float* ms_out, double* macs_out, char* names_out,
+                              int32_t name_stride, int32_t cap, int32_t* n_steps);
+/* A group of n <= max_batch images is uploaded and processed in `parts` chunks so that the H2D copy of one
+ * chunk overlaps the kernels of the previous one (default 2; 1 = one chunk). */
+MDB_API int mdb_set_pipeline_split(mdb_engine* e, int32_t parts);
 /* number of kernels the engine launched since creation (bench.py's gpu_launches) */
 MDB_API int64_t mdb_launch_count(const mdb_engine* e);
 

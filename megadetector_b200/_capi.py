@@ -18,7 +18,7 @@ MDB_FETCH_STEM_INPUT, MDB_FETCH_PRED, MDB_FETCH_LAYER = 1, 2, 3
 
 EXPORTS = [
     'mdb_create', 'mdb_load_weights', 'mdb_destroy', 'mdb_last_error', 'mdb_infer_batch', 'mdb_infer_preprocessed',
-    'mdb_letterbox_geometry', 'mdb_debug_fetch', 'mdb_last_timing', 'mdb_launch_count', 'mdb_op_letterbox',
+    'mdb_letterbox_geometry', 'mdb_set_image_size', 'mdb_debug_fetch', 'mdb_last_timing', 'mdb_bench_resident', 'mdb_profile_steps', 'mdb_set_pipeline_split', 'mdb_launch_count', 'mdb_op_letterbox',
     'mdb_op_conv2d', 'mdb_op_nms', 'mdb_alloc_pinned', 'mdb_free_pinned', 'mdb_version',
 ]
 
@@ -46,6 +46,12 @@ def load_library():
     global _lib
     if _lib is not None:
         return _lib
+    try:  # rebuild when the sources changed and nvcc is here (a no-op stamp check otherwise)
+        from .build import build as _build
+        _build()
+    except Exception as e:  # an up-to-date prebuilt .so is fine without nvcc
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError('libmdb200.so is missing and could not be built: {}'.format(e))
     if not os.path.exists(LIB_PATH):
         raise RuntimeError(
             'libmdb200.so is missing ({}): build it with `python -m megadetector_b200.build`. '
@@ -69,10 +75,18 @@ def load_library():
     lib.mdb_infer_preprocessed.restype = C.c_int
     lib.mdb_letterbox_geometry.argtypes = [P(MdbConfig), C.c_int32, C.c_int32, P(C.c_int32), P(C.c_double)]
     lib.mdb_letterbox_geometry.restype = C.c_int
+    lib.mdb_set_image_size.argtypes = [vp, C.c_int32]
+    lib.mdb_set_image_size.restype = C.c_int
     lib.mdb_debug_fetch.argtypes = [vp, C.c_int32, C.c_int32, vp, C.c_size_t, P(C.c_int64)]
     lib.mdb_debug_fetch.restype = C.c_int
     lib.mdb_last_timing.argtypes = [vp, P(C.c_float)]
     lib.mdb_last_timing.restype = C.c_int
+    lib.mdb_bench_resident.argtypes = [vp, C.c_int32, C.c_float, C.c_int32, P(C.c_float)]
+    lib.mdb_bench_resident.restype = C.c_int
+    lib.mdb_profile_steps.argtypes = [vp, C.c_int32, vp, vp, vp, C.c_int32, C.c_int32, P(C.c_int32)]
+    lib.mdb_profile_steps.restype = C.c_int
+    lib.mdb_set_pipeline_split.argtypes = [vp, C.c_int32]
+    lib.mdb_set_pipeline_split.restype = C.c_int
     lib.mdb_launch_count.argtypes = [vp]
     lib.mdb_launch_count.restype = C.c_int64
     lib.mdb_op_letterbox.argtypes = [vp, vp, C.c_int32, C.c_int32, C.c_int64, vp, P(C.c_int32)]
@@ -260,10 +274,38 @@ class Engine:
         self._check(rc, 'mdb_infer_preprocessed')
         return det, cnt, anc, status
 
+    def set_image_size(self, img_size):
+        self._check(self.lib.mdb_set_image_size(self.h, int(img_size)), 'mdb_set_image_size')
+        self.cfg.img_size = int(img_size)
+
     def last_timing(self):
         ms = (C.c_float * 4)()
         self._check(self.lib.mdb_last_timing(self.h, ms), 'mdb_last_timing')
         return {'preprocess_ms': ms[0], 'network_ms': ms[1], 'postprocess_ms': ms[2], 'total_ms': ms[3]}
+
+    def bench_resident(self, iters, conf_thres, stages_mask=7):
+        """Device time (ms) of `iters` back-to-back passes over the batch left staged in HBM by the last infer call."""
+        ms = C.c_float(0)
+        self._check(self.lib.mdb_bench_resident(self.h, int(iters), float(conf_thres), int(stages_mask), C.byref(ms)),
+                    'mdb_bench_resident')
+        return float(ms.value)
+
+    def profile_steps(self, iters=5):
+        """[(description, ms, macs)] per plan step for the batch left staged by the last infer call."""
+        cap, stride = 512, 160
+        ms = np.zeros(cap, np.float32)
+        macs = np.zeros(cap, np.float64)
+        names = C.create_string_buffer(cap * stride)
+        n = C.c_int32(0)
+        self._check(self.lib.mdb_profile_steps(self.h, int(iters), ms.ctypes.data, macs.ctypes.data, names, stride, cap,
+                                               C.byref(n)), 'mdb_profile_steps')
+        out = []
+        for i in range(min(n.value, cap)):
+            out.append((names.raw[i * stride:(i + 1) * stride].split(b'\0', 1)[0].decode(), float(ms[i]), float(macs[i])))
+        return out
+
+    def set_pipeline_split(self, parts):
+        self._check(self.lib.mdb_set_pipeline_split(self.h, int(parts)), 'mdb_set_pipeline_split')
 
     def launch_count(self):
         return int(self.lib.mdb_launch_count(self.h))

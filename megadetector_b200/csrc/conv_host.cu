@@ -3,6 +3,9 @@
 #include <cmath>
 
 #include "common.h"
+#include <cstdlib>
+
+#include "conv_pair_tcgen05.cuh"
 #include "conv_tcgen05.cuh"
 
 namespace mdb {
@@ -11,6 +14,8 @@ struct ConvOp {
   CUtensorMap tmA[4];
   CUtensorMap tmB;
   ConvParams p;
+  PairParams pp;
+  bool pair = true;
   int kc = 64;
   bool flat = false;
   int HW_out = 0;  // output pixels per image
@@ -44,6 +49,25 @@ static void pick_tile(int H, int W, int* tw, int* th) {
   }
   *tw = bw;
   *th = bh;
+}
+
+static bool use_pair_kernel() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MDB_CONV_V1");
+    v = (e && e[0] == '1') ? 0 : 1;
+  }
+  return v == 1;
+}
+
+template <int KC>
+static void set_smem_attr_pair(size_t bytes) {
+  static size_t current = 0;
+  if (bytes > current) {
+    MDB_CUDA(cudaFuncSetAttribute(conv_pair_kernel<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(bytes)));
+    current = bytes;
+  }
 }
 
 template <int KC>
@@ -118,6 +142,35 @@ ConvOp* conv_build(const ConvDesc& d, int num_sms) {
           for (int px = 0; px < 2; ++px) make_act_tmap(&op->tmA[py * 2 + px], in, kc, p.tw, p.th, py, px);
       }
     }
+    op->pair = use_pair_kernel();
+    if (op->pair) {
+      // CTA pair: each CTA stages half of the B tile
+      make_wgt_tmap(&op->tmB, d.wgt, d.k * d.k * in.C, d.cout_pad, kc, p.BN / 2);
+      PairParams& q = op->pp;
+      q.H_out = p.H_out; q.W_out = p.W_out; q.tw = p.tw; q.th = p.th;
+      q.n_tiles = p.n_tiles; q.BN = p.BN; q.Cout = p.Cout;
+      q.KH = p.KH; q.KW = p.KW; q.stride = p.stride; q.pad = p.pad;
+      q.chunks = p.chunks; q.Cin = p.Cin;
+      q.total_chunks = d.k * d.k * p.chunks;
+      q.cps = 64 / kc;
+      q.bias = p.bias; q.out = p.out; q.out_pix_stride = p.out_pix_stride; q.out_c_off = p.out_c_off;
+      q.out_fp32 = p.out_fp32; q.res = p.res; q.res_pix_stride = p.res_pix_stride; q.res_c_off = p.res_c_off;
+      q.act = p.act;
+      q.idesc = make_idesc_f16(256, static_cast<uint32_t>(p.BN));
+      const size_t a_chunk = static_cast<size_t>(kTileM) * kc * 2;
+      const size_t b_chunk = (static_cast<size_t>(p.BN / 2) * kc * 2 + 1023) & ~static_cast<size_t>(1023);
+      const size_t stage = static_cast<size_t>(q.cps) * (a_chunk + b_chunk);
+      const size_t budget = 227 * 1024 - 4096;  // static: barriers + bias staging; alignment slack
+      const int stage_iters = (q.total_chunks + q.cps - 1) / q.cps;
+      int stages = static_cast<int>(std::min<size_t>(kPairMaxStages, (budget - 1024) / stage));
+      stages = std::max(2, std::min(stages, std::max(2, stage_iters * 2)));
+      q.stages = stages;
+      op->smem = stage * stages + 1024;
+      if (kc == 64) set_smem_attr_pair<64>(op->smem);
+      else if (kc == 32) set_smem_attr_pair<32>(op->smem);
+      else set_smem_attr_pair<16>(op->smem);
+      return op;
+    }
     make_wgt_tmap(&op->tmB, d.wgt, d.k * d.k * in.C, d.cout_pad, kc, p.BN);
 
     const size_t a_bytes = static_cast<size_t>(kTileM) * kc * 2;
@@ -139,7 +192,40 @@ ConvOp* conv_build(const ConvDesc& d, int num_sms) {
   return op;
 }
 
+static void conv_launch_pair(ConvOp* op, int n_img, cudaStream_t st) {
+  PairParams p = op->pp;
+  if (op->flat) {
+    const long long npix = static_cast<long long>(n_img) * op->HW_out;
+    p.n_img = 1;
+    p.H_out = 1;
+    p.W_out = static_cast<int>(npix);
+    p.tiles_x = static_cast<int>((npix + 127) / 128);
+    p.tiles_y = 1;
+  } else {
+    p.n_img = n_img;
+    p.tiles_x = (p.W_out + p.tw - 1) / p.tw;
+    p.tiles_y = (p.H_out + p.th - 1) / p.th;
+  }
+  p.m_tiles = p.n_img * p.tiles_x * p.tiles_y;
+  p.pair_m = (p.m_tiles + 1) / 2;
+  const long long total = static_cast<long long>(p.pair_m) * p.n_tiles;
+  if (total <= 0) return;
+  const int clusters = static_cast<int>(std::min<long long>(total, op->num_sms / 2));
+  const int grid = clusters * 2;
+  if (op->kc == 64)
+    conv_pair_kernel<64><<<grid, kPairThreads, op->smem, st>>>(op->tmA[0], op->tmA[1], op->tmA[2], op->tmA[3], op->tmB, p);
+  else if (op->kc == 32)
+    conv_pair_kernel<32><<<grid, kPairThreads, op->smem, st>>>(op->tmA[0], op->tmA[1], op->tmA[2], op->tmA[3], op->tmB, p);
+  else
+    conv_pair_kernel<16><<<grid, kPairThreads, op->smem, st>>>(op->tmA[0], op->tmA[1], op->tmA[2], op->tmA[3], op->tmB, p);
+  MDB_CUDA(cudaGetLastError());
+}
+
 void conv_launch(ConvOp* op, int n_img, cudaStream_t st) {
+  if (op->pair) {
+    conv_launch_pair(op, n_img, st);
+    return;
+  }
   ConvParams p = op->p;
   if (op->flat) {
     const long long npix = static_cast<long long>(n_img) * op->HW_out;

@@ -1,0 +1,405 @@
+// K2 (v2): implicit-GEMM convolution on CTA PAIRS -- tcgen05.mma.cta_group::2, 256 x BN pair tiles.
+//
+// Same GEMM view as conv_tcgen05.cuh (A = shifted NHWC boxes fetched by TMA with zero-fill, B = fused weights
+// [C_out][KH][KW][C_in], D in TMEM), re-organised after the first ncu captures (profiles/r01_*):
+//   * the 128 x BN single-CTA kernel could not keep the tensor pipe fed: 36 KB of operands per 1.3 M MACs and
+//     <= 216 KB in flight per SM is not enough at the observed TMA latency (tensor pipe 40 % active on the
+//     3x3 320->320 layer, L2 at 37 %, DRAM at 7 %).  A CTA pair shares B: each CTA stages its own 128 A rows
+//     and only HALF of the B tile; one elected thread of the leader CTA issues M=256 MMAs that read both
+//     CTAs' shared memory.  Operand bytes per MAC drop by 1.4-1.8x, and shared-memory read pressure with them.
+//   * every pipeline stage now carries 64 K-elements regardless of the swizzle width (1/2/4 TMA boxes of
+//     64/32/16 channels), so the C_in = 80 and C_in = 16 layers no longer pay one mbarrier round trip per MMA.
+//   * the epilogue was the bottleneck of every 1x1 layer (17.8 k cycles per 128x160 tile): now 8 warps
+//     (two per TMEM lane quadrant, interleaved 16-column chunks), TMEM loads issued one chunk ahead, bias from
+//     shared memory, SiLU as ex2.approx + rcp.approx (2 MUFU ops per element).
+//
+// Warp roles per CTA (320 threads): warp 0 = TMA producer, warp 1 = TMEM owner (+ MMA issuer in the leader CTA),
+// warps 2..9 = epilogue.  Barriers: full[s] lives in the LEADER (2 arrivals + bytes of both CTAs),
+// empty[s] / acc_full[a] are per CTA and signalled by multicast tcgen05.commit, acc_empty[a] lives in the leader
+// (16 warp arrivals).
+#pragma once
+#include <cuda_fp16.h>
+
+#include "conv_tcgen05.cuh"
+#include "ptx.cuh"
+
+namespace mdb {
+
+constexpr int kPairThreads = 320;
+constexpr int kPairEpiWarps = 8;
+constexpr int kPairMaxStages = 10;
+
+struct PairParams {
+  int n_img, H_out, W_out;
+  int tw, th;
+  int tiles_x, tiles_y;
+  int m_tiles, pair_m, n_tiles;
+  int BN, Cout;
+  int KH, KW, stride, pad;
+  int chunks;        // C_in / KC
+  int Cin;
+  int total_chunks;  // KH*KW*chunks
+  int cps;           // chunks per stage (64 / KC)
+  int stages;
+  const float* bias;
+  void* out;
+  long long out_pix_stride;
+  int out_c_off, out_fp32;
+  const __half* res;
+  long long res_pix_stride;
+  int res_c_off;
+  int act;
+  uint32_t idesc;  // M = 256
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive (count 1, no tx) on the mbarrier at the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank) {
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(rank)
+      : "memory");
+}
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;  // clears the CTA-pair rank bit of a shared::cluster address
+__device__ __forceinline__ void tma2_load_2d(const CUtensorMap* m, uint64_t* leader_bar, uint32_t dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(leader_bar) & kPeerBitMask), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma2_load_4d(const CUtensorMap* m, uint64_t* leader_bar, uint32_t dst, int c0, int c1,
+                                             int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, "
+      "%6}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(leader_bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t* smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)),
+               "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish2() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma2_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on the barrier at this offset in BOTH CTAs of the pair once all prior MMAs of this thread retired
+__device__ __forceinline__ void umma2_commit_mc(uint64_t* bar) {
+  const uint16_t mask = 3;
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ float silu_fast(float x) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  return x * r;
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+template <int KC>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1)
+conv_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+                 const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmA3,
+                 const __grid_constant__ CUtensorMap tmB, const PairParams p) {
+  constexpr uint32_t ROW_BYTES = KC * 2;
+  constexpr uint32_t A_CHUNK = kTileM * ROW_BYTES;  // 128 rows of one K chunk
+
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[kPairMaxStages];
+  __shared__ __align__(8) uint64_t empty_bar[kPairMaxStages];
+  __shared__ __align__(8) uint64_t acc_full_bar[2];
+  __shared__ __align__(8) uint64_t acc_empty_bar[2];
+  __shared__ uint32_t tmem_base_smem;
+  __shared__ __align__(16) float bias_s[2][256];
+
+  const uint32_t warp = threadIdx.x >> 5;
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t half_n = static_cast<uint32_t>(p.BN) >> 1;
+  const uint32_t b_chunk = (half_n * ROW_BYTES + 1023u) & ~1023u;
+  const uint32_t chunk_bytes = A_CHUNK + b_chunk;
+  const uint32_t stage_bytes = static_cast<uint32_t>(p.cps) * chunk_bytes;
+  // bytes that land in ONE CTA per chunk (A box + half-B box); the leader's barrier expects both CTAs' bytes
+  const uint32_t tx_per_chunk = static_cast<uint32_t>(p.tw * p.th) * ROW_BYTES + half_n * ROW_BYTES;
+
+  const int S = p.stages;
+  const int stage_iters = (p.total_chunks + p.cps - 1) / p.cps;
+  const int total_tiles = p.pair_m * p.n_tiles;
+  const int num_clusters = gridDim.x >> 1;
+  const int cluster_id = blockIdx.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA0);
+    tma_prefetch_desc(&tmB);
+    if (p.stride == 2) {
+      tma_prefetch_desc(&tmA1);
+      tma_prefetch_desc(&tmA2);
+      tma_prefetch_desc(&tmA3);
+    }
+    for (int s = 0; s < S; ++s) {
+      mbar_init(&full_bar[s], 2);   // leader's instance is the one in use: both producers arrive
+      mbar_init(&empty_bar[s], 1);  // multicast commit of the leader's MMA thread
+    }
+    mbar_init(&acc_full_bar[0], 1);
+    mbar_init(&acc_full_bar[1], 1);
+    mbar_init(&acc_empty_bar[0], 2 * kPairEpiWarps);  // leader's instance: 8 warps of each CTA
+    mbar_init(&acc_empty_bar[1], 2 * kPairEpiWarps);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc2(&tmem_base_smem, kTmemCols);
+    tmem_relinquish2();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
+        const int n_tile = tile % p.n_tiles;
+        const int m_tile = 2 * (tile / p.n_tiles) + static_cast<int>(rank);
+        const int txi = m_tile % p.tiles_x;
+        const int tyi = (m_tile / p.tiles_x) % p.tiles_y;
+        const int img = m_tile / (p.tiles_x * p.tiles_y);  // >= n_img for the padding tile: TMA zero-fills
+        const int ox0 = txi * p.tw, oy0 = tyi * p.th;
+        const int nb0 = n_tile * p.BN + static_cast<int>(rank * half_n);
+        int g = 0;
+        for (int si = 0; si < stage_iters; ++si, ++it) {
+          const int s = it % S;
+          const uint32_t ph = (it / S) & 1u;
+          const int nch = min(p.cps, p.total_chunks - g);
+          mbar_wait(&empty_bar[s], ph ^ 1u);
+          if (leader) mbar_arrive_expect_tx(&full_bar[s], 2u * static_cast<uint32_t>(nch) * tx_per_chunk);
+          else mbar_arrive_remote(&full_bar[s], 0);
+          const uint32_t sbase = smem_base + static_cast<uint32_t>(s) * stage_bytes;
+          for (int j = 0; j < nch; ++j, ++g) {
+            const int tap = g / p.chunks;
+            const int c = g - tap * p.chunks;
+            const int kh = tap / p.KW, kw = tap - kh * p.KW;
+            const CUtensorMap* ma = &tmA0;
+            int x, y;
+            if (p.stride == 1) {
+              x = ox0 + kw - p.pad;
+              y = oy0 + kh - p.pad;
+            } else {
+              const int ty_ = kh - p.pad, tx_ = kw - p.pad;
+              const int py = ty_ & 1, px = tx_ & 1;
+              y = oy0 + (ty_ - py) / 2;
+              x = ox0 + (tx_ - px) / 2;
+              const int par = py * 2 + px;
+              ma = par == 0 ? &tmA0 : (par == 1 ? &tmA1 : (par == 2 ? &tmA2 : &tmA3));
+            }
+            const uint32_t dst = sbase + static_cast<uint32_t>(j) * chunk_bytes;
+            tma2_load_4d(ma, &full_bar[s], dst, c * KC, x, y, img);
+            tma2_load_2d(&tmB, &full_bar[s], dst + A_CHUNK, tap * p.Cin + c * KC, nb0);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (leader && lane == 0) {
+      uint32_t it = 0;
+      uint32_t tcount = 0;
+      for (int tile = cluster_id; tile < total_tiles; tile += num_clusters, ++tcount) {
+        const uint32_t acc = tcount & 1u;
+        const uint32_t acc_ph = (tcount >> 1) & 1u;
+        mbar_wait(&acc_empty_bar[acc], acc_ph ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * kAccStride;
+        int g = 0;
+        for (int si = 0; si < stage_iters; ++si, ++it) {
+          const int s = it % S;
+          const uint32_t ph = (it / S) & 1u;
+          const int nch = min(p.cps, p.total_chunks - g);
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t sbase = smem_base + static_cast<uint32_t>(s) * stage_bytes;
+          for (int j = 0; j < nch; ++j, ++g) {
+            const uint32_t a_addr = sbase + static_cast<uint32_t>(j) * chunk_bytes;
+            const uint64_t da = make_kmajor_desc(a_addr, ROW_BYTES);
+            const uint64_t db = make_kmajor_desc(a_addr + A_CHUNK, ROW_BYTES);
+#pragma unroll
+            for (int k = 0; k < KC / 16; ++k)
+              umma2_f16(d_tmem, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), p.idesc,
+                        (g > 0 || k > 0) ? 1u : 0u);
+          }
+          umma2_commit_mc(&empty_bar[s]);
+        }
+        umma2_commit_mc(&acc_full_bar[acc]);
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..9 of both CTAs) =====================
+    const uint32_t ew = warp - 2;          // 0..7
+    const uint32_t quad = warp & 3u;       // TMEM lane quadrant this warp may read
+    const uint32_t half = ew >> 2;         // which interleaved set of 16-column chunks
+    const uint32_t row = quad * 32u + lane;
+    const int ty = static_cast<int>(row) / p.tw;
+    const int tx = static_cast<int>(row) - ty * p.tw;
+    const int et = static_cast<int>(threadIdx.x) - 64;  // 0..255
+    const int nchunks = p.BN >> 4;
+    uint32_t tcount = 0;
+    for (int tile = cluster_id; tile < total_tiles; tile += num_clusters, ++tcount) {
+      const uint32_t acc = tcount & 1u;
+      const uint32_t acc_ph = (tcount >> 1) & 1u;
+      const int n_tile = tile % p.n_tiles;
+      const int m_tile = 2 * (tile / p.n_tiles) + static_cast<int>(rank);
+      const int txi = m_tile % p.tiles_x;
+      const int tyi = (m_tile / p.tiles_x) % p.tiles_y;
+      const int img = m_tile / (p.tiles_x * p.tiles_y);
+      const int ox = txi * p.tw + tx, oy = tyi * p.th + ty;
+      const int n0 = n_tile * p.BN;
+      const bool valid = (img < p.n_img) && (ty < p.th) && (ox < p.W_out) && (oy < p.H_out);
+      const long long pix = (static_cast<long long>(img) * p.H_out + oy) * p.W_out + ox;
+
+      // bias of this N tile -> shared memory (double-buffered by tile parity; one named barrier per tile)
+      float* bs = bias_s[tcount & 1u];
+      if (et < p.BN) bs[et] = __ldg(p.bias + n0 + et);
+      named_bar_sync(1, kPairEpiWarps * 32);
+
+      mbar_wait(&acc_full_bar[acc], acc_ph);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((quad * 32u) << 16) + acc * kAccStride;
+      // one 16-column chunk: +bias -> SiLU -> (+residual) -> store.  Registers only (static indexing).
+      auto process = [&](const uint32_t (&vv)[16], int jj) {
+        const int col0 = n0 + jj * 16;
+        if (!(valid && col0 < p.Cout)) return;
+        uint4 r0 = make_uint4(0, 0, 0, 0), r1 = make_uint4(0, 0, 0, 0);
+        if (p.res != nullptr) {
+          const uint4* rp = reinterpret_cast<const uint4*>(p.res + pix * p.res_pix_stride + p.res_c_off + col0);
+          r0 = __ldg(rp);
+          r1 = __ldg(rp + 1);
+        }
+        float f[16];
+        const float4* b4 = reinterpret_cast<const float4*>(bs + jj * 16);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 bb = b4[q];
+          f[4 * q + 0] = __uint_as_float(vv[4 * q + 0]) + bb.x;
+          f[4 * q + 1] = __uint_as_float(vv[4 * q + 1]) + bb.y;
+          f[4 * q + 2] = __uint_as_float(vv[4 * q + 2]) + bb.z;
+          f[4 * q + 3] = __uint_as_float(vv[4 * q + 3]) + bb.w;
+        }
+        if (p.act) {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) f[e] = silu_fast(f[e]);
+        }
+        if (p.res != nullptr) {
+          const __half2* h0 = reinterpret_cast<const __half2*>(&r0);
+          const __half2* h1 = reinterpret_cast<const __half2*>(&r1);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 a = __half22float2(h0[e]);
+            const float2 b = __half22float2(h1[e]);
+            f[2 * e] += a.x;
+            f[2 * e + 1] += a.y;
+            f[8 + 2 * e] += b.x;
+            f[8 + 2 * e + 1] += b.y;
+          }
+        }
+        if (p.out_fp32) {
+          float* op = reinterpret_cast<float*>(p.out) + pix * p.out_pix_stride + p.out_c_off + col0;
+          if (col0 + 16 <= p.Cout) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              reinterpret_cast<float4*>(op)[e] = make_float4(f[4 * e], f[4 * e + 1], f[4 * e + 2], f[4 * e + 3]);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 16; ++e)
+              if (col0 + e < p.Cout) op[e] = f[e];
+          }
+        } else {
+          __half* op = reinterpret_cast<__half*>(p.out) + pix * p.out_pix_stride + p.out_c_off + col0;
+          if (col0 + 16 <= p.Cout) {
+            uint4 o0, o1;
+            __half2* q0 = reinterpret_cast<__half2*>(&o0);
+            __half2* q1 = reinterpret_cast<__half2*>(&o1);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              q0[e] = __floats2half2_rn(f[2 * e], f[2 * e + 1]);
+              q1[e] = __floats2half2_rn(f[8 + 2 * e], f[8 + 2 * e + 1]);
+            }
+            reinterpret_cast<uint4*>(op)[0] = o0;
+            reinterpret_cast<uint4*>(op)[1] = o1;
+          } else {
+#pragma unroll
+            for (int e = 0; e < 16; ++e)
+              if (col0 + e < p.Cout) op[e] = __float2half_rn(f[e]);
+          }
+        }
+      };
+      // TMEM loads run one chunk ahead of the math (two register buffers, statically indexed)
+      uint32_t va[16], vb[16];
+      int j = static_cast<int>(half);
+      if (j < nchunks) tmem_ld16(taddr + static_cast<uint32_t>(j * 16), va);
+      while (j < nchunks) {
+        tmem_ld_wait();
+        if (j + 2 < nchunks) tmem_ld16(taddr + static_cast<uint32_t>((j + 2) * 16), vb);
+        process(va, j);
+        j += 2;
+        if (j >= nchunks) break;
+        tmem_ld_wait();
+        if (j + 2 < nchunks) tmem_ld16(taddr + static_cast<uint32_t>((j + 2) * 16), va);
+        process(vb, j);
+        j += 2;
+      }
+      // all TMEM reads of this warp have completed (tcgen05.wait::ld): hand the accumulator stage back
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (leader) mbar_arrive(&acc_empty_bar[acc]);
+        else mbar_arrive_remote(&acc_empty_bar[acc], 0);
+      }
+    }
+  }
+
+  // both CTAs must be past every remote barrier access before either frees TMEM or exits
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc2(tmem_base, kTmemCols);
+  }
+}
+
+}  // namespace mdb

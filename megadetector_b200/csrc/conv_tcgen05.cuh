@@ -244,7 +244,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
               for (int e = 0; e < 4; ++e)
                 reinterpret_cast<float4*>(op)[e] = make_float4(f[4 * e], f[4 * e + 1], f[4 * e + 2], f[4 * e + 3]);
             } else {
-              for (int e = 0; e < 16 && col0 + e < p.Cout; ++e) op[e] = f[e];
+#pragma unroll
+              for (int e = 0; e < 16; ++e)
+                if (col0 + e < p.Cout) op[e] = f[e];
             }
           } else {
             __half* op = reinterpret_cast<__half*>(p.out) + pix * p.out_pix_stride + p.out_c_off + col0;
@@ -260,7 +262,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
               reinterpret_cast<uint4*>(op)[0] = o0;
               reinterpret_cast<uint4*>(op)[1] = o1;
             } else {
-              for (int e = 0; e < 16 && col0 + e < p.Cout; ++e) op[e] = __float2half_rn(f[e]);
+#pragma unroll
+              for (int e = 0; e < 16; ++e)
+                if (col0 + e < p.Cout) op[e] = __float2half_rn(f[e]);
             }
           }
         }

@@ -108,17 +108,24 @@ struct mdb_engine {
   PreImage* d_pre[2] = {nullptr, nullptr};
   NmsImageParams* h_nmsp[2] = {nullptr, nullptr};  // pinned
   NmsImageParams* d_nmsp[2] = {nullptr, nullptr};
-  float* d_det = nullptr;  // [max_batch][max_det][6]
-  int32_t* d_cnt = nullptr;
-  int32_t* d_anchor = nullptr;
-  float* h_det = nullptr;  // pinned mirrors
-  int32_t* h_cnt = nullptr;
-  int32_t* h_anchor = nullptr;
+  float* d_det[2] = {nullptr, nullptr};  // [max_batch][max_det][6], one per pipeline slot
+  int32_t* d_cnt[2] = {nullptr, nullptr};
+  int32_t* d_anchor[2] = {nullptr, nullptr};
+  float* h_det[2] = {nullptr, nullptr};  // pinned mirrors
+  int32_t* h_cnt[2] = {nullptr, nullptr};
+  int32_t* h_anchor[2] = {nullptr, nullptr};
+  cudaEvent_t ev_tt[2][4] = {{nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr}};
+  // what is staged in each slot (for mdb_bench_resident)
+  Plan* slot_plan[2] = {nullptr, nullptr};
+  int slot_n[2] = {0, 0};
+  float slot_max_scale[2] = {1.f, 1.f};
+  int last_slot = 0;
   // last-run bookkeeping for debug fetch
   Plan* last_plan = nullptr;
   int last_n = 0;
   float last_ms[4] = {0, 0, 0, 0};
   int64_t launches = 0;
+  int pipeline_split = 2;
   std::string err;
 };
 
@@ -268,7 +275,7 @@ void build_graph(Plan& P, const mdb_arch& A) {
   // keep the stem input and the raw heads alive to the end (debug fetch / decode)
   const int last = static_cast<int>(P.steps.size());
   P.bufs[P.stem_buf].first = 0;
-  P.bufs[P.stem_buf].last = std::max(P.bufs[P.stem_buf].last, 0);
+  P.bufs[P.stem_buf].last = last;
   for (int l = 0; l < 4; ++l) P.bufs[P.raw_buf[l]].last = last;
 }
 
@@ -414,14 +421,43 @@ struct ImgIn {
   int index;         // position in the caller's arrays
 };
 
-// One chunk (<= max_batch images of one letterboxed shape): H2D on the copy stream, everything else on
-// the compute stream; two staging slots so that the copy of chunk i+1 overlaps the compute of chunk i.
-void run_chunk(mdb_engine* e, Plan* P, const std::vector<ImgIn>& imgs, const std::vector<LetterboxGeom>& geoms,
-               bool preprocessed, float conf_thres, int slot, float* det_out, int32_t* det_count,
-               int32_t* kept_anchor, bool record_timing) {
-  const int n = static_cast<int>(imgs.size());
+// One chunk (<= max_batch images of one letterboxed shape).  enqueue_chunk() queues the H2D copies on the copy
+// stream and K1..K8 + the result D2H on the compute stream and returns; finish_chunk() waits for it and scatters
+// the results.  Two slots => the copies of chunk i+1 overlap the kernels of chunk i.
+struct Pending {
+  int slot;
+  Plan* plan;
+  std::vector<ImgIn> imgs;
+};
+
+void stage_compute(mdb_engine* e, Plan* P, int n, int slot, float conf_thres, int stages_mask, bool timing) {
+  cudaStream_t st = e->st_compute;
   const int max_det = e->cfg.max_det;
-  // ---- stage sources ----
+  const int no = e->cfg.arch.nc + 5;
+  if (timing) MDB_CUDA(cudaEventRecord(e->ev_tt[slot][0], st));
+  if (stages_mask & 1) {
+    View stem = P->view(VView{P->stem_buf, 0, 16});
+    preprocess_launch(e->d_pre[slot], n, P->H, P->W, static_cast<__half*>(stem.base), e->slot_max_scale[slot], st);
+    e->launches++;
+  }
+  if (timing) MDB_CUDA(cudaEventRecord(e->ev_tt[slot][1], st));
+  if (stages_mask & 2) run_network(e, P, n, st);
+  if (timing) MDB_CUDA(cudaEventRecord(e->ev_tt[slot][2], st));
+  if (stages_mask & 4) {
+    decode_launch(P->lv, n, no, P->anchors, P->pred, st);
+    nms_launch(P->pred, n, P->anchors, no, conf_thres, float_floor_of_double(static_cast<double>(e->cfg.iou_thres)),
+               max_det, e->d_nmsp[slot], P->nms_scratch, e->d_det[slot], e->d_cnt[slot], e->d_anchor[slot], st);
+    e->launches += 2;
+    MDB_CUDA(cudaMemcpyAsync(e->h_det[slot], e->d_det[slot], sizeof(float) * n * max_det * 6, cudaMemcpyDeviceToHost, st));
+    MDB_CUDA(cudaMemcpyAsync(e->h_cnt[slot], e->d_cnt[slot], sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
+    MDB_CUDA(cudaMemcpyAsync(e->h_anchor[slot], e->d_anchor[slot], sizeof(int32_t) * n * max_det, cudaMemcpyDeviceToHost, st));
+  }
+  if (timing) MDB_CUDA(cudaEventRecord(e->ev_tt[slot][3], st));
+}
+
+void enqueue_chunk(mdb_engine* e, Plan* P, const std::vector<ImgIn>& imgs, const std::vector<LetterboxGeom>& geoms,
+                   float conf_thres, int slot) {
+  const int n = static_cast<int>(imgs.size());
   size_t total = 0;
   std::vector<size_t> offs(n);
   for (int i = 0; i < n; ++i) {
@@ -457,51 +493,39 @@ void run_chunk(mdb_engine* e, Plan* P, const std::vector<ImgIn>& imgs, const std
     np.gain = static_cast<float>(gain); np.pad_x = static_cast<float>(padx); np.pad_y = static_cast<float>(pady);
     np.max_x = static_cast<float>(im.src_w); np.max_y = static_cast<float>(im.src_h);
   }
-  (void)preprocessed;
   MDB_CUDA(cudaMemcpyAsync(e->d_pre[slot], e->h_pre[slot], sizeof(PreImage) * n, cudaMemcpyHostToDevice, e->st_copy));
   MDB_CUDA(cudaMemcpyAsync(e->d_nmsp[slot], e->h_nmsp[slot], sizeof(NmsImageParams) * n, cudaMemcpyHostToDevice, e->st_copy));
   MDB_CUDA(cudaEventRecord(e->ev_copy_done[slot], e->st_copy));
+  e->slot_plan[slot] = P;
+  e->slot_n[slot] = n;
+  e->slot_max_scale[slot] = max_scale;
+  e->last_slot = slot;
+  MDB_CUDA(cudaStreamWaitEvent(e->st_compute, e->ev_copy_done[slot], 0));
+  stage_compute(e, P, n, slot, conf_thres, 7, true);
+  MDB_CUDA(cudaEventRecord(e->ev_compute_done[slot], e->st_compute));
+}
 
-  // ---- compute ----
-  cudaStream_t st = e->st_compute;
-  if (record_timing) MDB_CUDA(cudaEventRecord(e->ev_t[0], st));
-  MDB_CUDA(cudaStreamWaitEvent(st, e->ev_copy_done[slot], 0));
-  View stem = P->view(VView{P->stem_buf, 0, 16});
-  preprocess_launch(e->d_pre[slot], n, P->H, P->W, static_cast<__half*>(stem.base), max_scale, st);
-  e->launches++;
-  if (record_timing) MDB_CUDA(cudaEventRecord(e->ev_t[1], st));
-  run_network(e, P, n, st);
-  if (record_timing) MDB_CUDA(cudaEventRecord(e->ev_t[2], st));
-  const int no = e->cfg.arch.nc + 5;
-  decode_launch(P->lv, n, no, P->anchors, P->pred, st);
-  nms_launch(P->pred, n, P->anchors, no, conf_thres, float_floor_of_double(static_cast<double>(e->cfg.iou_thres)),
-             max_det, e->d_nmsp[slot], P->nms_scratch, e->d_det, e->d_cnt, e->d_anchor, st);
-  e->launches += 2;
-  MDB_CUDA(cudaMemcpyAsync(e->h_det, e->d_det, sizeof(float) * n * max_det * 6, cudaMemcpyDeviceToHost, st));
-  MDB_CUDA(cudaMemcpyAsync(e->h_cnt, e->d_cnt, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
-  MDB_CUDA(cudaMemcpyAsync(e->h_anchor, e->d_anchor, sizeof(int32_t) * n * max_det, cudaMemcpyDeviceToHost, st));
-  if (record_timing) MDB_CUDA(cudaEventRecord(e->ev_t[3], st));
-  MDB_CUDA(cudaEventRecord(e->ev_compute_done[slot], st));
-  // results of this chunk are consumed before the next chunk reuses the pinned mirrors
-  MDB_CUDA(cudaStreamSynchronize(st));
+void finish_chunk(mdb_engine* e, const Pending& pd, float* det_out, int32_t* det_count, int32_t* kept_anchor) {
+  const int slot = pd.slot;
+  const int n = static_cast<int>(pd.imgs.size());
+  const int max_det = e->cfg.max_det;
+  MDB_CUDA(cudaEventSynchronize(e->ev_compute_done[slot]));
   for (int i = 0; i < n; ++i) {
-    const int dst = imgs[i].index;
-    det_count[dst] = e->h_cnt[i];
-    memcpy(det_out + static_cast<size_t>(dst) * max_det * 6, e->h_det + static_cast<size_t>(i) * max_det * 6,
+    const int dst = pd.imgs[i].index;
+    det_count[dst] = e->h_cnt[slot][i];
+    memcpy(det_out + static_cast<size_t>(dst) * max_det * 6, e->h_det[slot] + static_cast<size_t>(i) * max_det * 6,
            sizeof(float) * max_det * 6);
     if (kept_anchor)
-      memcpy(kept_anchor + static_cast<size_t>(dst) * max_det, e->h_anchor + static_cast<size_t>(i) * max_det,
+      memcpy(kept_anchor + static_cast<size_t>(dst) * max_det, e->h_anchor[slot] + static_cast<size_t>(i) * max_det,
              sizeof(int32_t) * max_det);
   }
-  if (record_timing) {
-    float a = 0, b = 0, c = 0, d = 0;
-    cudaEventElapsedTime(&a, e->ev_t[0], e->ev_t[1]);
-    cudaEventElapsedTime(&b, e->ev_t[1], e->ev_t[2]);
-    cudaEventElapsedTime(&c, e->ev_t[2], e->ev_t[3]);
-    cudaEventElapsedTime(&d, e->ev_t[0], e->ev_t[3]);
-    e->last_ms[0] += a; e->last_ms[1] += b; e->last_ms[2] += c; e->last_ms[3] += d;
-  }
-  e->last_plan = P;
+  float a = 0, b = 0, c = 0, d = 0;
+  cudaEventElapsedTime(&a, e->ev_tt[slot][0], e->ev_tt[slot][1]);
+  cudaEventElapsedTime(&b, e->ev_tt[slot][1], e->ev_tt[slot][2]);
+  cudaEventElapsedTime(&c, e->ev_tt[slot][2], e->ev_tt[slot][3]);
+  cudaEventElapsedTime(&d, e->ev_tt[slot][0], e->ev_tt[slot][3]);
+  e->last_ms[0] += a; e->last_ms[1] += b; e->last_ms[2] += c; e->last_ms[3] += d;
+  e->last_plan = pd.plan;
   e->last_n = n;
 }
 
@@ -529,28 +553,51 @@ int infer_common(mdb_engine* e, std::vector<ImgIn>& all, bool preprocessed, floa
     status[im.index] = MDB_IMG_OK;
   }
   int slot = 0;
+  std::vector<Pending> inflight;
+  auto drain_one = [&]() {
+    Pending pd = inflight.front();
+    inflight.erase(inflight.begin());
+    finish_chunk(e, pd, det_out, det_count, kept_anchor);
+  };
   for (auto& kv : groups) {
-    Plan* P = nullptr;
     try {
-      P = get_plan(e, kv.first.first, kv.first.second);
+      Plan* P = get_plan(e, kv.first.first, kv.first.second);
       const std::vector<int>& ids = kv.second;
-      for (size_t b = 0; b < ids.size(); b += cfg.max_batch) {
-        std::vector<ImgIn> chunk;
+      // chunking: full max_batch chunks when there are several; otherwise two halves so that the upload of
+      // the second half overlaps the kernels of the first
+      size_t chunk = static_cast<size_t>(cfg.max_batch);
+      if (ids.size() <= chunk && ids.size() > 16 && e->pipeline_split > 1)
+        chunk = (ids.size() + e->pipeline_split - 1) / e->pipeline_split;
+      for (size_t b = 0; b < ids.size(); b += chunk) {
+        Pending pd;
+        pd.slot = slot;
+        pd.plan = P;
         std::vector<LetterboxGeom> cg;
-        for (size_t j = b; j < std::min(ids.size(), b + static_cast<size_t>(cfg.max_batch)); ++j) {
-          chunk.push_back(all[ids[j]]);
+        for (size_t j = b; j < std::min(ids.size(), b + chunk); ++j) {
+          pd.imgs.push_back(all[ids[j]]);
           cg.push_back(geom[ids[j]]);
         }
-        run_chunk(e, P, chunk, cg, preprocessed, conf_thres, slot, det_out, det_count, kept_anchor, true);
+        if (inflight.size() == 2) drain_one();
+        enqueue_chunk(e, P, pd.imgs, cg, conf_thres, slot);
+        inflight.push_back(pd);
         slot ^= 1;
       }
     } catch (const CudaError& ex) {
       // a whole shape group fails together (pytorch_detector.py:1236-1249)
       e->err = ex.msg;
       for (int id : kv.second) { status[all[id].index] = MDB_IMG_INFER_FAILED; det_count[all[id].index] = 0; }
+      // chunks of this group that were already queued must not be reported as good
+      for (auto it = inflight.begin(); it != inflight.end();)
+        it = (it->plan && it->plan->H == kv.first.first && it->plan->W == kv.first.second) ? inflight.erase(it) : it + 1;
       cudaError_t sticky = cudaGetLastError();
       if (sticky != cudaSuccess && cudaDeviceSynchronize() != cudaSuccess) return MDB_ERR_CUDA;
     }
+  }
+  try {
+    while (!inflight.empty()) drain_one();
+  } catch (const CudaError& ex) {
+    e->err = ex.msg;
+    return MDB_ERR_CUDA;
   }
   (void)n;
   return MDB_OK;
@@ -620,12 +667,15 @@ int mdb_create(mdb_engine** out, const mdb_config* cfg) {
     }
     for (int i = 0; i < 4; ++i) MDB_CUDA(cudaEventCreate(&e->ev_t[i]));
     const size_t nd = static_cast<size_t>(cfg->max_batch) * cfg->max_det;
-    MDB_CUDA(cudaMalloc(&e->d_det, nd * 6 * sizeof(float)));
-    MDB_CUDA(cudaMalloc(&e->d_cnt, cfg->max_batch * sizeof(int32_t)));
-    MDB_CUDA(cudaMalloc(&e->d_anchor, nd * sizeof(int32_t)));
-    MDB_CUDA(cudaHostAlloc(&e->h_det, nd * 6 * sizeof(float), cudaHostAllocDefault));
-    MDB_CUDA(cudaHostAlloc(&e->h_cnt, cfg->max_batch * sizeof(int32_t), cudaHostAllocDefault));
-    MDB_CUDA(cudaHostAlloc(&e->h_anchor, nd * sizeof(int32_t), cudaHostAllocDefault));
+    for (int i = 0; i < 2; ++i) {
+      MDB_CUDA(cudaMalloc(&e->d_det[i], nd * 6 * sizeof(float)));
+      MDB_CUDA(cudaMalloc(&e->d_cnt[i], cfg->max_batch * sizeof(int32_t)));
+      MDB_CUDA(cudaMalloc(&e->d_anchor[i], nd * sizeof(int32_t)));
+      MDB_CUDA(cudaHostAlloc(&e->h_det[i], nd * 6 * sizeof(float), cudaHostAllocDefault));
+      MDB_CUDA(cudaHostAlloc(&e->h_cnt[i], cfg->max_batch * sizeof(int32_t), cudaHostAllocDefault));
+      MDB_CUDA(cudaHostAlloc(&e->h_anchor[i], nd * sizeof(int32_t), cudaHostAllocDefault));
+      for (int j = 0; j < 4; ++j) MDB_CUDA(cudaEventCreate(&e->ev_tt[i][j]));
+    }
     preprocess_init_constants();
   } catch (const CudaError& ex) {
     g_create_error = ex.msg;
@@ -653,10 +703,13 @@ void mdb_destroy(mdb_engine* e) {
     if (e->ev_compute_done[i]) cudaEventDestroy(e->ev_compute_done[i]);
   }
   for (int i = 0; i < 4; ++i) if (e->ev_t[i]) cudaEventDestroy(e->ev_t[i]);
-  cudaFree(e->d_det); cudaFree(e->d_cnt); cudaFree(e->d_anchor);
-  if (e->h_det) cudaFreeHost(e->h_det);
-  if (e->h_cnt) cudaFreeHost(e->h_cnt);
-  if (e->h_anchor) cudaFreeHost(e->h_anchor);
+  for (int i = 0; i < 2; ++i) {
+    cudaFree(e->d_det[i]); cudaFree(e->d_cnt[i]); cudaFree(e->d_anchor[i]);
+    if (e->h_det[i]) cudaFreeHost(e->h_det[i]);
+    if (e->h_cnt[i]) cudaFreeHost(e->h_cnt[i]);
+    if (e->h_anchor[i]) cudaFreeHost(e->h_anchor[i]);
+    for (int j = 0; j < 4; ++j) if (e->ev_tt[i][j]) cudaEventDestroy(e->ev_tt[i][j]);
+  }
   if (e->st_compute) cudaStreamDestroy(e->st_compute);
   if (e->st_copy) cudaStreamDestroy(e->st_copy);
   delete e;
@@ -740,6 +793,92 @@ int mdb_infer_preprocessed(mdb_engine* e, const uint8_t* const* lb_hwc, const in
   } catch (const CudaError& ex) {
     return fail(e, MDB_ERR_CUDA, ex.msg);
   }
+}
+
+int mdb_set_image_size(mdb_engine* e, int32_t img_size) {
+  if (!e || img_size < 64 || img_size > 8192) return fail(e, MDB_ERR_ARG, "image size out of range");
+  e->cfg.img_size = img_size;
+  return MDB_OK;
+}
+
+int mdb_set_pipeline_split(mdb_engine* e, int32_t parts) {
+  if (!e || parts < 1 || parts > 8) return fail(e, MDB_ERR_ARG, "pipeline split out of range");
+  e->pipeline_split = parts;
+  return MDB_OK;
+}
+
+int mdb_bench_resident(mdb_engine* e, int32_t iters, float conf_thres, int32_t stages_mask, float* ms_total) {
+  if (!e || iters < 1 || !ms_total) return fail(e, MDB_ERR_ARG, "bad argument");
+  const int slot = e->last_slot;
+  Plan* P = e->slot_plan[slot];
+  if (!P || e->slot_n[slot] <= 0) return fail(e, MDB_ERR_STATE, "no batch is staged: call mdb_infer_batch first");
+  try {
+    MDB_CUDA(cudaSetDevice(e->cfg.device));
+    cudaStream_t st = e->st_compute;
+    MDB_CUDA(cudaStreamSynchronize(st));
+    MDB_CUDA(cudaEventRecord(e->ev_t[0], st));
+    for (int i = 0; i < iters; ++i) stage_compute(e, P, e->slot_n[slot], slot, conf_thres, stages_mask, false);
+    MDB_CUDA(cudaEventRecord(e->ev_t[1], st));
+    MDB_CUDA(cudaEventSynchronize(e->ev_t[1]));
+    MDB_CUDA(cudaEventElapsedTime(ms_total, e->ev_t[0], e->ev_t[1]));
+  } catch (const CudaError& ex) {
+    return fail(e, MDB_ERR_CUDA, ex.msg);
+  }
+  return MDB_OK;
+}
+
+int mdb_profile_steps(mdb_engine* e, int32_t iters, float* ms_out, double* macs_out, char* names_out,
+                      int32_t name_stride, int32_t cap, int32_t* n_steps) {
+  if (!e || iters < 1 || !n_steps) return fail(e, MDB_ERR_ARG, "bad argument");
+  const int slot = e->last_slot;
+  Plan* P = e->slot_plan[slot];
+  if (!P || e->slot_n[slot] <= 0) return fail(e, MDB_ERR_STATE, "no batch is staged: call mdb_infer_batch first");
+  try {
+    MDB_CUDA(cudaSetDevice(e->cfg.device));
+    cudaStream_t st = e->st_compute;
+    const int n = e->slot_n[slot];
+    const int total = static_cast<int>(P->steps.size());
+    *n_steps = total;
+    for (int i = 0; i < total && i < cap; ++i) {
+      Step& s = P->steps[i];
+      MDB_CUDA(cudaStreamSynchronize(st));
+      MDB_CUDA(cudaEventRecord(e->ev_t[0], st));
+      for (int it = 0; it < iters; ++it) {
+        if (s.kind == STEP_CONV) conv_launch(s.op, n, st);
+        else if (s.kind == STEP_UPSAMPLE) upsample2x_launch(P->view(s.in), P->view(s.out), n, st);
+        else {
+          const VBuf& b = P->bufs[s.in.buf];
+          const int hs = b.C / 4;
+          View cat = P->view(s.in);
+          View s1 = cat, p1 = cat, p2 = cat, p3 = cat;
+          s1.c_off = 0; p1.c_off = hs; p2.c_off = 2 * hs; p3.c_off = 3 * hs;
+          s1.C = p1.C = p2.C = p3.C = hs;
+          sppf_pool_launch(s1, p1, p2, p3, n, st);
+        }
+      }
+      MDB_CUDA(cudaEventRecord(e->ev_t[1], st));
+      MDB_CUDA(cudaEventSynchronize(e->ev_t[1]));
+      float ms = 0;
+      MDB_CUDA(cudaEventElapsedTime(&ms, e->ev_t[0], e->ev_t[1]));
+      e->launches += iters;
+      if (ms_out) ms_out[i] = ms / iters;
+      if (macs_out) macs_out[i] = s.kind == STEP_CONV ? conv_macs_per_image(s.op) * n : 0.0;
+      if (names_out && name_stride > 1) {
+        char buf[160];
+        if (s.kind == STEP_CONV) {
+          const VBuf& ib = P->bufs[s.in.buf];
+          snprintf(buf, sizeof(buf), "%s k%d s%d %dx%d %d->%d", s.name.c_str(), s.k, s.s, ib.H, ib.W, s.in.C, s.cout);
+        } else {
+          snprintf(buf, sizeof(buf), "%s", s.name.c_str());
+        }
+        strncpy(names_out + static_cast<size_t>(i) * name_stride, buf, name_stride - 1);
+        names_out[static_cast<size_t>(i) * name_stride + name_stride - 1] = 0;
+      }
+    }
+  } catch (const CudaError& ex) {
+    return fail(e, MDB_ERR_CUDA, ex.msg);
+  }
+  return MDB_OK;
 }
 
 int mdb_last_timing(mdb_engine* e, float* ms4) {

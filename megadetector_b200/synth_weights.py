@@ -6,7 +6,8 @@ no checkpoint offline, so this module manufactures one.  Plain random weights ar
 residual network without normalisation layers (BN is folded): activations explode or die, every anchor gets the
 same score and threshold/NMS degenerate into pure tie-breaking (SURVEY.md par. 8d).  So the generator draws
 N(0, 1/fan_in) weights and then walks the graph once over a letterboxed synthetic benchmark image, rescaling
-each conv so that its pre-activation std is 1 (0.7 on residual branches) and shaping the Detect logits
+each conv so that its pre-activation std is 1 (0.7 on residual branches; with SiLU that puts the stack close to the
+edge of chaos, perturbation gain ~1.07 per layer) and shaping the Detect logits
 (objectness ~ N(-13, 2.5): 10^3..10^4 anchors above the 1e-5 batch-path threshold, 10^1..10^2 above 0.005).
 
 This is a workload generator (it plays the role of a checkpoint file), not part of the detection path and not
@@ -87,6 +88,8 @@ class _Calibrator:
                     wt[a, c] *= sc
                     b[a, c] = tgt_mean - float(v.mean()) * sc
         else:
+            # one scale per layer (not per channel: per-channel statistics of a single calibration image do not
+            # transfer to other images and make the network chaotic)
             tgt = 0.7 if ('.m.' in name and name.endswith('cv2.conv')) else 1.0
             w[name + '.weight'] *= tgt / float(y.std() + 1e-12)
         y = F.conv2d(x, w[name + '.weight'], w[name + '.bias'], stride=s, padding=p)

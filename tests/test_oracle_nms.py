@@ -52,3 +52,14 @@ def test_threshold_is_compared_in_float32():
     x[0, :, 5] = 1.0
     det, _ = onms.nms(x, conf_thres=0.3)[0]
     assert det.shape[0] == 0
+
+
+def test_torchvision_backed_variant_agrees():
+    import torch
+    z, names = _cases()
+    for name in names:
+        pred = z[name + '/pred']
+        thr, iou = z[name + '/thr']
+        res = onms.nms_torch(torch.from_numpy(pred.copy()), conf_thres=thr, iou_thres=iou)
+        for b, det in enumerate(res):
+            assert_dets_equal_modulo_ties(z['{}/det{}'.format(name, b)], det.numpy(), '{}[{}]'.format(name, b))

@@ -1,0 +1,34 @@
+"""Runs a few real MDv5 layer shapes through mdb_op_conv2d (for ncu captures and quick timing on the GPU box)."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+
+from megadetector_b200 import _capi
+
+CASES = {
+    'c1x1_160': (16, 96, 160, 160, 160, 1, 1, 0, False),
+    'c1x1_320': (16, 48, 80, 320, 320, 1, 1, 0, False),
+    'c3x3_80': (16, 192, 320, 80, 80, 3, 1, 1, True),
+    'c3x3_160': (16, 96, 160, 160, 160, 3, 1, 1, True),
+    'c3x3_320': (16, 48, 80, 320, 320, 3, 1, 1, True),
+    'c3x3_480': (16, 24, 40, 480, 480, 3, 1, 1, True),
+    'stem': (16, 384, 640, 16, 80, 3, 1, 1, False),
+    's2_80_160': (16, 384, 640, 80, 160, 3, 2, 1, False),
+}
+names = sys.argv[1].split(',') if len(sys.argv) > 1 else list(CASES)
+iters = int(sys.argv[2]) if len(sys.argv) > 2 else 10
+e = _capi.Engine(_capi.make_config(max_batch=16))
+rng = np.random.default_rng(0)
+for nm in names:
+    n, h, w, ci, co, k, s, p, res = CASES[nm]
+    x = rng.standard_normal((n, h, w, ci)).astype(np.float16)
+    wt = (rng.standard_normal((co, ci, k, k)) / np.sqrt(ci * k * k)).astype(np.float32)
+    b = np.zeros(co, np.float32)
+    ho, wo = (h + 2 * p - k) // s + 1, (w + 2 * p - k) // s + 1
+    r = rng.standard_normal((n, ho, wo, co)).astype(np.float16) if res else None
+    _, ms = e.op_conv2d(x, wt, b, k, s, p, act=True, residual=r, iters=iters)
+    fl = 2.0 * n * ho * wo * co * ci * k * k
+    byt = 2.0 * n * (h * w * ci + ho * wo * co * (2 if res else 1))
+    print('%-10s %8.4f ms  %7.1f TFLOP/s  %6.0f GB/s (in+out%s)' % (nm, ms, fl / ms / 1e9, byt / ms / 1e6, '+res' if res else ''), flush=True)
