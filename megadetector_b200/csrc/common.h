@@ -70,6 +70,7 @@ struct ConvDesc {
   const void* wgt = nullptr;  // device fp16 [cout_pad][k][k][cin]
   const float* bias = nullptr;  // device fp32 [cout_pad]
   int cout = 0, cout_pad = 0;
+  int cin_pad = 0;  // channels per filter tap in the packed weights (>= in.C, zero padded)
   int k = 1, s = 1, pad = 0, act = 1;
 };
 ConvOp* conv_build(const ConvDesc& d, int num_sms);
@@ -81,7 +82,7 @@ int conv_pick_bn(int cout_pad);
 // weight re-layout helpers (host): PyTorch [co][ci][k][k] fp32 -> [co_pad][k][k][ci_pad] fp16
 void pack_weights_khwc(const float* w, int co, int ci, int k, int co_pad, int ci_pad, std::vector<__half>& out);
 // stem: [co][3][6][6] -> 3x3 conv over the 2x2 space-to-depth input with 16 (12 used) channels
-void pack_weights_stem_s2d(const float* w, int co, int co_pad, std::vector<__half>& out);
+void pack_weights_stem_s2d(const float* w, int co, int co_pad, int ci_pad, std::vector<__half>& out);
 
 // ---------------------------------------------------------------------------------------------
 // K1 letterbox / preprocess (preprocess.cu)

@@ -4,6 +4,7 @@
 
 #include "common.h"
 #include <cstdlib>
+#include <vector>
 
 #include "conv_pair_tcgen05.cuh"
 #include "conv_tcgen05.cuh"
@@ -85,11 +86,16 @@ ConvOp* conv_build(const ConvDesc& d, int num_sms) {
   try {
     const View& in = d.in;
     const View& out = d.out;
-    MDB_REQUIRE(in.C % 16 == 0, "conv input channels must be a multiple of 16");
+    MDB_REQUIRE(in.C % 8 == 0, "conv input channels must be a multiple of 8");
+    MDB_REQUIRE(d.cin_pad >= in.C && d.cin_pad % 16 == 0, "bad cin_pad");
     MDB_REQUIRE(d.cout_pad % 16 == 0 && d.cout_pad >= d.cout, "bad cout_pad");
     MDB_REQUIRE(d.s == 1 || d.s == 2, "stride must be 1 or 2");
     MDB_REQUIRE(out.C >= d.cout, "output view too narrow");
-    const int kc = in.C % 64 == 0 ? 64 : (in.C % 32 == 0 ? 32 : 16);
+    // K chunk = one swizzle row of channels.  Always 64 (128-byte rows) when the packed weights allow it: short
+    // rows (32/64 B) make the TMA unit request-bound (measured: 3x3 80->80 ran 15x off the MMA floor with 32-byte
+    // rows).  Channels beyond in.C inside the last chunk are zero-filled by the TMA unit (no memory traffic) and
+    // meet zero weights.
+    const int kc = d.cin_pad % 64 == 0 ? 64 : (d.cin_pad % 32 == 0 ? 32 : 16);
     op->kc = kc;
     op->num_sms = num_sms;
     ConvParams& p = op->p;
@@ -108,8 +114,8 @@ ConvOp* conv_build(const ConvDesc& d, int num_sms) {
     p.KH = p.KW = d.k;
     p.stride = d.s;
     p.pad = d.pad;
-    p.Cin = in.C;
-    p.chunks = in.C / kc;
+    p.Cin = d.cin_pad;
+    p.chunks = d.cin_pad / kc;
     p.bias = d.bias;
     p.out = out.base;
     p.out_pix_stride = out.Ctot;
@@ -145,23 +151,31 @@ ConvOp* conv_build(const ConvDesc& d, int num_sms) {
     op->pair = use_pair_kernel();
     if (op->pair) {
       // CTA pair: each CTA stages half of the B tile
-      make_wgt_tmap(&op->tmB, d.wgt, d.k * d.k * in.C, d.cout_pad, kc, p.BN / 2);
+      make_wgt_tmap(&op->tmB, d.wgt, d.k * d.k * d.cin_pad, d.cout_pad, kc, p.BN / 2);
       PairParams& q = op->pp;
       q.H_out = p.H_out; q.W_out = p.W_out; q.tw = p.tw; q.th = p.th;
       q.n_tiles = p.n_tiles; q.BN = p.BN; q.Cout = p.Cout;
       q.KH = p.KH; q.KW = p.KW; q.stride = p.stride; q.pad = p.pad;
       q.chunks = p.chunks; q.Cin = p.Cin;
       q.total_chunks = d.k * d.k * p.chunks;
-      q.cps = 64 / kc;
+      q.cps = 1;
       q.bias = p.bias; q.out = p.out; q.out_pix_stride = p.out_pix_stride; q.out_c_off = p.out_c_off;
       q.out_fp32 = p.out_fp32; q.res = p.res; q.res_pix_stride = p.res_pix_stride; q.res_c_off = p.res_c_off;
       q.act = p.act;
       q.idesc = make_idesc_f16(256, static_cast<uint32_t>(p.BN));
+      q.dbg = nullptr;
+      {
+        const int oa = out.fp32 ? 8 : 16;  // elements per 32 bytes
+        bool wide = (out.Ctot % oa == 0) && (out.c_off % oa == 0) && (reinterpret_cast<uintptr_t>(out.base) % 32 == 0);
+        if (d.res.base)
+          wide = wide && (d.res.Ctot % 16 == 0) && (d.res.c_off % 16 == 0) && (reinterpret_cast<uintptr_t>(d.res.base) % 32 == 0);
+        q.wide = wide ? 1 : 0;
+      }
       const size_t a_chunk = static_cast<size_t>(kTileM) * kc * 2;
       const size_t b_chunk = (static_cast<size_t>(p.BN / 2) * kc * 2 + 1023) & ~static_cast<size_t>(1023);
       const size_t stage = static_cast<size_t>(q.cps) * (a_chunk + b_chunk);
       const size_t budget = 227 * 1024 - 4096;  // static: barriers + bias staging; alignment slack
-      const int stage_iters = (q.total_chunks + q.cps - 1) / q.cps;
+      const int stage_iters = q.total_chunks;
       int stages = static_cast<int>(std::min<size_t>(kPairMaxStages, (budget - 1024) / stage));
       stages = std::max(2, std::min(stages, std::max(2, stage_iters * 2)));
       q.stages = stages;
@@ -171,7 +185,7 @@ ConvOp* conv_build(const ConvDesc& d, int num_sms) {
       else set_smem_attr_pair<16>(op->smem);
       return op;
     }
-    make_wgt_tmap(&op->tmB, d.wgt, d.k * d.k * in.C, d.cout_pad, kc, p.BN);
+    make_wgt_tmap(&op->tmB, d.wgt, d.k * d.k * d.cin_pad, d.cout_pad, kc, p.BN);
 
     const size_t a_bytes = static_cast<size_t>(kTileM) * kc * 2;
     const size_t b_bytes = (static_cast<size_t>(p.BN) * kc * 2 + 1023) & ~static_cast<size_t>(1023);
@@ -212,6 +226,13 @@ static void conv_launch_pair(ConvOp* op, int n_img, cudaStream_t st) {
   if (total <= 0) return;
   const int clusters = static_cast<int>(std::min<long long>(total, op->num_sms / 2));
   const int grid = clusters * 2;
+  static const bool debug = getenv("MDB_CONV_DEBUG") && getenv("MDB_CONV_DEBUG")[0] == '1';
+  long long* d_dbg = nullptr;
+  if (debug) {
+    MDB_CUDA(cudaMalloc(&d_dbg, sizeof(long long) * 8 * grid));
+    MDB_CUDA(cudaMemsetAsync(d_dbg, 0, sizeof(long long) * 8 * grid, st));
+  }
+  p.dbg = d_dbg;
   if (op->kc == 64)
     conv_pair_kernel<64><<<grid, kPairThreads, op->smem, st>>>(op->tmA[0], op->tmA[1], op->tmA[2], op->tmA[3], op->tmB, p);
   else if (op->kc == 32)
@@ -219,6 +240,23 @@ static void conv_launch_pair(ConvOp* op, int n_img, cudaStream_t st) {
   else
     conv_pair_kernel<16><<<grid, kPairThreads, op->smem, st>>>(op->tmA[0], op->tmA[1], op->tmA[2], op->tmA[3], op->tmB, p);
   MDB_CUDA(cudaGetLastError());
+  if (debug) {
+    std::vector<long long> h(static_cast<size_t>(8) * grid);
+    MDB_CUDA(cudaStreamSynchronize(st));
+    MDB_CUDA(cudaMemcpy(h.data(), d_dbg, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost));
+    cudaFree(d_dbg);
+    double prod_tot = 0, prod_wait = 0, its = 0, mma_tot = 0, mma_wfull = 0, mma_wacc = 0, tiles = 0;
+    int leaders = 0;
+    for (int b = 0; b < grid; ++b) {
+      prod_tot += h[b * 8 + 0]; prod_wait += h[b * 8 + 1]; its += h[b * 8 + 2];
+      if (b % 2 == 0) { mma_tot += h[b * 8 + 4]; mma_wfull += h[b * 8 + 5]; mma_wacc += h[b * 8 + 6]; tiles += h[b * 8 + 7]; ++leaders; }
+    }
+    fprintf(stderr,
+            "[conv dbg] grid %d BN %d stages %d cps %d tiles/cluster %.1f | producer: %.0f cyc total, %.1f%% waiting on empty, "
+            "%.0f cyc/stage | mma thread: %.0f cyc total, %.1f%% waiting on full, %.1f%% waiting on acc_empty, %.0f cyc/tile\n",
+            grid, p.BN, p.stages, p.cps, tiles / leaders, prod_tot / grid, 100.0 * prod_wait / prod_tot, prod_tot / its,
+            mma_tot / leaders, 100.0 * mma_wfull / mma_tot, 100.0 * mma_wacc / mma_tot, mma_tot / tiles);
+  }
 }
 
 void conv_launch(ConvOp* op, int n_img, cudaStream_t st) {
@@ -265,16 +303,16 @@ void pack_weights_khwc(const float* w, int co, int ci, int k, int co_pad, int ci
               __float2half_rn(w[((static_cast<size_t>(o) * ci + c) * k + y) * k + x]);
 }
 
-void pack_weights_stem_s2d(const float* w, int co, int co_pad, std::vector<__half>& out) {
+void pack_weights_stem_s2d(const float* w, int co, int co_pad, int ci_pad, std::vector<__half>& out) {
   // 6x6 stride-2 pad-2 conv over RGB == 3x3 stride-1 pad-1 conv over the 2x2 space-to-depth image whose
   // channel is (py*2+px)*3+c:  W'[o][a][b][(py*2+px)*3+c] = W[o][c][2a+py][2b+px]
-  out.assign(static_cast<size_t>(co_pad) * 9 * 16, __float2half(0.f));
+  out.assign(static_cast<size_t>(co_pad) * 9 * ci_pad, __float2half(0.f));
   for (int o = 0; o < co; ++o)
     for (int c = 0; c < 3; ++c)
       for (int ky = 0; ky < 6; ++ky)
         for (int kx = 0; kx < 6; ++kx) {
           const int a = ky / 2, py = ky % 2, b = kx / 2, px = kx % 2;
-          out[((static_cast<size_t>(o) * 3 + a) * 3 + b) * 16 + (py * 2 + px) * 3 + c] =
+          out[((static_cast<size_t>(o) * 3 + a) * 3 + b) * ci_pad + (py * 2 + px) * 3 + c] =
               __float2half_rn(w[((static_cast<size_t>(o) * 3 + c) * 6 + ky) * 6 + kx]);
         }
 }

@@ -9,14 +9,14 @@
 //     CTAs' shared memory.  Operand bytes per MAC drop by 1.4-1.8x, and shared-memory read pressure with them.
 //   * every pipeline stage now carries 64 K-elements regardless of the swizzle width (1/2/4 TMA boxes of
 //     64/32/16 channels), so the C_in = 80 and C_in = 16 layers no longer pay one mbarrier round trip per MMA.
-//   * the epilogue was the bottleneck of every 1x1 layer (17.8 k cycles per 128x160 tile): now 8 warps
-//     (two per TMEM lane quadrant, interleaved 16-column chunks), TMEM loads issued one chunk ahead, bias from
+//   * the epilogue was the bottleneck of every 1x1 layer (17.8 k cycles per 128x160 tile): now 16 warps
+//     (four per TMEM lane quadrant, interleaved 16-column chunks), TMEM loads issued one chunk ahead, bias from
 //     shared memory, SiLU as ex2.approx + rcp.approx (2 MUFU ops per element).
 //
 // Warp roles per CTA (320 threads): warp 0 = TMA producer, warp 1 = TMEM owner (+ MMA issuer in the leader CTA),
-// warps 2..9 = epilogue.  Barriers: full[s] lives in the LEADER (2 arrivals + bytes of both CTAs),
+// warps 2..17 = epilogue.  Barriers: full[s] lives in the LEADER (2 arrivals + bytes of both CTAs),
 // empty[s] / acc_full[a] are per CTA and signalled by multicast tcgen05.commit, acc_empty[a] lives in the leader
-// (16 warp arrivals).
+// (one arrival per epilogue warp of both CTAs).
 #pragma once
 #include <cuda_fp16.h>
 
@@ -25,8 +25,8 @@
 
 namespace mdb {
 
-constexpr int kPairThreads = 320;
-constexpr int kPairEpiWarps = 8;
+constexpr int kPairEpiWarps = 16;  // four per TMEM lane quadrant
+constexpr int kPairThreads = 64 + 32 * kPairEpiWarps;
 constexpr int kPairMaxStages = 10;
 
 struct PairParams {
@@ -49,7 +49,9 @@ struct PairParams {
   long long res_pix_stride;
   int res_c_off;
   int act;
+  int wide;        // 1: every epilogue row segment is 32-byte aligned -> 256-bit global accesses
   uint32_t idesc;  // M = 256
+  long long* dbg;  // optional per-CTA cycle counters (MDB_CONV_DEBUG=1), null in production
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -61,13 +63,15 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-// arrive (count 1, no tx) on the mbarrier at the same shared-memory offset in CTA `rank` of the cluster
+// arrive (count 1, no tx) on the mbarrier at the same shared-memory offset in CTA `rank` of the cluster.
+// Default (cta-scope) semantics on purpose: a .release.cluster arrive costs a cluster-scope fence per stage
+// in the peer's producer thread and halved the main-loop rate (measured, profiles/r01_conv_cases_v2a).
 __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank) {
   asm volatile(
       "{\n\t"
       ".reg .b32 ra;\n\t"
       "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t"
       "}\n" ::"r"(smem_u32(bar)),
       "r"(rank)
       : "memory");
@@ -124,8 +128,27 @@ __device__ __forceinline__ float silu_fast(float x) {
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
   return x * r;
 }
+// 256-bit global accesses (sm_100: LDG/STG.E.ENL2.256): one full 32-byte sector per lane and instruction -- half
+// the LSU wavefronts of two 128-bit accesses for the pixel-strided epilogue traffic
+__device__ __forceinline__ void ldg256(const void* p, uint4& a, uint4& b) {
+  asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+               : "l"(p));
+}
+__device__ __forceinline__ void stg256(void* p, const uint4& a, const uint4& b) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w),
+               "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
+               : "memory");
+}
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait_timed(uint64_t* bar, uint32_t parity, long long& acc, bool on) {
+  if (!on) { mbar_wait(bar, parity); return; }
+  const long long t0 = clock64();
+  mbar_wait(bar, parity);
+  acc += clock64() - t0;
 }
 
 template <int KC>
@@ -153,12 +176,11 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   const uint32_t half_n = static_cast<uint32_t>(p.BN) >> 1;
   const uint32_t b_chunk = (half_n * ROW_BYTES + 1023u) & ~1023u;
   const uint32_t chunk_bytes = A_CHUNK + b_chunk;
-  const uint32_t stage_bytes = static_cast<uint32_t>(p.cps) * chunk_bytes;
+  const uint32_t stage_bytes = chunk_bytes;  // one 64-channel chunk (A 128 rows + half of B) per stage
   // bytes that land in ONE CTA per chunk (A box + half-B box); the leader's barrier expects both CTAs' bytes
   const uint32_t tx_per_chunk = static_cast<uint32_t>(p.tw * p.th) * ROW_BYTES + half_n * ROW_BYTES;
 
   const int S = p.stages;
-  const int stage_iters = (p.total_chunks + p.cps - 1) / p.cps;
   const int total_tiles = p.pair_m * p.n_tiles;
   const int num_clusters = gridDim.x >> 1;
   const int cluster_id = blockIdx.x >> 1;
@@ -192,8 +214,17 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================
+    // One thread; the loop body is kept to a few dozen instructions per stage: no integer division inside
+    // (running stage/phase counters, incremental tap/chunk counters) -- with ~150 dependent scalar instructions
+    // per stage this thread, not the memory system, was the bottleneck (profiles/r01_conv_dbg_v2b.txt).
     if (lane == 0) {
+      const bool dbg = p.dbg != nullptr;
+      long long w_empty = 0;
       uint32_t it = 0;
+      const long long t_start = clock64();
+      int s = 0;
+      uint32_t ph = 0;
+      const uint32_t tx_stage = 2u * tx_per_chunk;  // both CTAs' bytes, one chunk per stage
       for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
         const int n_tile = tile % p.n_tiles;
         const int m_tile = 2 * (tile / p.n_tiles) + static_cast<int>(rank);
@@ -202,81 +233,97 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         const int img = m_tile / (p.tiles_x * p.tiles_y);  // >= n_img for the padding tile: TMA zero-fills
         const int ox0 = txi * p.tw, oy0 = tyi * p.th;
         const int nb0 = n_tile * p.BN + static_cast<int>(rank * half_n);
-        int g = 0;
-        for (int si = 0; si < stage_iters; ++si, ++it) {
-          const int s = it % S;
-          const uint32_t ph = (it / S) & 1u;
-          const int nch = min(p.cps, p.total_chunks - g);
-          mbar_wait(&empty_bar[s], ph ^ 1u);
-          if (leader) mbar_arrive_expect_tx(&full_bar[s], 2u * static_cast<uint32_t>(nch) * tx_per_chunk);
-          else mbar_arrive_remote(&full_bar[s], 0);
-          const uint32_t sbase = smem_base + static_cast<uint32_t>(s) * stage_bytes;
-          for (int j = 0; j < nch; ++j, ++g) {
-            const int tap = g / p.chunks;
-            const int c = g - tap * p.chunks;
-            const int kh = tap / p.KW, kw = tap - kh * p.KW;
-            const CUtensorMap* ma = &tmA0;
-            int x, y;
-            if (p.stride == 1) {
-              x = ox0 + kw - p.pad;
-              y = oy0 + kh - p.pad;
-            } else {
-              const int ty_ = kh - p.pad, tx_ = kw - p.pad;
-              const int py = ty_ & 1, px = tx_ & 1;
-              y = oy0 + (ty_ - py) / 2;
-              x = ox0 + (tx_ - px) / 2;
-              const int par = py * 2 + px;
-              ma = par == 0 ? &tmA0 : (par == 1 ? &tmA1 : (par == 2 ? &tmA2 : &tmA3));
-            }
-            const uint32_t dst = sbase + static_cast<uint32_t>(j) * chunk_bytes;
-            tma2_load_4d(ma, &full_bar[s], dst, c * KC, x, y, img);
-            tma2_load_2d(&tmB, &full_bar[s], dst + A_CHUNK, tap * p.Cin + c * KC, nb0);
+        int kh = 0, kw = 0, c = 0, kcol = 0;
+        // coordinates of the current filter tap
+        const CUtensorMap* ma = &tmA0;
+        int x = 0, y = 0;
+        auto set_tap = [&]() {
+          if (p.stride == 1) {
+            x = ox0 + kw - p.pad;
+            y = oy0 + kh - p.pad;
+            ma = &tmA0;
+          } else {
+            const int ty_ = kh - p.pad, tx_ = kw - p.pad;
+            const int py = ty_ & 1, px = tx_ & 1;
+            y = oy0 + ((ty_ - py) >> 1);
+            x = ox0 + ((tx_ - px) >> 1);
+            const int par = py * 2 + px;
+            ma = par == 0 ? &tmA0 : (par == 1 ? &tmA1 : (par == 2 ? &tmA2 : &tmA3));
           }
+        };
+        set_tap();
+        for (int si = 0; si < p.total_chunks; ++si) {
+          mbar_wait_timed(&empty_bar[s], ph ^ 1u, w_empty, dbg);
+          if (leader) mbar_arrive_expect_tx(&full_bar[s], tx_stage);
+          else mbar_arrive_remote(&full_bar[s], 0);
+          const uint32_t dst = smem_base + static_cast<uint32_t>(s) * stage_bytes;
+          tma2_load_4d(ma, &full_bar[s], dst, c * KC, x, y, img);
+          tma2_load_2d(&tmB, &full_bar[s], dst + A_CHUNK, kcol, nb0);
+          kcol += KC;
+          if (++c == p.chunks) {
+            c = 0;
+            if (++kw == p.KW) { kw = 0; ++kh; }
+            set_tap();
+          }
+          if (++s == S) { s = 0; ph ^= 1u; }
+          ++it;
         }
+      }
+      if (dbg) {
+        p.dbg[blockIdx.x * 8 + 0] = clock64() - t_start;
+        p.dbg[blockIdx.x * 8 + 1] = w_empty;
+        p.dbg[blockIdx.x * 8 + 2] = it;
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
     if (leader && lane == 0) {
-      uint32_t it = 0;
       uint32_t tcount = 0;
+      const bool dbg = p.dbg != nullptr;
+      long long w_full = 0, w_acc = 0;
+      const long long t_start = clock64();
+      int s = 0;
+      uint32_t ph = 0;
+      // descriptor template: everything except the 14-bit start address is constant for the whole kernel
+      const uint64_t desc_tmpl = make_kmajor_desc(0, ROW_BYTES);
       for (int tile = cluster_id; tile < total_tiles; tile += num_clusters, ++tcount) {
         const uint32_t acc = tcount & 1u;
         const uint32_t acc_ph = (tcount >> 1) & 1u;
-        mbar_wait(&acc_empty_bar[acc], acc_ph ^ 1u);
+        mbar_wait_timed(&acc_empty_bar[acc], acc_ph ^ 1u, w_acc, dbg);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * kAccStride;
-        int g = 0;
-        for (int si = 0; si < stage_iters; ++si, ++it) {
-          const int s = it % S;
-          const uint32_t ph = (it / S) & 1u;
-          const int nch = min(p.cps, p.total_chunks - g);
-          mbar_wait(&full_bar[s], ph);
+        for (int si = 0; si < p.total_chunks; ++si) {
+          mbar_wait_timed(&full_bar[s], ph, w_full, dbg);
           tc_fence_after();
-          const uint32_t sbase = smem_base + static_cast<uint32_t>(s) * stage_bytes;
-          for (int j = 0; j < nch; ++j, ++g) {
-            const uint32_t a_addr = sbase + static_cast<uint32_t>(j) * chunk_bytes;
-            const uint64_t da = make_kmajor_desc(a_addr, ROW_BYTES);
-            const uint64_t db = make_kmajor_desc(a_addr + A_CHUNK, ROW_BYTES);
+          const uint32_t a_addr = smem_base + static_cast<uint32_t>(s) * stage_bytes;
+          const uint64_t da = desc_tmpl | static_cast<uint64_t>((a_addr & 0x3FFFFu) >> 4);
+          const uint64_t db = desc_tmpl | static_cast<uint64_t>(((a_addr + A_CHUNK) & 0x3FFFFu) >> 4);
 #pragma unroll
-            for (int k = 0; k < KC / 16; ++k)
-              umma2_f16(d_tmem, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), p.idesc,
-                        (g > 0 || k > 0) ? 1u : 0u);
-          }
+          for (int k = 0; k < KC / 16; ++k)
+            umma2_f16(d_tmem, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), p.idesc,
+                      (si > 0 || k > 0) ? 1u : 0u);
           umma2_commit_mc(&empty_bar[s]);
+          if (++s == S) { s = 0; ph ^= 1u; }
         }
         umma2_commit_mc(&acc_full_bar[acc]);
+      }
+      if (dbg) {
+        p.dbg[blockIdx.x * 8 + 4] = clock64() - t_start;
+        p.dbg[blockIdx.x * 8 + 5] = w_full;
+        p.dbg[blockIdx.x * 8 + 6] = w_acc;
+        p.dbg[blockIdx.x * 8 + 7] = tcount;
       }
     }
   } else {
     // ===================== epilogue (warps 2..9 of both CTAs) =====================
-    const uint32_t ew = warp - 2;          // 0..7
+    const uint32_t ew = warp - 2;          // 0..kPairEpiWarps-1
     const uint32_t quad = warp & 3u;       // TMEM lane quadrant this warp may read
-    const uint32_t half = ew >> 2;         // which interleaved set of 16-column chunks
+    const uint32_t part = ew >> 2;         // which interleaved set of 16-column chunks
+    constexpr int kParts = kPairEpiWarps / 4;
     const uint32_t row = quad * 32u + lane;
     const int ty = static_cast<int>(row) / p.tw;
     const int tx = static_cast<int>(row) - ty * p.tw;
-    const int et = static_cast<int>(threadIdx.x) - 64;  // 0..255
+    const int et = static_cast<int>(threadIdx.x) - 64;  // 0..32*kPairEpiWarps-1
     const int nchunks = p.BN >> 4;
     uint32_t tcount = 0;
     for (int tile = cluster_id; tile < total_tiles; tile += num_clusters, ++tcount) {
@@ -294,7 +341,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 
       // bias of this N tile -> shared memory (double-buffered by tile parity; one named barrier per tile)
       float* bs = bias_s[tcount & 1u];
-      if (et < p.BN) bs[et] = __ldg(p.bias + n0 + et);
+      if (et < p.BN) bs[et] = __ldg(p.bias + n0 + et);  // BN <= 256 <= epilogue threads
       named_bar_sync(1, kPairEpiWarps * 32);
 
       mbar_wait(&acc_full_bar[acc], acc_ph);
@@ -306,9 +353,13 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         if (!(valid && col0 < p.Cout)) return;
         uint4 r0 = make_uint4(0, 0, 0, 0), r1 = make_uint4(0, 0, 0, 0);
         if (p.res != nullptr) {
-          const uint4* rp = reinterpret_cast<const uint4*>(p.res + pix * p.res_pix_stride + p.res_c_off + col0);
-          r0 = __ldg(rp);
-          r1 = __ldg(rp + 1);
+          const __half* rp = p.res + pix * p.res_pix_stride + p.res_c_off + col0;
+          if (p.wide) {
+            ldg256(rp, r0, r1);
+          } else {
+            r0 = __ldg(reinterpret_cast<const uint4*>(rp));
+            r1 = __ldg(reinterpret_cast<const uint4*>(rp) + 1);
+          }
         }
         float f[16];
         const float4* b4 = reinterpret_cast<const float4*>(bs + jj * 16);
@@ -339,7 +390,17 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         }
         if (p.out_fp32) {
           float* op = reinterpret_cast<float*>(p.out) + pix * p.out_pix_stride + p.out_c_off + col0;
-          if (col0 + 16 <= p.Cout) {
+          if (col0 + 16 <= p.Cout && p.wide) {
+            uint4 w0, w1;
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+              w0 = make_uint4(__float_as_uint(f[8 * hh]), __float_as_uint(f[8 * hh + 1]), __float_as_uint(f[8 * hh + 2]),
+                              __float_as_uint(f[8 * hh + 3]));
+              w1 = make_uint4(__float_as_uint(f[8 * hh + 4]), __float_as_uint(f[8 * hh + 5]),
+                              __float_as_uint(f[8 * hh + 6]), __float_as_uint(f[8 * hh + 7]));
+              stg256(op + 8 * hh, w0, w1);
+            }
+          } else if (col0 + 16 <= p.Cout) {
 #pragma unroll
             for (int e = 0; e < 4; ++e)
               reinterpret_cast<float4*>(op)[e] = make_float4(f[4 * e], f[4 * e + 1], f[4 * e + 2], f[4 * e + 3]);
@@ -359,8 +420,12 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
               q0[e] = __floats2half2_rn(f[2 * e], f[2 * e + 1]);
               q1[e] = __floats2half2_rn(f[8 + 2 * e], f[8 + 2 * e + 1]);
             }
-            reinterpret_cast<uint4*>(op)[0] = o0;
-            reinterpret_cast<uint4*>(op)[1] = o1;
+            if (p.wide) {
+              stg256(op, o0, o1);
+            } else {
+              reinterpret_cast<uint4*>(op)[0] = o0;
+              reinterpret_cast<uint4*>(op)[1] = o1;
+            }
           } else {
 #pragma unroll
             for (int e = 0; e < 16; ++e)
@@ -370,18 +435,18 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       };
       // TMEM loads run one chunk ahead of the math (two register buffers, statically indexed)
       uint32_t va[16], vb[16];
-      int j = static_cast<int>(half);
+      int j = static_cast<int>(part);
       if (j < nchunks) tmem_ld16(taddr + static_cast<uint32_t>(j * 16), va);
       while (j < nchunks) {
         tmem_ld_wait();
-        if (j + 2 < nchunks) tmem_ld16(taddr + static_cast<uint32_t>((j + 2) * 16), vb);
+        if (j + kParts < nchunks) tmem_ld16(taddr + static_cast<uint32_t>((j + kParts) * 16), vb);
         process(va, j);
-        j += 2;
+        j += kParts;
         if (j >= nchunks) break;
         tmem_ld_wait();
-        if (j + 2 < nchunks) tmem_ld16(taddr + static_cast<uint32_t>((j + 2) * 16), va);
+        if (j + kParts < nchunks) tmem_ld16(taddr + static_cast<uint32_t>((j + kParts) * 16), va);
         process(vb, j);
-        j += 2;
+        j += kParts;
       }
       // all TMEM reads of this warp have completed (tcgen05.wait::ld): hand the accumulator stage back
       tc_fence_before();

@@ -342,9 +342,9 @@ Plan* get_plan(mdb_engine* e, int H, int W) {
     d.in = P->view(s.in);
     d.out = P->view(s.out);
     if (s.res.buf >= 0) d.res = P->view(s.res);
-    d.wgt = cw.w; d.bias = cw.b; d.cout = cw.cout; d.cout_pad = cw.cout_pad;
+    d.wgt = cw.w; d.bias = cw.b; d.cout = cw.cout; d.cout_pad = cw.cout_pad; d.cin_pad = cw.cin_pad;
     d.k = s.k; d.s = s.s; d.pad = s.pad; d.act = s.act;
-    MDB_REQUIRE(cw.cin_pad == d.in.C && cw.k == s.k && cw.cout == s.cout, ("weight shape mismatch for " + s.name).c_str());
+    MDB_REQUIRE(cw.cin == d.in.C && cw.k == s.k && cw.cout == s.cout, ("weight shape mismatch for " + s.name).c_str());
     s.op = conv_build(d, e->num_sms);
     P->macs_per_image += conv_macs_per_image(s.op);
   }
@@ -738,12 +738,12 @@ int mdb_load_weights(mdb_engine* e, const mdb_tensor_desc* tensors, int32_t n) {
       std::vector<__half> packed;
       if (base == "model.0.conv") {
         MDB_REQUIRE(ci == 3 && k == 6, "stem must be a 6x6 conv over 3 channels");
-        pack_weights_stem_s2d(tw->data, co, cw.cout_pad, packed);
-        cw.cin = 12; cw.cin_pad = 16; cw.k = 3;
+        cw.cin = 16; cw.cin_pad = 64; cw.k = 3;
+        pack_weights_stem_s2d(tw->data, co, cw.cout_pad, cw.cin_pad, packed);
       } else {
         MDB_REQUIRE(ci % 16 == 0, "conv input channels must be a multiple of 16");
-        pack_weights_khwc(tw->data, co, ci, k, cw.cout_pad, ci, packed);
-        cw.cin = ci; cw.cin_pad = ci; cw.k = k;
+        cw.cin = ci; cw.cin_pad = ((ci + 63) / 64) * 64; cw.k = k;
+        pack_weights_khwc(tw->data, co, ci, k, cw.cout_pad, cw.cin_pad, packed);
       }
       std::vector<float> bias(cw.cout_pad, 0.f);
       memcpy(bias.data(), bi->second->data, sizeof(float) * co);
@@ -995,7 +995,8 @@ int mdb_op_conv2d(mdb_engine* e, const void* x_fp16, int32_t n, int32_t h, int32
     const int cstore = out_fp32 ? ((cout + 3) / 4) * 4 : ((cout + 7) / 8) * 8;
     MDB_REQUIRE(cstore == cout, "cout must be a multiple of 8 (fp16) / 4 (fp32) for this test entry point");
     std::vector<__half> packed;
-    pack_weights_khwc(wgt, cout, cin, k, cout_pad, cin, packed);
+    const int cin_pad = ((cin + 63) / 64) * 64;
+    pack_weights_khwc(wgt, cout, cin, k, cout_pad, cin_pad, packed);
     std::vector<float> bp(cout_pad, 0.f);
     memcpy(bp.data(), bias, sizeof(float) * cout);
     const size_t xb = static_cast<size_t>(n) * h * w * cin * 2;
@@ -1017,7 +1018,7 @@ int mdb_op_conv2d(mdb_engine* e, const void* x_fp16, int32_t n, int32_t h, int32
       MDB_CUDA(cudaMemcpy(d_r, residual_fp16, rb, cudaMemcpyHostToDevice));
       d.res.base = d_r; d.res.N = n; d.res.H = ho; d.res.W = wo; d.res.Ctot = cout; d.res.C = cout;
     }
-    d.wgt = d_w; d.bias = d_b; d.cout = cout; d.cout_pad = cout_pad; d.k = k; d.s = s; d.pad = pad; d.act = act;
+    d.wgt = d_w; d.bias = d_b; d.cout = cout; d.cout_pad = cout_pad; d.cin_pad = cin_pad; d.k = k; d.s = s; d.pad = pad; d.act = act;
     op = conv_build(d, e->num_sms);
     conv_launch(op, n, st);
     e->launches++;

@@ -156,9 +156,11 @@ def decode_level(raw, level, arch):
     na, no = 3, arch.no
     x = raw.view(B, na, no, ny, nx).permute(0, 1, 3, 4, 2).contiguous()
     y = x.sigmoid()
-    yv, xv = torch.meshgrid(torch.arange(ny, dtype=torch.float32), torch.arange(nx, dtype=torch.float32), indexing='ij')
+    dev = raw.device
+    yv, xv = torch.meshgrid(torch.arange(ny, dtype=torch.float32, device=dev),
+                            torch.arange(nx, dtype=torch.float32, device=dev), indexing='ij')
     grid = torch.stack((xv, yv), 2).expand(1, na, ny, nx, 2) - 0.5
-    anchor_grid = torch.tensor(arch.anchors_px[level], dtype=torch.float32).view(1, na, 1, 1, 2)
+    anchor_grid = torch.tensor(arch.anchors_px[level], dtype=torch.float32, device=dev).view(1, na, 1, 1, 2)
     xy = (y[..., 0:2] * 2 + grid) * float(STRIDES[level])
     wh = (y[..., 2:4] * 2) ** 2 * anchor_grid
     out = torch.cat((xy, wh, y[..., 4:]), 4)

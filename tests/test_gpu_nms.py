@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 from conftest import GOLDEN
-from helpers import assert_dets_equal_modulo_ties
+from helpers import assert_anchors_equal_modulo_ties, assert_dets_equal_modulo_ties
 
 pytestmark = pytest.mark.gpu
 
@@ -57,9 +57,7 @@ def test_nms_matches_oracle_at_full_size(engine, anchors, ncl, thr):
         assert cnt[b] == odet.shape[0]
         assert_dets_equal_modulo_ties(odet, det[b, :cnt[b]], 'img{}'.format(b))
         # kept anchor indices: identical as sets inside tie groups -> compare sorted per confidence value
-        got = sorted(zip(det[b, :cnt[b], 4].tolist(), anc[b, :cnt[b]].tolist()))
-        want = sorted(zip(odet[:, 4].tolist(), oanc.tolist()))
-        assert got == want, 'kept anchor indices differ'
+        assert_anchors_equal_modulo_ties(odet[:, 4], oanc, det[b, :cnt[b], 4], anc[b, :cnt[b]], 'img{}'.format(b))
 
 
 def test_nms_empty_and_all_below_threshold(engine):
