@@ -217,7 +217,9 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     // One thread; the loop body is kept to a few dozen instructions per stage: no integer division inside
     // (running stage/phase counters, incremental tap/chunk counters) -- with ~150 dependent scalar instructions
     // per stage this thread, not the memory system, was the bottleneck (profiles/r01_conv_dbg_v2b.txt).
-    if (lane == 0) {
+    // elect.sync (not `lane == 0`): inside an elected region ptxas knows a single thread is active and keeps TMA
+    // operands in uniform registers instead of emitting a waterfall loop around every UTMALDG.
+    if (elect_one()) {
       const bool dbg = p.dbg != nullptr;
       long long w_empty = 0;
       uint32_t it = 0;
@@ -277,7 +279,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
-    if (leader && lane == 0) {
+    if (leader && elect_one()) {
       uint32_t tcount = 0;
       const bool dbg = p.dbg != nullptr;
       long long w_full = 0, w_acc = 0;
