@@ -162,6 +162,8 @@ def main():
     W = max(3, args.warmup)
     det = B200Detector(MODEL, {'max_batch': B, 'device': 'cuda:%d' % local_rank})
     eng = det.engine
+    if os.environ.get('MDB_SPLIT'):
+        eng.set_pipeline_split(int(os.environ['MDB_SPLIT']))
     # synthetic pool in page-locked host memory (each rank its own images: image-sharded job)
     pins = [_capi.PinnedArray((SRC_H, SRC_W, 3)) for _ in range(POOL)]
     for i, p in enumerate(pins):
@@ -298,5 +300,30 @@ def cpu_baseline(n_images):
                       'torch {} threads (best of several settings on {} hardware threads), 1 warm-up'.format(n_images, torch.get_num_threads(), os.cpu_count())}
 
 
+def _main_quiet():
+    # the drop-in detector prints the reference's load-time messages ("PTDetector using device ...", which AddaxAI
+    # parses); bench.py's stdout must carry exactly one JSON line, so everything else goes to stderr
+    import contextlib
+    import io
+    real_stdout = sys.stdout
+    lines = []
+
+    class _Tee(io.TextIOBase):
+        def write(self, t):
+            for ln in t.splitlines(True):
+                if ln.startswith('{"') and '"metric"' in ln or ln.startswith('{"impl"'):
+                    lines.append(ln)
+                else:
+                    sys.stderr.write(ln)
+            return len(t)
+
+    with contextlib.redirect_stdout(_Tee()):
+        rc = main()
+    for ln in lines:
+        real_stdout.write(ln if ln.endswith('\n') else ln + '\n')
+    real_stdout.flush()
+    return rc
+
+
 if __name__ == '__main__':
-    sys.exit(main())
+    sys.exit(_main_quiet())

@@ -99,6 +99,16 @@ MDB_API int mdb_infer_batch(mdb_engine* e, const uint8_t* const* rgb_hwc, const 
                     const int64_t* row_stride, int32_t n, float conf_thres, float* det_out, int32_t* det_count,
                     int32_t* kept_anchor, int32_t* status);
 
+/* Streaming form of mdb_infer_batch (same arguments; the output arrays must stay valid until the batch is done):
+ * begin() plans the chunks and queues the first ones, every next() completes the oldest outstanding chunk and
+ * returns the caller-array indices whose results (or failure status) are final, queuing further chunks behind it.
+ * *n_done == 0 means the batch is finished.  Lets the host format records (pytorch_detector.py:1384-1411) for
+ * chunk i while the GPU runs chunk i+1. */
+MDB_API int mdb_batch_begin(mdb_engine* e, const uint8_t* const* rgb_hwc, const int32_t* h, const int32_t* w,
+                            const int64_t* row_stride, int32_t n, float conf_thres, float* det_out, int32_t* det_count,
+                            int32_t* kept_anchor, int32_t* status);
+MDB_API int mdb_batch_next(mdb_engine* e, int32_t* done_idx, int32_t cap, int32_t* n_done);
+
 /* Same, for images already letterboxed by a producer worker (dict inputs, run_detector_batch.py:175-183):
  * lb_hwc[i] is lh[i] x lw[i] x 3 (dense), src_h/src_w the original size used by scale_coords. */
 MDB_API int mdb_infer_preprocessed(mdb_engine* e, const uint8_t* const* lb_hwc, const int32_t* lh, const int32_t* lw,

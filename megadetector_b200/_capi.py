@@ -17,7 +17,7 @@ MDB_IMG_OK, MDB_IMG_BAD_INPUT, MDB_IMG_INFER_FAILED = 0, 1, 2
 MDB_FETCH_STEM_INPUT, MDB_FETCH_PRED, MDB_FETCH_LAYER = 1, 2, 3
 
 EXPORTS = [
-    'mdb_create', 'mdb_load_weights', 'mdb_destroy', 'mdb_last_error', 'mdb_infer_batch', 'mdb_infer_preprocessed',
+    'mdb_create', 'mdb_load_weights', 'mdb_destroy', 'mdb_last_error', 'mdb_infer_batch', 'mdb_batch_begin', 'mdb_batch_next', 'mdb_infer_preprocessed',
     'mdb_letterbox_geometry', 'mdb_set_image_size', 'mdb_debug_fetch', 'mdb_last_timing', 'mdb_bench_resident', 'mdb_profile_steps', 'mdb_set_pipeline_split', 'mdb_launch_count', 'mdb_op_letterbox',
     'mdb_op_conv2d', 'mdb_op_nms', 'mdb_alloc_pinned', 'mdb_free_pinned', 'mdb_version',
 ]
@@ -70,6 +70,10 @@ def load_library():
     lib.mdb_infer_batch.argtypes = [vp, P(vp), P(C.c_int32), P(C.c_int32), P(C.c_int64), C.c_int32, C.c_float,
                                     vp, vp, vp, vp]
     lib.mdb_infer_batch.restype = C.c_int
+    lib.mdb_batch_begin.argtypes = lib.mdb_infer_batch.argtypes
+    lib.mdb_batch_begin.restype = C.c_int
+    lib.mdb_batch_next.argtypes = [vp, P(C.c_int32), C.c_int32, P(C.c_int32)]
+    lib.mdb_batch_next.restype = C.c_int
     lib.mdb_infer_preprocessed.argtypes = [vp, P(vp), P(C.c_int32), P(C.c_int32), P(C.c_int32), P(C.c_int32),
                                            C.c_int32, C.c_float, vp, vp, vp, vp]
     lib.mdb_infer_preprocessed.restype = C.c_int
@@ -249,6 +253,48 @@ class Engine:
                                       anc.ctypes.data if anc is not None else None, status.ctypes.data)
         self._check(rc, 'mdb_infer_batch')
         return det, cnt, anc, status
+
+    def infer_batch_stream(self, images, conf_thres):
+        """
+        Generator form of infer_batch: yields (indices, det, count, status) each time a chunk of the batch is final
+        (det/count/status are the full-batch arrays, valid at `indices`), so the caller can post-process finished
+        images while the GPU works on the rest.
+        """
+        n = len(images)
+        ptrs = (C.c_void_p * n)()
+        hs = (C.c_int32 * n)()
+        ws = (C.c_int32 * n)()
+        st = (C.c_int64 * n)()
+        for i, im in enumerate(images):
+            ok = isinstance(im, np.ndarray) and im.dtype == np.uint8 and im.ndim == 3 and im.shape[2] == 3 and \
+                im.strides[2] == 1 and im.strides[1] == 3
+            if not ok:
+                ptrs[i] = None
+                hs[i] = ws[i] = 0
+                continue
+            ptrs[i] = im.ctypes.data
+            hs[i], ws[i] = im.shape[0], im.shape[1]
+            st[i] = im.strides[0]
+        det = np.zeros((n, self.max_det, 6), np.float32)
+        cnt = np.zeros((n,), np.int32)
+        status = np.zeros((n,), np.int32)
+        self._check(self.lib.mdb_batch_begin(self.h, ptrs, hs, ws, st, n, float(conf_thres), det.ctypes.data,
+                                             cnt.ctypes.data, None, status.ctypes.data), 'mdb_batch_begin')
+        done = (C.c_int32 * max(1, n))()
+        nd = C.c_int32(0)
+        finished = False
+        try:
+            while True:
+                self._check(self.lib.mdb_batch_next(self.h, done, max(1, n), C.byref(nd)), 'mdb_batch_next')
+                if nd.value == 0:
+                    finished = True
+                    break
+                yield [done[i] for i in range(nd.value)], det, cnt, status
+        finally:
+            # never leave a half-consumed batch inside the engine (its output arrays die with this frame)
+            while not finished:
+                if self.lib.mdb_batch_next(self.h, done, max(1, n), C.byref(nd)) != MDB_OK or nd.value == 0:
+                    finished = True
 
     def infer_preprocessed(self, images, src_shapes, conf_thres, want_anchors=True):
         n = len(images)

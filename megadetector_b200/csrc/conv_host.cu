@@ -158,7 +158,13 @@ ConvOp* conv_build(const ConvDesc& d, int num_sms) {
       q.KH = p.KH; q.KW = p.KW; q.stride = p.stride; q.pad = p.pad;
       q.chunks = p.chunks; q.Cin = p.Cin;
       q.total_chunks = d.k * d.k * p.chunks;
-      q.cps = 1;
+      // chunks per pipeline stage: enough MMA time per mbarrier round trip (>= ~320 tensor cycles)
+      {
+        static const char* e = getenv("MDB_CONV_CPS");
+        q.cps = e ? atoi(e) : 2;  // measured sweep (profiles/r01_conv_cases_cps*.txt): 2 wins on every layer shape
+        if (q.cps < 1) q.cps = 1;
+        if (q.cps > 4) q.cps = 4;
+      }
       q.bias = p.bias; q.out = p.out; q.out_pix_stride = p.out_pix_stride; q.out_c_off = p.out_c_off;
       q.out_fp32 = p.out_fp32; q.res = p.res; q.res_pix_stride = p.res_pix_stride; q.res_c_off = p.res_c_off;
       q.act = p.act;
@@ -175,7 +181,7 @@ ConvOp* conv_build(const ConvDesc& d, int num_sms) {
       const size_t b_chunk = (static_cast<size_t>(p.BN / 2) * kc * 2 + 1023) & ~static_cast<size_t>(1023);
       const size_t stage = static_cast<size_t>(q.cps) * (a_chunk + b_chunk);
       const size_t budget = 227 * 1024 - 4096;  // static: barriers + bias staging; alignment slack
-      const int stage_iters = q.total_chunks;
+      const int stage_iters = (q.total_chunks + q.cps - 1) / q.cps;
       int stages = static_cast<int>(std::min<size_t>(kPairMaxStages, (budget - 1024) / stage));
       stages = std::max(2, std::min(stages, std::max(2, stage_iters * 2)));
       q.stages = stages;

@@ -176,7 +176,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   const uint32_t half_n = static_cast<uint32_t>(p.BN) >> 1;
   const uint32_t b_chunk = (half_n * ROW_BYTES + 1023u) & ~1023u;
   const uint32_t chunk_bytes = A_CHUNK + b_chunk;
-  const uint32_t stage_bytes = chunk_bytes;  // one 64-channel chunk (A 128 rows + half of B) per stage
+  const uint32_t stage_bytes = static_cast<uint32_t>(p.cps) * chunk_bytes;  // cps 64-channel chunks per stage
   // bytes that land in ONE CTA per chunk (A box + half-B box); the leader's barrier expects both CTAs' bytes
   const uint32_t tx_per_chunk = static_cast<uint32_t>(p.tw * p.th) * ROW_BYTES + half_n * ROW_BYTES;
 
@@ -226,7 +226,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       const long long t_start = clock64();
       int s = 0;
       uint32_t ph = 0;
-      const uint32_t tx_stage = 2u * tx_per_chunk;  // both CTAs' bytes, one chunk per stage
+      const uint32_t tx_stage = 2u * tx_per_chunk;  // both CTAs' bytes of one chunk
       for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
         const int n_tile = tile % p.n_tiles;
         const int m_tile = 2 * (tile / p.n_tiles) + static_cast<int>(rank);
@@ -254,19 +254,23 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           }
         };
         set_tap();
-        for (int si = 0; si < p.total_chunks; ++si) {
+        for (int done = 0; done < p.total_chunks;) {
+          const int nch = min(p.cps, p.total_chunks - done);
           mbar_wait_timed(&empty_bar[s], ph ^ 1u, w_empty, dbg);
-          if (leader) mbar_arrive_expect_tx(&full_bar[s], tx_stage);
+          if (leader) mbar_arrive_expect_tx(&full_bar[s], static_cast<uint32_t>(nch) * tx_stage);
           else mbar_arrive_remote(&full_bar[s], 0);
-          const uint32_t dst = smem_base + static_cast<uint32_t>(s) * stage_bytes;
-          tma2_load_4d(ma, &full_bar[s], dst, c * KC, x, y, img);
-          tma2_load_2d(&tmB, &full_bar[s], dst + A_CHUNK, kcol, nb0);
-          kcol += KC;
-          if (++c == p.chunks) {
-            c = 0;
-            if (++kw == p.KW) { kw = 0; ++kh; }
-            set_tap();
+          uint32_t dst = smem_base + static_cast<uint32_t>(s) * stage_bytes;
+          for (int j = 0; j < nch; ++j, dst += chunk_bytes) {
+            tma2_load_4d(ma, &full_bar[s], dst, c * KC, x, y, img);
+            tma2_load_2d(&tmB, &full_bar[s], dst + A_CHUNK, kcol, nb0);
+            kcol += KC;
+            if (++c == p.chunks) {
+              c = 0;
+              if (++kw == p.KW) { kw = 0; ++kh; }
+              set_tap();
+            }
           }
+          done += nch;
           if (++s == S) { s = 0; ph ^= 1u; }
           ++it;
         }
@@ -294,17 +298,21 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         mbar_wait_timed(&acc_empty_bar[acc], acc_ph ^ 1u, w_acc, dbg);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * kAccStride;
-        for (int si = 0; si < p.total_chunks; ++si) {
+        for (int done = 0; done < p.total_chunks;) {
+          const int nch = min(p.cps, p.total_chunks - done);
           mbar_wait_timed(&full_bar[s], ph, w_full, dbg);
           tc_fence_after();
-          const uint32_t a_addr = smem_base + static_cast<uint32_t>(s) * stage_bytes;
-          const uint64_t da = desc_tmpl | static_cast<uint64_t>((a_addr & 0x3FFFFu) >> 4);
-          const uint64_t db = desc_tmpl | static_cast<uint64_t>(((a_addr + A_CHUNK) & 0x3FFFFu) >> 4);
+          uint32_t a_addr = smem_base + static_cast<uint32_t>(s) * stage_bytes;
+          for (int j = 0; j < nch; ++j, a_addr += chunk_bytes) {
+            const uint64_t da = desc_tmpl | static_cast<uint64_t>((a_addr & 0x3FFFFu) >> 4);
+            const uint64_t db = desc_tmpl | static_cast<uint64_t>(((a_addr + A_CHUNK) & 0x3FFFFu) >> 4);
 #pragma unroll
-          for (int k = 0; k < KC / 16; ++k)
-            umma2_f16(d_tmem, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), p.idesc,
-                      (si > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < KC / 16; ++k)
+              umma2_f16(d_tmem, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), p.idesc,
+                        (done > 0 || j > 0 || k > 0) ? 1u : 0u);
+          }
           umma2_commit_mc(&empty_bar[s]);
+          done += nch;
           if (++s == S) { s = 0; ph ^= 1u; }
         }
         umma2_commit_mc(&acc_full_bar[acc]);

@@ -89,6 +89,45 @@ struct DevTable {
   int16_t* coef = nullptr;
 };
 
+struct ImgIn {
+  const uint8_t* ptr;
+  int h, w;
+  long long stride;
+  int src_h, src_w;  // original size for scale_coords
+  int index;         // position in the caller's arrays
+};
+
+struct Pending {
+  int slot;
+  Plan* plan;
+  std::vector<ImgIn> imgs;
+  int job = -1;
+};
+
+struct ChunkJob {
+  int H = 0, W = 0;  // letterboxed shape (plan key)
+  std::vector<int> ids;  // indices into BatchState::all
+  bool failed = false;
+};
+
+// state of the batch that is currently streaming through the engine (mdb_batch_begin / mdb_batch_next)
+struct BatchState {
+  bool active = false;
+  float thr = 0.f;
+  std::vector<ImgIn> all;
+  std::vector<LetterboxGeom> geom;
+  std::vector<ChunkJob> jobs;
+  size_t next_job = 0;
+  std::vector<Pending> inflight;
+  std::vector<size_t> failed_ready;
+  std::vector<int> immediate;  // caller indices whose status was final at begin()
+  int slot = 0;
+  float* det_out = nullptr;
+  int32_t* det_count = nullptr;
+  int32_t* kept_anchor = nullptr;
+  int32_t* status = nullptr;
+};
+
 }  // namespace
 
 struct mdb_engine {
@@ -125,7 +164,8 @@ struct mdb_engine {
   int last_n = 0;
   float last_ms[4] = {0, 0, 0, 0};
   int64_t launches = 0;
-  int pipeline_split = 2;
+  int pipeline_split = 4;
+  BatchState batch;
   std::string err;
 };
 
@@ -413,22 +453,9 @@ void ensure_src(mdb_engine* e, int slot, size_t bytes) {
   e->d_src_bytes[slot] = want;
 }
 
-struct ImgIn {
-  const uint8_t* ptr;
-  int h, w;
-  long long stride;
-  int src_h, src_w;  // original size for scale_coords
-  int index;         // position in the caller's arrays
-};
-
 // One chunk (<= max_batch images of one letterboxed shape).  enqueue_chunk() queues the H2D copies on the copy
 // stream and K1..K8 + the result D2H on the compute stream and returns; finish_chunk() waits for it and scatters
 // the results.  Two slots => the copies of chunk i+1 overlap the kernels of chunk i.
-struct Pending {
-  int slot;
-  Plan* plan;
-  std::vector<ImgIn> imgs;
-};
 
 void stage_compute(mdb_engine* e, Plan* P, int n, int slot, float conf_thres, int stages_mask, bool timing) {
   cudaStream_t st = e->st_compute;
@@ -529,16 +556,66 @@ void finish_chunk(mdb_engine* e, const Pending& pd, float* det_out, int32_t* det
   e->last_n = n;
 }
 
-int infer_common(mdb_engine* e, std::vector<ImgIn>& all, bool preprocessed, float conf_thres, float* det_out,
-                 int32_t* det_count, int32_t* kept_anchor, int32_t* status, int n) {
+// ---- streaming batch: begin() plans the chunks and queues the first two, next() completes the oldest chunk,
+// reports which images are ready and queues one more.  The host can format finished records while the GPU works
+// on the following chunks (B200Detector does); mdb_infer_batch is begin + next-until-empty. ----
+void fail_job(mdb_engine* e, BatchState& B, size_t job, const std::string& why) {
+  e->err = why;
+  // a whole shape group fails together (pytorch_detector.py:1236-1249): this job and every later job of its shape
+  const int H = B.jobs[job].H, W = B.jobs[job].W;
+  for (size_t j = job; j < B.jobs.size(); ++j) {
+    if (B.jobs[j].H != H || B.jobs[j].W != W || B.jobs[j].failed) continue;
+    B.jobs[j].failed = true;
+    for (int id : B.jobs[j].ids) { B.status[B.all[id].index] = MDB_IMG_INFER_FAILED; B.det_count[B.all[id].index] = 0; }
+  }
+}
+
+void enqueue_next_job(mdb_engine* e, BatchState& B) {
+  while (B.next_job < B.jobs.size() && B.inflight.size() < 2) {
+    const size_t j = B.next_job++;
+    ChunkJob& job = B.jobs[j];
+    if (job.failed) { B.failed_ready.push_back(j); continue; }
+    try {
+      Plan* P = get_plan(e, job.H, job.W);
+      Pending pd;
+      pd.slot = B.slot;
+      pd.plan = P;
+      pd.job = static_cast<int>(j);
+      std::vector<LetterboxGeom> cg;
+      for (int id : job.ids) { pd.imgs.push_back(B.all[id]); cg.push_back(B.geom[id]); }
+      enqueue_chunk(e, P, pd.imgs, cg, B.thr, B.slot);
+      B.inflight.push_back(pd);
+      B.slot ^= 1;
+    } catch (const CudaError& ex) {
+      fail_job(e, B, j, ex.msg);
+      B.failed_ready.push_back(j);
+      cudaError_t sticky = cudaGetLastError();
+      if (sticky != cudaSuccess && cudaDeviceSynchronize() != cudaSuccess) throw;
+    }
+  }
+}
+
+int batch_begin(mdb_engine* e, std::vector<ImgIn>& all, bool preprocessed, float conf_thres, float* det_out,
+                int32_t* det_count, int32_t* kept_anchor, int32_t* status) {
   const mdb_config& cfg = e->cfg;
+  BatchState& B = e->batch;
+  if (B.active) return fail(e, MDB_ERR_STATE, "a batch is already in progress");
+  B = BatchState();
+  B.active = true;
+  B.thr = conf_thres;
+  B.det_out = det_out; B.det_count = det_count; B.kept_anchor = kept_anchor; B.status = status;
+  B.all = all;
+  B.geom.resize(all.size());
   memset(e->last_ms, 0, sizeof(e->last_ms));
   // group by letterboxed shape, keeping input order inside a group (pytorch_detector.py:1226-1233)
   std::map<std::pair<int, int>, std::vector<int>> groups;
-  std::vector<LetterboxGeom> geom(all.size());
   for (size_t i = 0; i < all.size(); ++i) {
-    ImgIn& im = all[i];
-    if (im.ptr == nullptr || im.h <= 0 || im.w <= 0) { status[im.index] = MDB_IMG_BAD_INPUT; det_count[im.index] = 0; continue; }
+    const ImgIn& im = all[i];
+    if (im.ptr == nullptr || im.h <= 0 || im.w <= 0) {
+      status[im.index] = MDB_IMG_BAD_INPUT; det_count[im.index] = 0;
+      B.immediate.push_back(im.index);
+      continue;
+    }
     LetterboxGeom g;
     if (preprocessed) {
       g = LetterboxGeom{}; g.src_h = im.h; g.src_w = im.w; g.new_w = im.w; g.new_h = im.h; g.out_h = im.h; g.out_w = im.w;
@@ -546,60 +623,90 @@ int infer_common(mdb_engine* e, std::vector<ImgIn>& all, bool preprocessed, floa
       g = letterbox_geometry(im.h, im.w, cfg.img_size, cfg.stride, cfg.letterbox_auto != 0, cfg.letterbox_scaleup != 0);
     }
     if (g.out_h % 64 != 0 || g.out_w % 64 != 0 || g.new_w < 1 || g.new_h < 1) {
-      status[im.index] = MDB_IMG_INFER_FAILED; det_count[im.index] = 0; continue;
+      status[im.index] = MDB_IMG_INFER_FAILED; det_count[im.index] = 0;
+      B.immediate.push_back(im.index);
+      continue;
     }
-    geom[i] = g;
+    B.geom[i] = g;
     groups[std::make_pair(g.out_h, g.out_w)].push_back(static_cast<int>(i));
     status[im.index] = MDB_IMG_OK;
   }
-  int slot = 0;
-  std::vector<Pending> inflight;
-  auto drain_one = [&]() {
-    Pending pd = inflight.front();
-    inflight.erase(inflight.begin());
-    finish_chunk(e, pd, det_out, det_count, kept_anchor);
-  };
   for (auto& kv : groups) {
-    try {
-      Plan* P = get_plan(e, kv.first.first, kv.first.second);
-      const std::vector<int>& ids = kv.second;
-      // chunking: full max_batch chunks when there are several; otherwise two halves so that the upload of
-      // the second half overlaps the kernels of the first
-      size_t chunk = static_cast<size_t>(cfg.max_batch);
-      if (ids.size() <= chunk && ids.size() > 16 && e->pipeline_split > 1)
-        chunk = (ids.size() + e->pipeline_split - 1) / e->pipeline_split;
-      for (size_t b = 0; b < ids.size(); b += chunk) {
-        Pending pd;
-        pd.slot = slot;
-        pd.plan = P;
-        std::vector<LetterboxGeom> cg;
-        for (size_t j = b; j < std::min(ids.size(), b + chunk); ++j) {
-          pd.imgs.push_back(all[ids[j]]);
-          cg.push_back(geom[ids[j]]);
-        }
-        if (inflight.size() == 2) drain_one();
-        enqueue_chunk(e, P, pd.imgs, cg, conf_thres, slot);
-        inflight.push_back(pd);
-        slot ^= 1;
-      }
-    } catch (const CudaError& ex) {
-      // a whole shape group fails together (pytorch_detector.py:1236-1249)
-      e->err = ex.msg;
-      for (int id : kv.second) { status[all[id].index] = MDB_IMG_INFER_FAILED; det_count[all[id].index] = 0; }
-      // chunks of this group that were already queued must not be reported as good
-      for (auto it = inflight.begin(); it != inflight.end();)
-        it = (it->plan && it->plan->H == kv.first.first && it->plan->W == kv.first.second) ? inflight.erase(it) : it + 1;
-      cudaError_t sticky = cudaGetLastError();
-      if (sticky != cudaSuccess && cudaDeviceSynchronize() != cudaSuccess) return MDB_ERR_CUDA;
+    const std::vector<int>& ids = kv.second;
+    // chunking: max_batch-sized chunks when there are several; a single group that fits one chunk is split
+    // into `pipeline_split` parts so that uploads and host-side formatting overlap the kernels
+    size_t chunk = static_cast<size_t>(cfg.max_batch);
+    if (ids.size() <= chunk && ids.size() > 16 && e->pipeline_split > 1)
+      chunk = std::max<size_t>(8, (ids.size() + e->pipeline_split - 1) / e->pipeline_split);
+    for (size_t b = 0; b < ids.size(); b += chunk) {
+      ChunkJob job;
+      job.H = kv.first.first; job.W = kv.first.second;
+      job.ids.assign(ids.begin() + b, ids.begin() + std::min(ids.size(), b + chunk));
+      B.jobs.push_back(job);
     }
   }
   try {
-    while (!inflight.empty()) drain_one();
+    enqueue_next_job(e, B);
   } catch (const CudaError& ex) {
-    e->err = ex.msg;
-    return MDB_ERR_CUDA;
+    B.active = false;
+    return fail(e, MDB_ERR_CUDA, ex.msg);
   }
-  (void)n;
+  return MDB_OK;
+}
+
+// completes the oldest outstanding piece of work; writes the caller-array indices that became final
+int batch_next(mdb_engine* e, int32_t* done_idx, int32_t cap, int32_t* n_done) {
+  BatchState& B = e->batch;
+  *n_done = 0;
+  if (!B.active) return MDB_OK;
+  auto emit = [&](int idx) { if (*n_done < cap) done_idx[(*n_done)++] = idx; };
+  try {
+    if (!B.immediate.empty()) {
+      for (int idx : B.immediate) emit(idx);
+      B.immediate.clear();
+      return MDB_OK;
+    }
+    if (!B.failed_ready.empty()) {
+      const size_t j = B.failed_ready.front();
+      B.failed_ready.erase(B.failed_ready.begin());
+      for (int id : B.jobs[j].ids) emit(B.all[id].index);
+      return MDB_OK;
+    }
+    if (!B.inflight.empty()) {
+      Pending pd = B.inflight.front();
+      B.inflight.erase(B.inflight.begin());
+      try {
+        finish_chunk(e, pd, B.det_out, B.det_count, B.kept_anchor);
+      } catch (const CudaError& ex) {
+        fail_job(e, B, static_cast<size_t>(pd.job), ex.msg);
+        cudaError_t sticky = cudaGetLastError();
+        if (sticky != cudaSuccess && cudaDeviceSynchronize() != cudaSuccess) throw;
+      }
+      for (const ImgIn& im : pd.imgs) emit(im.index);
+      enqueue_next_job(e, B);
+      return MDB_OK;
+    }
+    enqueue_next_job(e, B);
+    if (B.inflight.empty() && B.failed_ready.empty()) B.active = false;
+    else return batch_next(e, done_idx, cap, n_done);
+  } catch (const CudaError& ex) {
+    B.active = false;
+    return fail(e, MDB_ERR_CUDA, ex.msg);
+  }
+  return MDB_OK;
+}
+
+int infer_common(mdb_engine* e, std::vector<ImgIn>& all, bool preprocessed, float conf_thres, float* det_out,
+                 int32_t* det_count, int32_t* kept_anchor, int32_t* status, int n) {
+  int rc = batch_begin(e, all, preprocessed, conf_thres, det_out, det_count, kept_anchor, status);
+  if (rc != MDB_OK) return rc;
+  std::vector<int32_t> done(std::max(1, n));
+  while (true) {
+    int32_t nd = 0;
+    rc = batch_next(e, done.data(), static_cast<int32_t>(done.size()), &nd);
+    if (rc != MDB_OK) return rc;
+    if (nd == 0) break;
+  }
   return MDB_OK;
 }
 
@@ -879,6 +986,27 @@ int mdb_profile_steps(mdb_engine* e, int32_t iters, float* ms_out, double* macs_
     return fail(e, MDB_ERR_CUDA, ex.msg);
   }
   return MDB_OK;
+}
+
+int mdb_batch_begin(mdb_engine* e, const uint8_t* const* rgb_hwc, const int32_t* h, const int32_t* w,
+                    const int64_t* row_stride, int32_t n, float conf_thres, float* det_out, int32_t* det_count,
+                    int32_t* kept_anchor, int32_t* status) {
+  if (!e || !rgb_hwc || !h || !w || !det_out || !det_count || !status || n < 0) return fail(e, MDB_ERR_ARG, "null argument");
+  try {
+    MDB_CUDA(cudaSetDevice(e->cfg.device));
+    std::vector<ImgIn> all(n);
+    for (int i = 0; i < n; ++i)
+      all[i] = ImgIn{rgb_hwc[i], h[i], w[i], row_stride ? row_stride[i] : static_cast<long long>(w[i]) * 3, h[i], w[i], i};
+    return batch_begin(e, all, false, conf_thres, det_out, det_count, kept_anchor, status);
+  } catch (const CudaError& ex) {
+    return fail(e, MDB_ERR_CUDA, ex.msg);
+  }
+}
+
+int mdb_batch_next(mdb_engine* e, int32_t* done_idx, int32_t cap, int32_t* n_done) {
+  if (!e || !done_idx || !n_done || cap < 1) return fail(e, MDB_ERR_ARG, "null argument");
+  if (cudaSetDevice(e->cfg.device) != cudaSuccess) return fail(e, MDB_ERR_CUDA, "cudaSetDevice failed");
+  return batch_next(e, done_idx, cap, n_done);
 }
 
 int mdb_last_timing(mdb_engine* e, float* ms4) {

@@ -273,35 +273,42 @@ class B200Detector:
                 ids[i] = ids[i] if ids[i] is not None else (image_id[i] if image_id else f'index_{i}')
                 results[i] = {'file': ids[i], 'detections': None, 'failure': FAILURE_IMAGE_OPEN}
         good = [i for i in range(n) if results[i] is None]
+
+        def finish(j, i, det, cnt, status):
+            if status[j] == _capi.MDB_IMG_BAD_INPUT:
+                results[i] = {'file': ids[i], 'detections': None, 'failure': FAILURE_IMAGE_OPEN}
+            elif status[j] != _capi.MDB_IMG_OK:
+                if verbose:
+                    print('Warning: batch inference failed for image {}: {}'.format(ids[i], self.engine.last_error()))
+                results[i] = {'file': ids[i], 'detections': None, 'failure': FAILURE_INFER}
+            else:
+                try:
+                    dets, max_conf = format_detections(det[j], cnt[j], src_shapes[i][0], src_shapes[i][1],
+                                                       self.use_model_native_classes)
+                    results[i] = {'file': ids[i], 'detections': dets, 'max_detection_conf': max_conf}
+                except KeyError as e:
+                    # the reference raises inside _process_batch_group and records an inference failure (:1236-1249)
+                    print('Warning: batch inference failed for image {}: {}'.format(ids[i], str(e)))
+                    results[i] = {'file': ids[i], 'detections': None, 'failure': FAILURE_INFER}
+
         if good:
             try:
                 if dict_mode:
                     det, cnt, _, status = self.engine.infer_preprocessed([arrays[i] for i in good],
                                                                          [src_shapes[i] for i in good],
                                                                          detection_threshold, want_anchors=False)
+                    for j, i in enumerate(good):
+                        finish(j, i, det, cnt, status)
                 else:
-                    det, cnt, _, status = self.engine.infer_batch([arrays[i] for i in good], detection_threshold,
-                                                                  want_anchors=False)
+                    # records of finished chunks are formatted while the GPU runs the following chunks
+                    for done, det, cnt, status in self.engine.infer_batch_stream([arrays[i] for i in good],
+                                                                                detection_threshold):
+                        for j in done:
+                            finish(j, good[j], det, cnt, status)
             except Exception as e:
                 print('Warning: batch inference failed: {}'.format(str(e)))
                 for i in good:
-                    results[i] = {'file': ids[i], 'detections': None, 'failure': FAILURE_INFER}
-                return results
-            for j, i in enumerate(good):
-                if status[j] == _capi.MDB_IMG_BAD_INPUT:
-                    results[i] = {'file': ids[i], 'detections': None, 'failure': FAILURE_IMAGE_OPEN}
-                elif status[j] != _capi.MDB_IMG_OK:
-                    if verbose:
-                        print('Warning: batch inference failed for image {}: {}'.format(ids[i], self.engine.last_error()))
-                    results[i] = {'file': ids[i], 'detections': None, 'failure': FAILURE_INFER}
-                else:
-                    try:
-                        dets, max_conf = format_detections(det[j], cnt[j], src_shapes[i][0], src_shapes[i][1],
-                                                           self.use_model_native_classes)
-                        results[i] = {'file': ids[i], 'detections': dets, 'max_detection_conf': max_conf}
-                    except KeyError as e:
-                        # the reference raises inside _process_batch_group and records an inference failure (:1236-1249)
-                        print('Warning: batch inference failed for image {}: {}'.format(ids[i], str(e)))
+                    if results[i] is None:
                         results[i] = {'file': ids[i], 'detections': None, 'failure': FAILURE_INFER}
         return results
 

@@ -16,6 +16,9 @@ CASES = {
     'c3x3_480': (16, 24, 40, 480, 480, 3, 1, 1, True),
     'stem': (16, 384, 640, 16, 80, 3, 1, 1, False),
     's2_80_160': (16, 384, 640, 80, 160, 3, 2, 1, False),
+    'c1x1_160_noact': (16, 96, 160, 160, 160, 1, 1, 0, False),
+    'c1x1_80': (16, 192, 320, 80, 80, 1, 1, 0, False),
+    'c1x1_640': (16, 48, 80, 640, 640, 1, 1, 0, False),
 }
 names = sys.argv[1].split(',') if len(sys.argv) > 1 else list(CASES)
 iters = int(sys.argv[2]) if len(sys.argv) > 2 else 10
@@ -28,7 +31,7 @@ for nm in names:
     b = np.zeros(co, np.float32)
     ho, wo = (h + 2 * p - k) // s + 1, (w + 2 * p - k) // s + 1
     r = rng.standard_normal((n, ho, wo, co)).astype(np.float16) if res else None
-    _, ms = e.op_conv2d(x, wt, b, k, s, p, act=True, residual=r, iters=iters)
+    _, ms = e.op_conv2d(x, wt, b, k, s, p, act=not nm.endswith('_noact'), residual=r, iters=iters)
     fl = 2.0 * n * ho * wo * co * ci * k * k
     byt = 2.0 * n * (h * w * ci + ho * wo * co * (2 if res else 1))
     print('%-10s %8.4f ms  %7.1f TFLOP/s  %6.0f GB/s (in+out%s)' % (nm, ms, fl / ms / 1e9, byt / ms / 1e6, '+res' if res else ''), flush=True)
