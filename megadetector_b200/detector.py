@@ -20,6 +20,7 @@ Not supported this round (raise NotImplementedError, never a silent approximatio
 than 'classic' (SURVEY.md par. 8f-4), `augment=True` (TTA), `force_cpu` (there is no CPU path).
 """
 
+import gc
 import math
 
 import numpy as np
@@ -291,6 +292,19 @@ class B200Detector:
                     print('Warning: batch inference failed for image {}: {}'.format(ids[i], str(e)))
                     results[i] = {'file': ids[i], 'detections': None, 'failure': FAILURE_INFER}
 
+        # A batch creates ~20 k small dicts/lists that all survive; with the cyclic collector enabled CPython
+        # re-traverses them over and over (measured: 35 ms vs 8 ms per 64 images).  They are acyclic, so the
+        # collector is paused while the records are built and restored afterwards.
+        gc_was_enabled = gc.isenabled()
+        gc.disable()
+        try:
+            self._infer_and_format(good, dict_mode, arrays, src_shapes, detection_threshold, finish, results, ids)
+        finally:
+            if gc_was_enabled:
+                gc.enable()
+        return results
+
+    def _infer_and_format(self, good, dict_mode, arrays, src_shapes, detection_threshold, finish, results, ids):
         if good:
             try:
                 if dict_mode:

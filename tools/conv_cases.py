@@ -19,6 +19,10 @@ CASES = {
     'c1x1_160_noact': (16, 96, 160, 160, 160, 1, 1, 0, False),
     'c1x1_80': (16, 192, 320, 80, 80, 1, 1, 0, False),
     'c1x1_640': (16, 48, 80, 640, 640, 1, 1, 0, False),
+    'p2_c64': (16, 192, 320, 64, 80, 3, 1, 1, False),
+    'p2_c80': (16, 192, 320, 80, 80, 3, 1, 1, False),
+    'p2_c128': (16, 192, 320, 128, 80, 3, 1, 1, False),
+    'stem_c64': (16, 384, 640, 64, 80, 3, 1, 1, False),
 }
 names = sys.argv[1].split(',') if len(sys.argv) > 1 else list(CASES)
 iters = int(sys.argv[2]) if len(sys.argv) > 2 else 10
