@@ -301,27 +301,36 @@ def cpu_baseline(n_images):
 
 
 def _main_quiet():
-    # the drop-in detector prints the reference's load-time messages ("PTDetector using device ...", which AddaxAI
-    # parses); bench.py's stdout must carry exactly one JSON line, so everything else goes to stderr
+    """
+    bench.py's stdout must carry exactly one JSON line.  The drop-in detector prints the reference's load-time
+    messages ("PTDetector using device ...", which AddaxAI parses) and NCCL prints its version banner from C, so
+    file descriptor 1 is pointed at stderr for the whole run and the JSON line is written to the saved descriptor.
+    """
     import contextlib
     import io
-    real_stdout = sys.stdout
+    sys.stdout.flush()
+    saved_fd = os.dup(1)
+    os.dup2(2, 1)
     lines = []
 
     class _Tee(io.TextIOBase):
         def write(self, t):
             for ln in t.splitlines(True):
-                if ln.startswith('{"') and '"metric"' in ln or ln.startswith('{"impl"'):
+                if (ln.startswith('{"metric"') or ln.startswith('{"impl"')):
                     lines.append(ln)
                 else:
                     sys.stderr.write(ln)
             return len(t)
 
-    with contextlib.redirect_stdout(_Tee()):
-        rc = main()
+    try:
+        with contextlib.redirect_stdout(_Tee()):
+            rc = main()
+    finally:
+        sys.stderr.flush()
+        os.dup2(saved_fd, 1)
     for ln in lines:
-        real_stdout.write(ln if ln.endswith('\n') else ln + '\n')
-    real_stdout.flush()
+        os.write(saved_fd, (ln if ln.endswith('\n') else ln + '\n').encode())
+    os.close(saved_fd)
     return rc
 
 

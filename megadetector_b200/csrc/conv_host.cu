@@ -170,6 +170,12 @@ ConvOp* conv_build(const ConvDesc& d, int num_sms) {
       q.act = p.act;
       q.idesc = make_idesc_f16(256, static_cast<uint32_t>(p.BN));
       q.dbg = nullptr;
+      q.halo = 0;
+      q.a_stages = 0;
+      {
+        static const char* ep = getenv("MDB_CONV_PROBE");
+        q.probe = ep ? atoi(ep) : 0;
+      }
       {
         const int oa = out.fp32 ? 8 : 16;  // elements per 32 bytes
         bool wide = (out.Ctot % oa == 0) && (out.c_off % oa == 0) && (reinterpret_cast<uintptr_t>(out.base) % 32 == 0);
@@ -179,6 +185,29 @@ ConvOp* conv_build(const ConvDesc& d, int num_sms) {
       }
       const size_t a_chunk = static_cast<size_t>(kTileM) * kc * 2;
       const size_t b_chunk = (static_cast<size_t>(p.BN / 2) * kc * 2 + 1023) & ~static_cast<size_t>(1023);
+      // 3x3 / stride-1 layers whose output tiles well with 8 x 16 blocks use the row-halo main loop
+      {
+        static const char* eh = getenv("MDB_CONV_HALO");
+        const bool allow = !(eh && eh[0] == '0');
+        const double eff = static_cast<double>(Ho) * Wo / (static_cast<double>((Wo + 7) / 8 * 8) * ((Ho + 15) / 16 * 16));
+        if (allow && kc == 64 && d.k == 3 && d.s == 1 && d.pad == 1 && eff >= 0.85 && p.chunks >= 3) {  // measured: +9% at 160 ch, 0 at 320, -10% at 80
+          q.halo = 1;
+          q.a_stages = 2;
+          q.tw = kHaloTw;
+          q.th = kHaloTh;
+          make_act_tmap(&op->tmA[0], in, kc, kHaloTw, kHaloRows, -1, -1);
+          op->tmA[1] = op->tmA[2] = op->tmA[3] = op->tmA[0];
+          const size_t budget = 227 * 1024 - 4096 - 1024;
+          const size_t a_bytes = static_cast<size_t>(q.a_stages) * 3 * kHaloBox;
+          int stages = static_cast<int>(std::min<size_t>(kPairMaxStages, (budget - a_bytes) / b_chunk));
+          MDB_REQUIRE(stages >= 4, "not enough shared memory for the halo pipeline");
+          q.stages = stages;
+          q.cps = 1;
+          op->smem = a_bytes + b_chunk * stages + 1024;
+          set_smem_attr_pair<64>(op->smem);
+          return op;
+        }
+      }
       const size_t stage = static_cast<size_t>(q.cps) * (a_chunk + b_chunk);
       const size_t budget = 227 * 1024 - 4096;  // static: barriers + bias staging; alignment slack
       const int stage_iters = (q.total_chunks + q.cps - 1) / q.cps;

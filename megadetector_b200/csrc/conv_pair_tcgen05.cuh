@@ -27,7 +27,11 @@ namespace mdb {
 
 constexpr int kPairEpiWarps = 16;  // four per TMEM lane quadrant
 constexpr int kPairThreads = 64 + 32 * kPairEpiWarps;
-constexpr int kPairMaxStages = 10;
+constexpr int kPairMaxStages = 12;
+constexpr int kHaloRows = 18;                       // th + 2
+constexpr int kHaloTw = 8, kHaloTh = 16;
+constexpr uint32_t kHaloBox = kHaloRows * kHaloTw * 128;  // bytes of one {64 ch, 8 px, 18 rows} box
+constexpr int kHaloMaxA = 3;
 
 struct PairParams {
   int n_img, H_out, W_out;
@@ -50,8 +54,11 @@ struct PairParams {
   int res_c_off;
   int act;
   int wide;        // 1: every epilogue row segment is 32-byte aligned -> 256-bit global accesses
+  int halo;        // 1: 3x3/s1 row-halo main loop (tile 8 x 16; A fetched per kw shift, reused across kh)
+  int a_stages;    // halo mode: number of A (3-box) buffers
   uint32_t idesc;  // M = 256
   long long* dbg;  // optional per-CTA cycle counters (MDB_CONV_DEBUG=1), null in production
+  int probe;       // timing probes only (results are garbage): 1 = skip TMA loads, 2 = skip MMAs
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -140,6 +147,25 @@ __device__ __forceinline__ void stg256(void* p, const uint4& a, const uint4& b) 
                "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
                : "memory");
 }
+// SiLU of four values with ONE reciprocal: 1/a, 1/b, 1/c, 1/d from r = 1/(abcd) and a few multiplies.  The SFU
+// (16 lanes per SM) is the scarcest unit of the epilogue; this cuts it from 2 to 1.25 operations per element.
+// a_i = 1 + 2^t with t clamped to 30 keeps abcd < 2^121; for x < -20.8 the result is |x| * 9.3e-10 instead of
+// something even smaller -- far below half precision.
+__device__ __forceinline__ void silu4(float& x0, float& x1, float& x2, float& x3) {
+  float e0, e1, e2, e3, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(fminf(x0 * -1.4426950408889634f, 30.0f)));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(fminf(x1 * -1.4426950408889634f, 30.0f)));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e2) : "f"(fminf(x2 * -1.4426950408889634f, 30.0f)));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e3) : "f"(fminf(x3 * -1.4426950408889634f, 30.0f)));
+  const float a = 1.0f + e0, b = 1.0f + e1, c = 1.0f + e2, d = 1.0f + e3;
+  const float ab = a * b, cd = c * d;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(ab * cd));
+  const float rab = r * cd, rcd = r * ab;
+  x0 *= rab * b;
+  x1 *= rab * a;
+  x2 *= rcd * d;
+  x3 *= rcd * c;
+}
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -164,6 +190,8 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   __shared__ __align__(8) uint64_t empty_bar[kPairMaxStages];
   __shared__ __align__(8) uint64_t acc_full_bar[2];
   __shared__ __align__(8) uint64_t acc_empty_bar[2];
+  __shared__ __align__(8) uint64_t a_full_bar[kHaloMaxA];
+  __shared__ __align__(8) uint64_t a_empty_bar[kHaloMaxA];
   __shared__ uint32_t tmem_base_smem;
   __shared__ __align__(16) float bias_s[2][256];
 
@@ -197,6 +225,10 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       mbar_init(&full_bar[s], 2);   // leader's instance is the one in use: both producers arrive
       mbar_init(&empty_bar[s], 1);  // multicast commit of the leader's MMA thread
     }
+    for (int a = 0; a < kHaloMaxA; ++a) {
+      mbar_init(&a_full_bar[a], 2);
+      mbar_init(&a_empty_bar[a], 1);
+    }
     mbar_init(&acc_full_bar[0], 1);
     mbar_init(&acc_full_bar[1], 1);
     mbar_init(&acc_empty_bar[0], 2 * kPairEpiWarps);  // leader's instance: 8 warps of each CTA
@@ -227,6 +259,45 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       int s = 0;
       uint32_t ph = 0;
       const uint32_t tx_stage = 2u * tx_per_chunk;  // both CTAs' bytes of one chunk
+      if (p.halo) {
+        // ---- 3x3 / stride 1: per 64-channel chunk, three {64 ch, 8 px, 18 rows} boxes (one per kw shift) are
+        // fetched once and serve all three kh taps (the kh shift is a 1024-byte offset in shared memory);
+        // weights stream through their own ring, one tap per stage.  A bytes per chunk: 55 KB instead of 147 KB.
+        const uint32_t a_region = smem_base;
+        const uint32_t a_stage_bytes = 3u * kHaloBox;
+        const uint32_t b_region = smem_base + static_cast<uint32_t>(p.a_stages) * a_stage_bytes;
+        const uint32_t b_bytes = half_n * ROW_BYTES;
+        int as = 0;
+        uint32_t aph = 0;
+        for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
+          const int n_tile = tile % p.n_tiles;
+          const int m_tile = 2 * (tile / p.n_tiles) + static_cast<int>(rank);
+          const int txi = m_tile % p.tiles_x;
+          const int tyi = (m_tile / p.tiles_x) % p.tiles_y;
+          const int img = m_tile / (p.tiles_x * p.tiles_y);
+          const int ox0 = txi * kHaloTw, oy0 = tyi * kHaloTh;
+          const int nb0 = n_tile * p.BN + static_cast<int>(rank * half_n);
+          for (int c = 0; c < p.chunks; ++c) {
+            mbar_wait_timed(&a_empty_bar[as], aph ^ 1u, w_empty, dbg);
+            if (leader) mbar_arrive_expect_tx(&a_full_bar[as], 2u * a_stage_bytes);
+            else mbar_arrive_remote(&a_full_bar[as], 0);
+            const uint32_t abase = a_region + static_cast<uint32_t>(as) * a_stage_bytes;
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw)
+              tma2_load_4d(&tmA0, &a_full_bar[as], abase + static_cast<uint32_t>(kw) * kHaloBox, c * KC, ox0 + kw - 1,
+                           oy0 - 1, img);
+            if (++as == p.a_stages) { as = 0; aph ^= 1u; }
+            for (int tap = 0; tap < 9; ++tap) {
+              mbar_wait_timed(&empty_bar[s], ph ^ 1u, w_empty, dbg);
+              if (leader) mbar_arrive_expect_tx(&full_bar[s], 2u * b_bytes);
+              else mbar_arrive_remote(&full_bar[s], 0);
+              tma2_load_2d(&tmB, &full_bar[s], b_region + static_cast<uint32_t>(s) * b_chunk, tap * p.Cin + c * KC, nb0);
+              if (++s == S) { s = 0; ph ^= 1u; }
+              ++it;
+            }
+          }
+        }
+      } else
       for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
         const int n_tile = tile % p.n_tiles;
         const int m_tile = 2 * (tile / p.n_tiles) + static_cast<int>(rank);
@@ -257,12 +328,14 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         for (int done = 0; done < p.total_chunks;) {
           const int nch = min(p.cps, p.total_chunks - done);
           mbar_wait_timed(&empty_bar[s], ph ^ 1u, w_empty, dbg);
-          if (leader) mbar_arrive_expect_tx(&full_bar[s], static_cast<uint32_t>(nch) * tx_stage);
+          if (leader) mbar_arrive_expect_tx(&full_bar[s], p.probe == 1 ? 0u : static_cast<uint32_t>(nch) * tx_stage);
           else mbar_arrive_remote(&full_bar[s], 0);
           uint32_t dst = smem_base + static_cast<uint32_t>(s) * stage_bytes;
           for (int j = 0; j < nch; ++j, dst += chunk_bytes) {
-            tma2_load_4d(ma, &full_bar[s], dst, c * KC, x, y, img);
-            tma2_load_2d(&tmB, &full_bar[s], dst + A_CHUNK, kcol, nb0);
+            if (p.probe != 1) {
+              tma2_load_4d(ma, &full_bar[s], dst, c * KC, x, y, img);
+              tma2_load_2d(&tmB, &full_bar[s], dst + A_CHUNK, kcol, nb0);
+            }
             kcol += KC;
             if (++c == p.chunks) {
               c = 0;
@@ -290,6 +363,8 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       const long long t_start = clock64();
       int s = 0;
       uint32_t ph = 0;
+      int as = 0;
+      uint32_t aph = 0;
       // descriptor template: everything except the 14-bit start address is constant for the whole kernel
       const uint64_t desc_tmpl = make_kmajor_desc(0, ROW_BYTES);
       for (int tile = cluster_id; tile < total_tiles; tile += num_clusters, ++tcount) {
@@ -298,6 +373,33 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         mbar_wait_timed(&acc_empty_bar[acc], acc_ph ^ 1u, w_acc, dbg);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * kAccStride;
+        if (p.halo) {
+          const uint32_t a_stage_bytes = 3u * kHaloBox;
+          const uint32_t b_region = smem_base + static_cast<uint32_t>(p.a_stages) * a_stage_bytes;
+          for (int c = 0; c < p.chunks; ++c) {
+            mbar_wait_timed(&a_full_bar[as], aph, w_full, dbg);
+            tc_fence_after();
+            const uint32_t abase = smem_base + static_cast<uint32_t>(as) * a_stage_bytes;
+            for (int tap = 0; tap < 9; ++tap) {
+              const int kh = tap / 3, kw = tap - 3 * kh;
+              mbar_wait_timed(&full_bar[s], ph, w_full, dbg);
+              tc_fence_after();
+              // rows of the tile for this tap: halo rows kh .. kh+15 of the kw-shifted box (8 px = 1024 B per row)
+              const uint32_t a_addr = abase + static_cast<uint32_t>(kw) * kHaloBox + static_cast<uint32_t>(kh) * 1024u;
+              const uint32_t b_addr = b_region + static_cast<uint32_t>(s) * b_chunk;
+              const uint64_t da = desc_tmpl | static_cast<uint64_t>((a_addr & 0x3FFFFu) >> 4);
+              const uint64_t db = desc_tmpl | static_cast<uint64_t>((b_addr & 0x3FFFFu) >> 4);
+#pragma unroll
+              for (int k = 0; k < KC / 16; ++k)
+                umma2_f16(d_tmem, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), p.idesc,
+                          (c > 0 || tap > 0 || k > 0) ? 1u : 0u);
+              umma2_commit_mc(&empty_bar[s]);
+              if (++s == S) { s = 0; ph ^= 1u; }
+            }
+            umma2_commit_mc(&a_empty_bar[as]);
+            if (++as == p.a_stages) { as = 0; aph ^= 1u; }
+          }
+        } else
         for (int done = 0; done < p.total_chunks;) {
           const int nch = min(p.cps, p.total_chunks - done);
           mbar_wait_timed(&full_bar[s], ph, w_full, dbg);
@@ -306,10 +408,12 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           for (int j = 0; j < nch; ++j, a_addr += chunk_bytes) {
             const uint64_t da = desc_tmpl | static_cast<uint64_t>((a_addr & 0x3FFFFu) >> 4);
             const uint64_t db = desc_tmpl | static_cast<uint64_t>(((a_addr + A_CHUNK) & 0x3FFFFu) >> 4);
+            if (p.probe != 2) {
 #pragma unroll
-            for (int k = 0; k < KC / 16; ++k)
-              umma2_f16(d_tmem, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), p.idesc,
-                        (done > 0 || j > 0 || k > 0) ? 1u : 0u);
+              for (int k = 0; k < KC / 16; ++k)
+                umma2_f16(d_tmem, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), p.idesc,
+                          (done > 0 || j > 0 || k > 0) ? 1u : 0u);
+            }
           }
           umma2_commit_mc(&empty_bar[s]);
           done += nch;
@@ -383,7 +487,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         }
         if (p.act) {
 #pragma unroll
-          for (int e = 0; e < 16; ++e) f[e] = silu_fast(f[e]);
+          for (int e = 0; e < 16; e += 4) silu4(f[e], f[e + 1], f[e + 2], f[e + 3]);
         }
         if (p.res != nullptr) {
           const __half2* h0 = reinterpret_cast<const __half2*>(&r0);
