@@ -72,6 +72,8 @@ struct ConvDesc {
   int cout = 0, cout_pad = 0;
   int cin_pad = 0;  // channels per filter tap in the packed weights (>= in.C, zero padded)
   int k = 1, s = 1, pad = 0, act = 1;
+  int kw = 0;      // filter width when it differs from k (0: square)
+  int pad_x = -1;  // column padding when it differs from pad (-1: same)
 };
 ConvOp* conv_build(const ConvDesc& d, int num_sms);
 void conv_launch(ConvOp* op, int n_img, cudaStream_t st);
@@ -81,7 +83,7 @@ int conv_pick_bn(int cout_pad);
 
 // weight re-layout helpers (host): PyTorch [co][ci][k][k] fp32 -> [co_pad][k][k][ci_pad] fp16
 void pack_weights_khwc(const float* w, int co, int ci, int k, int co_pad, int ci_pad, std::vector<__half>& out);
-// stem: [co][3][6][6] -> 3x3 conv over the 2x2 space-to-depth input with 16 (12 used) channels
+// stem: [co][3][6][6] -> 3x1 conv over K1's tap-packed space-to-depth image (64 channels = 3 kw taps x 16)
 void pack_weights_stem_s2d(const float* w, int co, int co_pad, int ci_pad, std::vector<__half>& out);
 
 // ---------------------------------------------------------------------------------------------

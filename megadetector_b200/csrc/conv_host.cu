@@ -99,19 +99,22 @@ ConvOp* conv_build(const ConvDesc& d, int num_sms) {
     op->kc = kc;
     op->num_sms = num_sms;
     ConvParams& p = op->p;
+    const int kw = d.kw > 0 ? d.kw : d.k;
+    const int pad_x = d.pad_x >= 0 ? d.pad_x : d.pad;
     const int Ho = (in.H + 2 * d.pad - d.k) / d.s + 1;
-    const int Wo = (in.W + 2 * d.pad - d.k) / d.s + 1;
+    const int Wo = (in.W + 2 * pad_x - kw) / d.s + 1;
     MDB_REQUIRE(Ho == out.H && Wo == out.W && out.N == in.N, "conv output view has the wrong shape");
     op->HW_out = Ho * Wo;
     p.H_out = Ho;
     p.W_out = Wo;
-    op->macs_per_image = static_cast<double>(Ho) * Wo * d.cout * in.C * d.k * d.k;
+    op->macs_per_image = static_cast<double>(Ho) * Wo * d.cout * in.C * d.k * kw;
     op->flat = (d.k == 1 && d.s == 1 && d.pad == 0);
 
     p.BN = conv_pick_bn(d.cout_pad);
     p.n_tiles = d.cout_pad / p.BN;
     p.Cout = d.cout;
-    p.KH = p.KW = d.k;
+    p.KH = d.k;
+    p.KW = kw;
     p.stride = d.s;
     p.pad = d.pad;
     p.Cin = d.cin_pad;
@@ -151,13 +154,13 @@ ConvOp* conv_build(const ConvDesc& d, int num_sms) {
     op->pair = use_pair_kernel();
     if (op->pair) {
       // CTA pair: each CTA stages half of the B tile
-      make_wgt_tmap(&op->tmB, d.wgt, d.k * d.k * d.cin_pad, d.cout_pad, kc, p.BN / 2);
+      make_wgt_tmap(&op->tmB, d.wgt, d.k * kw * d.cin_pad, d.cout_pad, kc, p.BN / 2);
       PairParams& q = op->pp;
       q.H_out = p.H_out; q.W_out = p.W_out; q.tw = p.tw; q.th = p.th;
       q.n_tiles = p.n_tiles; q.BN = p.BN; q.Cout = p.Cout;
-      q.KH = p.KH; q.KW = p.KW; q.stride = p.stride; q.pad = p.pad;
+      q.KH = p.KH; q.KW = p.KW; q.stride = p.stride; q.pad = p.pad; q.pad_x = pad_x;
       q.chunks = p.chunks; q.Cin = p.Cin;
-      q.total_chunks = d.k * d.k * p.chunks;
+      q.total_chunks = d.k * kw * p.chunks;
       // chunks per pipeline stage: enough MMA time per mbarrier round trip (>= ~320 tensor cycles)
       {
         static const char* e = getenv("MDB_CONV_CPS");
@@ -190,7 +193,7 @@ ConvOp* conv_build(const ConvDesc& d, int num_sms) {
         static const char* eh = getenv("MDB_CONV_HALO");
         const bool allow = !(eh && eh[0] == '0');
         const double eff = static_cast<double>(Ho) * Wo / (static_cast<double>((Wo + 7) / 8 * 8) * ((Ho + 15) / 16 * 16));
-        if (allow && kc == 64 && d.k == 3 && d.s == 1 && d.pad == 1 && eff >= 0.85 && p.chunks >= 3) {  // measured: +9% at 160 ch, 0 at 320, -10% at 80
+        if (allow && kc == 64 && d.k == 3 && kw == 3 && d.s == 1 && d.pad == 1 && pad_x == 1 && eff >= 0.85 && p.chunks >= 3) {  // measured: +9% at 160 ch, 0 at 320, -10% at 80
           q.halo = 1;
           q.a_stages = 2;
           q.tw = kHaloTw;
@@ -220,6 +223,7 @@ ConvOp* conv_build(const ConvDesc& d, int num_sms) {
       else set_smem_attr_pair<16>(op->smem);
       return op;
     }
+    MDB_REQUIRE(kw == d.k && pad_x == d.pad, "the single-CTA fallback kernel handles square filters only");
     make_wgt_tmap(&op->tmB, d.wgt, d.k * d.k * d.cin_pad, d.cout_pad, kc, p.BN);
 
     const size_t a_bytes = static_cast<size_t>(kTileM) * kc * 2;
@@ -339,15 +343,18 @@ void pack_weights_khwc(const float* w, int co, int ci, int k, int co_pad, int ci
 }
 
 void pack_weights_stem_s2d(const float* w, int co, int co_pad, int ci_pad, std::vector<__half>& out) {
-  // 6x6 stride-2 pad-2 conv over RGB == 3x3 stride-1 pad-1 conv over the 2x2 space-to-depth image whose
-  // channel is (py*2+px)*3+c:  W'[o][a][b][(py*2+px)*3+c] = W[o][c][2a+py][2b+px]
-  out.assign(static_cast<size_t>(co_pad) * 9 * ci_pad, __float2half(0.f));
+  // 6x6 stride-2 pad-2 conv over RGB == 3x3 stride-1 pad-1 conv over the 2x2 space-to-depth image whose channel is
+  // (py*2+px)*3+c.  K1 additionally packs the three column taps into the channel dimension (channel t*16 + ...
+  // holds the s2d pixel at column x + t - 1), so the stem runs as a 3 (rows) x 1 conv over 64 channels:
+  //   W'[o][a][0][t*16 + (py*2+px)*3 + c] = W[o][c][2a+py][2t+px]
+  MDB_REQUIRE(ci_pad == 64, "stem weights are packed for 64 input channels");
+  out.assign(static_cast<size_t>(co_pad) * 3 * ci_pad, __float2half(0.f));
   for (int o = 0; o < co; ++o)
     for (int c = 0; c < 3; ++c)
       for (int ky = 0; ky < 6; ++ky)
         for (int kx = 0; kx < 6; ++kx) {
-          const int a = ky / 2, py = ky % 2, b = kx / 2, px = kx % 2;
-          out[((static_cast<size_t>(o) * 3 + a) * 3 + b) * ci_pad + (py * 2 + px) * 3 + c] =
+          const int a = ky / 2, py = ky % 2, t = kx / 2, px = kx % 2;
+          out[(static_cast<size_t>(o) * 3 + a) * ci_pad + t * 16 + (py * 2 + px) * 3 + c] =
               __float2half_rn(w[((static_cast<size_t>(o) * 3 + c) * 6 + ky) * 6 + kx]);
         }
 }

@@ -39,7 +39,8 @@ struct PairParams {
   int tiles_x, tiles_y;
   int m_tiles, pair_m, n_tiles;
   int BN, Cout;
-  int KH, KW, stride, pad;
+  int KH, KW, stride, pad;  // pad = rows (y)
+  int pad_x;                // columns; differs from pad only for the 3x1 stem
   int chunks;        // C_in / KC
   int Cin;
   int total_chunks;  // KH*KW*chunks
@@ -188,8 +189,8 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[kPairMaxStages];
   __shared__ __align__(8) uint64_t empty_bar[kPairMaxStages];
-  __shared__ __align__(8) uint64_t acc_full_bar[2];
-  __shared__ __align__(8) uint64_t acc_empty_bar[2];
+  __shared__ __align__(8) uint64_t acc_full_bar[4];
+  __shared__ __align__(8) uint64_t acc_empty_bar[4];
   __shared__ __align__(8) uint64_t a_full_bar[kHaloMaxA];
   __shared__ __align__(8) uint64_t a_empty_bar[kHaloMaxA];
   __shared__ uint32_t tmem_base_smem;
@@ -209,6 +210,10 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   const uint32_t tx_per_chunk = static_cast<uint32_t>(p.tw * p.th) * ROW_BYTES + half_n * ROW_BYTES;
 
   const int S = p.stages;
+  // TMEM accumulator ring: 512 columns hold 2 stages of up to 256 columns or 4 stages of up to 128
+  const uint32_t acc_shift = p.BN <= 128 ? 2u : 1u;
+  const uint32_t acc_mask = (1u << acc_shift) - 1u;
+  const uint32_t acc_stride = p.BN <= 128 ? 128u : 256u;
   const int total_tiles = p.pair_m * p.n_tiles;
   const int num_clusters = gridDim.x >> 1;
   const int cluster_id = blockIdx.x >> 1;
@@ -229,10 +234,10 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       mbar_init(&a_full_bar[a], 2);
       mbar_init(&a_empty_bar[a], 1);
     }
-    mbar_init(&acc_full_bar[0], 1);
-    mbar_init(&acc_full_bar[1], 1);
-    mbar_init(&acc_empty_bar[0], 2 * kPairEpiWarps);  // leader's instance: 8 warps of each CTA
-    mbar_init(&acc_empty_bar[1], 2 * kPairEpiWarps);
+    for (int a = 0; a < 4; ++a) {
+      mbar_init(&acc_full_bar[a], 1);
+      mbar_init(&acc_empty_bar[a], 2 * kPairEpiWarps);  // leader's instance: every epilogue warp of both CTAs
+    }
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -312,11 +317,11 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         int x = 0, y = 0;
         auto set_tap = [&]() {
           if (p.stride == 1) {
-            x = ox0 + kw - p.pad;
+            x = ox0 + kw - p.pad_x;
             y = oy0 + kh - p.pad;
             ma = &tmA0;
           } else {
-            const int ty_ = kh - p.pad, tx_ = kw - p.pad;
+            const int ty_ = kh - p.pad, tx_ = kw - p.pad_x;
             const int py = ty_ & 1, px = tx_ & 1;
             y = oy0 + ((ty_ - py) >> 1);
             x = ox0 + ((tx_ - px) >> 1);
@@ -368,11 +373,11 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       // descriptor template: everything except the 14-bit start address is constant for the whole kernel
       const uint64_t desc_tmpl = make_kmajor_desc(0, ROW_BYTES);
       for (int tile = cluster_id; tile < total_tiles; tile += num_clusters, ++tcount) {
-        const uint32_t acc = tcount & 1u;
-        const uint32_t acc_ph = (tcount >> 1) & 1u;
+        const uint32_t acc = tcount & acc_mask;
+        const uint32_t acc_ph = (tcount >> acc_shift) & 1u;
         mbar_wait_timed(&acc_empty_bar[acc], acc_ph ^ 1u, w_acc, dbg);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * kAccStride;
+        const uint32_t d_tmem = tmem_base + acc * acc_stride;
         if (p.halo) {
           const uint32_t a_stage_bytes = 3u * kHaloBox;
           const uint32_t b_region = smem_base + static_cast<uint32_t>(p.a_stages) * a_stage_bytes;
@@ -441,8 +446,8 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     const int nchunks = p.BN >> 4;
     uint32_t tcount = 0;
     for (int tile = cluster_id; tile < total_tiles; tile += num_clusters, ++tcount) {
-      const uint32_t acc = tcount & 1u;
-      const uint32_t acc_ph = (tcount >> 1) & 1u;
+      const uint32_t acc = tcount & acc_mask;
+      const uint32_t acc_ph = (tcount >> acc_shift) & 1u;
       const int n_tile = tile % p.n_tiles;
       const int m_tile = 2 * (tile / p.n_tiles) + static_cast<int>(rank);
       const int txi = m_tile % p.tiles_x;
@@ -460,7 +465,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 
       mbar_wait(&acc_full_bar[acc], acc_ph);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((quad * 32u) << 16) + acc * kAccStride;
+      const uint32_t taddr = tmem_base + ((quad * 32u) << 16) + acc * acc_stride;
       // one 16-column chunk: +bias -> SiLU -> (+residual) -> store.  Registers only (static indexing).
       auto process = [&](const uint32_t (&vv)[16], int jj) {
         const int col0 = n0 + jj * 16;

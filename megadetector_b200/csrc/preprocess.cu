@@ -6,12 +6,14 @@
 //   * HWC->CHW, ascontiguousarray, stack, .float(), /= 255.0 at pytorch_detector.py:1283-1306
 // The arithmetic is OpenCV's 8-bit fixed-point bilinear (11-bit coefficients), reproduced exactly:
 // coefficient tables are built on the host with the same float/double operations cv::resize uses, the
-// kernel is pure integer.  The output is what the first convolution wants to read: the 6x6/s2 stem is run
-// as a 3x3/s1 convolution over the 2x2 space-to-depth image, so K1 writes [H/2][W/2][16] fp16 with channel
-// (py*2+px)*3+c (12 used, 4 zero) -- one 32-byte store per thread, fully coalesced.
+// kernel is pure integer.  The output is what the first convolution wants to read: the 6x6/s2 stem equals a 3x3/s1
+// convolution over the 2x2 space-to-depth image (channel (py*2+px)*3+c); K1 also packs the three COLUMN taps
+// into the channel dimension, [H/2][W/2][64] fp16 (3 x (12 used + 4 zero) + 16 zero), so that the stem becomes a
+// 3x1 convolution whose operand rows are full 128-byte swizzle rows (measured: 9 mostly zero-filled 64-channel
+// chunks cost as much shared-memory fill as 9 real ones; 3 real chunks cost a third).
 //
 // HBM traffic per 1920x1080 -> 768x1280 image: 6.22 MB read (each source byte once, staged through shared
-// memory with 128-bit loads) + 7.86 MB written.
+// memory with 128-bit loads) + 31.5 MB written.
 #include <algorithm>
 #include <cmath>
 
@@ -81,21 +83,29 @@ void linear_tables(int ssize, int dsize, bool vertical, std::vector<int32_t>& of
 constexpr int kPreThreads = 256;
 constexpr int kTileW2 = 64;  // s2d columns per CTA  (128 output columns)
 constexpr int kTileH2 = 8;   // s2d rows per CTA     (16 output rows)
+constexpr int kHaloW2 = kTileW2 + 2;  // one extra s2d column on each side: the stem's column taps
 
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
+// Output layout (what the stem convolution reads, see pack_weights_stem_s2d): per s2d pixel (y, x) 64 fp16 channels,
+//   [t*16 + (py*2+px)*3 + c]  = normalised letterboxed pixel (2y+py, 2(x+t-1)+px), channel c, for t = 0,1,2
+// i.e. the three column taps of the stem packed into the channel dimension (zero outside the image = the conv's
+// zero padding; channels 12..15 of every tap and 48..63 are zero).  One 128-byte row per thread, fully coalesced.
 // STAGED: the source window of the tile is first copied to shared memory with 16-byte loads.
 template <bool STAGED>
 __global__ void __launch_bounds__(kPreThreads) letterbox_s2d_kernel(const PreImage* __restrict__ imgs, int out_h,
                                                                    int out_w, __half* __restrict__ dst,
                                                                    int smem_row_bytes, int smem_rows) {
-  extern __shared__ __align__(16) uint8_t s_src[];
+  extern __shared__ __align__(16) uint8_t s_dyn[];
+  // [kTileH2][kHaloW2] entries of 16 halves (12 used): the letterboxed, normalised s2d tile with column halo
+  uint4* s_tile = reinterpret_cast<uint4*>(s_dyn);
+  uint8_t* s_src = s_dyn + static_cast<size_t>(kTileH2) * kHaloW2 * 32;
   const PreImage im = imgs[blockIdx.z];
   const int W2 = out_w >> 1, H2 = out_h >> 1;
   const int sx2_0 = blockIdx.x * kTileW2, sy2_0 = blockIdx.y * kTileH2;
 
-  // output-pixel window of this tile that lies inside the resized image
-  const int ox_lo = max(2 * sx2_0, im.left), ox_hi = min(2 * (sx2_0 + kTileW2), im.left + im.new_w) - 1;
+  // output-pixel window (with the column halo) of this tile that lies inside the resized image
+  const int ox_lo = max(2 * (sx2_0 - 1), im.left), ox_hi = min(2 * (sx2_0 + kTileW2 + 1), im.left + im.new_w) - 1;
   const int oy_lo = max(2 * sy2_0, im.top), oy_hi = min(2 * (sy2_0 + kTileH2), im.top + im.new_h) - 1;
   const bool any_src = (ox_lo <= ox_hi) && (oy_lo <= oy_hi);
 
@@ -126,59 +136,79 @@ __global__ void __launch_bounds__(kPreThreads) letterbox_s2d_kernel(const PreIma
     __syncthreads();
   }
 
-  auto fetch = [&](int sy, int sxb) -> int {  // byte sxb of source row sy
+  // start of source row sy (byte 0 of the row) as an offset into s_src / a pointer into global memory
+  auto row_ptr = [&](int sy) -> const uint8_t* {
+    const uint8_t* g = im.src + static_cast<long long>(sy) * im.src_stride;
     if (STAGED) {
-      const uint8_t* p = im.src + static_cast<long long>(sy) * im.src_stride + byte0;
-      const int shift = static_cast<int>(reinterpret_cast<uintptr_t>(p) & 15);
-      return s_src[static_cast<size_t>(sy - row0) * smem_row_bytes + shift + (sxb - byte0)];
-    } else {
-      return __ldg(im.src + static_cast<long long>(sy) * im.src_stride + sxb);
+      const int shift = static_cast<int>(reinterpret_cast<uintptr_t>(g + byte0) & 15);
+      return s_src + static_cast<size_t>(sy - row0) * smem_row_bytes + shift - byte0;
     }
+    return g;
   };
 
+  // ---- phase 1: letterbox (OpenCV-exact bilinear or pad) every s2d pixel of the tile + halo columns ----
+  for (int t = threadIdx.x; t < kHaloW2 * kTileH2; t += kPreThreads) {
+    const int lx = t % kHaloW2, ly = t / kHaloW2;
+    const int sx2 = sx2_0 + lx - 1, sy2 = sy2_0 + ly;
+    __align__(16) __half px[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) px[i] = __ushort_as_half(0);
+    if (sx2 >= 0 && sx2 < W2 && sy2 < H2) {
+#pragma unroll
+      for (int py = 0; py < 2; ++py) {
+        const int oy = 2 * sy2 + py;
+        const int dy = oy - im.top;
+        const bool in_y = dy >= 0 && dy < im.new_h;
+        int b0 = 0, b1 = 0;
+        const uint8_t* r0 = nullptr;
+        const uint8_t* r1 = nullptr;
+        if (in_y) {
+          const int s = im.yofs[dy];
+          r0 = row_ptr(clampi(s, 0, im.src_h - 1));
+          r1 = row_ptr(clampi(s + 1, 0, im.src_h - 1));
+          b0 = im.ycoef[2 * dy];
+          b1 = im.ycoef[2 * dy + 1];
+        }
+#pragma unroll
+        for (int pxx = 0; pxx < 2; ++pxx) {
+          const int ox = 2 * sx2 + pxx;
+          const int dx = ox - im.left;
+          int v[3] = {114, 114, 114};
+          if (in_y && dx >= 0 && dx < im.new_w) {
+            const int sx0 = im.xofs[dx];
+            const int o0 = sx0 * 3, o1 = min(sx0 + 1, im.src_w - 1) * 3;
+            const int a0 = im.xcoef[2 * dx], a1 = im.xcoef[2 * dx + 1];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              const int h0 = (STAGED ? r0[o0 + c] : __ldg(r0 + o0 + c)) * a0 + (STAGED ? r0[o1 + c] : __ldg(r0 + o1 + c)) * a1;
+              const int h1 = (STAGED ? r1[o0 + c] : __ldg(r1 + o0 + c)) * a0 + (STAGED ? r1[o1 + c] : __ldg(r1 + o1 + c)) * a1;
+              v[c] = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
+            }
+          }
+#pragma unroll
+          for (int c = 0; c < 3; ++c) px[(py * 2 + pxx) * 3 + c] = c_norm_lut[v[c] & 255];
+        }
+      }
+    }
+    s_tile[t * 2] = reinterpret_cast<const uint4*>(px)[0];
+    s_tile[t * 2 + 1] = reinterpret_cast<const uint4*>(px)[1];
+  }
+  __syncthreads();
+
+  // ---- phase 2: one packed 128-byte row per s2d pixel: taps x-1, x, x+1, then 32 zero bytes ----
   for (int t = threadIdx.x; t < kTileW2 * kTileH2; t += kPreThreads) {
     const int lx = t % kTileW2, ly = t / kTileW2;
     const int sx2 = sx2_0 + lx, sy2 = sy2_0 + ly;
     if (sx2 >= W2 || sy2 >= H2) continue;
-    __align__(16) __half px[16];
+    uint4* o = reinterpret_cast<uint4*>(dst + ((static_cast<size_t>(blockIdx.z) * H2 + sy2) * W2 + sx2) * 64);
+    const uint4* e = s_tile + (ly * kHaloW2 + lx) * 2;  // entry of column x-1
 #pragma unroll
-    for (int i = 12; i < 16; ++i) px[i] = __ushort_as_half(0);
-#pragma unroll
-    for (int py = 0; py < 2; ++py) {
-      const int oy = 2 * sy2 + py;
-      const int dy = oy - im.top;
-      const bool in_y = dy >= 0 && dy < im.new_h;
-      int sy0 = 0, sy1 = 0, b0 = 0, b1 = 0;
-      if (in_y) {
-        const int s = im.yofs[dy];
-        sy0 = clampi(s, 0, im.src_h - 1);
-        sy1 = clampi(s + 1, 0, im.src_h - 1);
-        b0 = im.ycoef[2 * dy];
-        b1 = im.ycoef[2 * dy + 1];
-      }
-#pragma unroll
-      for (int pxx = 0; pxx < 2; ++pxx) {
-        const int ox = 2 * sx2 + pxx;
-        const int dx = ox - im.left;
-        int v[3] = {114, 114, 114};
-        if (in_y && dx >= 0 && dx < im.new_w) {
-          const int sx0 = im.xofs[dx];
-          const int sx1 = min(sx0 + 1, im.src_w - 1);
-          const int a0 = im.xcoef[2 * dx], a1 = im.xcoef[2 * dx + 1];
-#pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            const int h0 = fetch(sy0, sx0 * 3 + c) * a0 + fetch(sy0, sx1 * 3 + c) * a1;
-            const int h1 = fetch(sy1, sx0 * 3 + c) * a0 + fetch(sy1, sx1 * 3 + c) * a1;
-            v[c] = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
-          }
-        }
-#pragma unroll
-        for (int c = 0; c < 3; ++c) px[(py * 2 + pxx) * 3 + c] = c_norm_lut[v[c] & 255];
-      }
+    for (int tap = 0; tap < 3; ++tap) {
+      o[2 * tap] = e[2 * tap];
+      o[2 * tap + 1] = e[2 * tap + 1];
     }
-    uint4* o = reinterpret_cast<uint4*>(dst + ((static_cast<size_t>(blockIdx.z) * H2 + sy2) * W2 + sx2) * 16);
-    o[0] = reinterpret_cast<const uint4*>(px)[0];
-    o[1] = reinterpret_cast<const uint4*>(px)[1];
+    o[6] = make_uint4(0, 0, 0, 0);
+    o[7] = make_uint4(0, 0, 0, 0);
   }
 }
 
@@ -188,10 +218,11 @@ void preprocess_launch(const PreImage* d_imgs, int n, int out_h, int out_w, __ha
   const int W2 = out_w / 2, H2 = out_h / 2;
   dim3 grid((W2 + kTileW2 - 1) / kTileW2, (H2 + kTileH2 - 1) / kTileH2, n);
   // source window of one tile: (2*tile+1)*scale + 2 pixels each way, plus alignment slack
-  const int src_cols = static_cast<int>(std::ceil((2 * kTileW2 + 1) * max_scale)) + 3;
+  const int src_cols = static_cast<int>(std::ceil((2 * kHaloW2 + 1) * max_scale)) + 3;
   const int src_rows = static_cast<int>(std::ceil((2 * kTileH2 + 1) * max_scale)) + 3;
   const int row_bytes = ((src_cols * 3 + 15 + 15) / 16) * 16;
-  const size_t smem = static_cast<size_t>(row_bytes) * src_rows;
+  const size_t tile_bytes = static_cast<size_t>(kTileH2) * kHaloW2 * 32;
+  const size_t smem = tile_bytes + static_cast<size_t>(row_bytes) * src_rows;
   static size_t attr = 0;
   if (smem <= 200 * 1024) {
     if (smem > 48 * 1024 && smem > attr) {
@@ -202,7 +233,7 @@ void preprocess_launch(const PreImage* d_imgs, int n, int out_h, int out_w, __ha
     letterbox_s2d_kernel<true><<<grid, kPreThreads, smem, st>>>(d_imgs, out_h, out_w, dst, row_bytes, src_rows);
   } else {
     // extreme down-scales (source window larger than shared memory): read through L1 instead
-    letterbox_s2d_kernel<false><<<grid, kPreThreads, 0, st>>>(d_imgs, out_h, out_w, dst, 0, 0);
+    letterbox_s2d_kernel<false><<<grid, kPreThreads, tile_bytes, st>>>(d_imgs, out_h, out_w, dst, 0, 0);
   }
   MDB_CUDA(cudaGetLastError());
 }
