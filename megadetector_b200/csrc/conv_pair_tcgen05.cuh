@@ -445,6 +445,8 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     const int et = static_cast<int>(threadIdx.x) - 64;  // 0..32*kPairEpiWarps-1
     const int nchunks = p.BN >> 4;
     uint32_t tcount = 0;
+    int bias_tile = -1;
+    uint32_t bias_buf = 0;
     for (int tile = cluster_id; tile < total_tiles; tile += num_clusters, ++tcount) {
       const uint32_t acc = tcount & acc_mask;
       const uint32_t acc_ph = (tcount >> acc_shift) & 1u;
@@ -458,10 +460,15 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       const bool valid = (img < p.n_img) && (ty < p.th) && (ox < p.W_out) && (oy < p.H_out);
       const long long pix = (static_cast<long long>(img) * p.H_out + oy) * p.W_out + ox;
 
-      // bias of this N tile -> shared memory (double-buffered by tile parity; one named barrier per tile)
-      float* bs = bias_s[tcount & 1u];
-      if (et < p.BN) bs[et] = __ldg(p.bias + n0 + et);  // BN <= 256 <= epilogue threads
-      named_bar_sync(1, kPairEpiWarps * 32);
+      // bias of this N tile -> shared memory, only when the N tile changes (layers with a single N tile load it
+      // once per kernel); double-buffered by load count, one named barrier per load
+      if (n_tile != bias_tile) {
+        bias_tile = n_tile;
+        bias_buf ^= 1u;
+        if (et < p.BN) bias_s[bias_buf][et] = __ldg(p.bias + n0 + et);  // BN <= 256 <= epilogue threads
+        named_bar_sync(1, kPairEpiWarps * 32);
+      }
+      const float* bs = bias_s[bias_buf];
 
       mbar_wait(&acc_full_bar[acc], acc_ph);
       tc_fence_after();
