@@ -80,6 +80,9 @@ void conv_launch(ConvOp* op, int n_img, cudaStream_t st);
 void conv_free(ConvOp* op);
 double conv_macs_per_image(const ConvOp* op);
 int conv_pick_bn(int cout_pad);
+// channels per filter tap in the packed weights: C_in itself when the kernel can take it as 64-channel chunks plus
+// a 16/32-channel tail, else rounded up to a multiple of 64 (zero weights; the TMA unit zero-fills the activations)
+int conv_cin_pad(int cin);
 
 // weight re-layout helpers (host): PyTorch [co][ci][k][k] fp32 -> [co_pad][k][k][ci_pad] fp16
 void pack_weights_khwc(const float* w, int co, int ci, int k, int co_pad, int ci_pad, std::vector<__half>& out);

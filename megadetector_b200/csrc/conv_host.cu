@@ -14,6 +14,7 @@ namespace mdb {
 struct ConvOp {
   CUtensorMap tmA[4];
   CUtensorMap tmB;
+  ConvMaps maps;  // pair kernel
   ConvParams p;
   PairParams pp;
   bool pair = true;
@@ -30,6 +31,17 @@ int conv_pick_bn(int cout_pad) {
   for (int bn = 256; bn >= 16; bn -= 16)
     if (cout_pad % bn == 0) return bn;
   return 16;
+}
+
+int conv_cin_pad(int cin) {
+  // Narrow tail chunks are implemented and tested (MDB_CONV_TAIL=1) but OFF by default: measured on B200 they cost
+  // as much shared-memory fill time as a zero-filled 64-channel chunk (the TMA unit is bound by rows, not bytes:
+  // profiles/r01_conv_tail_probe.txt), and padded chunks keep the 3x3 row-halo main loop applicable.
+  static const char* e = getenv("MDB_CONV_TAIL");
+  const bool tails = e && e[0] == '1';
+  const int r = cin % 64;
+  if (tails && (r == 0 || r == 16 || r == 32)) return cin;
+  return ((cin + 63) / 64) * 64;
 }
 
 static void pick_tile(int H, int W, int* tw, int* th) {
@@ -95,7 +107,13 @@ ConvOp* conv_build(const ConvDesc& d, int num_sms) {
     // rows (32/64 B) make the TMA unit request-bound (measured: 3x3 80->80 ran 15x off the MMA floor with 32-byte
     // rows).  Channels beyond in.C inside the last chunk are zero-filled by the TMA unit (no memory traffic) and
     // meet zero weights.
-    const int kc = d.cin_pad % 64 == 0 ? 64 : (d.cin_pad % 32 == 0 ? 32 : 16);
+    // The pair kernel always works on 64-channel chunks; a remainder of 16 or 32 channels per tap becomes a narrow
+    // "tail" chunk with its own swizzle width (32 / 64-byte rows) instead of a mostly zero-filled 64-channel one:
+    // shared-memory fill, not the tensor pipe, bounds these layers (profiles/r01_conv_oob_probe.txt).
+    const bool pair = use_pair_kernel();
+    const int tail_w = (pair && (d.cin_pad % 64 == 16 || d.cin_pad % 64 == 32)) ? d.cin_pad % 64 : 0;
+    const int kc = pair ? 64 : (d.cin_pad % 64 == 0 ? 64 : (d.cin_pad % 32 == 0 ? 32 : 16));
+    MDB_REQUIRE(!pair || tail_w || d.cin_pad % 64 == 0, "pair kernel: C_in per tap must be 64k, 64k+16 or 64k+32");
     op->kc = kc;
     op->num_sms = num_sms;
     ConvParams& p = op->p;
@@ -118,7 +136,7 @@ ConvOp* conv_build(const ConvDesc& d, int num_sms) {
     p.stride = d.s;
     p.pad = d.pad;
     p.Cin = d.cin_pad;
-    p.chunks = d.cin_pad / kc;
+    p.chunks = (d.cin_pad + kc - 1) / kc;
     p.bias = d.bias;
     p.out = out.base;
     p.out_pix_stride = out.Ctot;
@@ -151,7 +169,7 @@ ConvOp* conv_build(const ConvDesc& d, int num_sms) {
           for (int px = 0; px < 2; ++px) make_act_tmap(&op->tmA[py * 2 + px], in, kc, p.tw, p.th, py, px);
       }
     }
-    op->pair = use_pair_kernel();
+    op->pair = pair;
     if (op->pair) {
       // CTA pair: each CTA stages half of the B tile
       make_wgt_tmap(&op->tmB, d.wgt, d.k * kw * d.cin_pad, d.cout_pad, kc, p.BN / 2);
@@ -175,6 +193,7 @@ ConvOp* conv_build(const ConvDesc& d, int num_sms) {
       q.dbg = nullptr;
       q.halo = 0;
       q.a_stages = 0;
+      q.tail_w = tail_w;
       {
         static const char* ep = getenv("MDB_CONV_PROBE");
         q.probe = ep ? atoi(ep) : 0;
@@ -193,13 +212,15 @@ ConvOp* conv_build(const ConvDesc& d, int num_sms) {
         static const char* eh = getenv("MDB_CONV_HALO");
         const bool allow = !(eh && eh[0] == '0');
         const double eff = static_cast<double>(Ho) * Wo / (static_cast<double>((Wo + 7) / 8 * 8) * ((Ho + 15) / 16 * 16));
-        if (allow && kc == 64 && d.k == 3 && kw == 3 && d.s == 1 && d.pad == 1 && pad_x == 1 && eff >= 0.85 && p.chunks >= 3) {  // measured: +9% at 160 ch, 0 at 320, -10% at 80
+        if (allow && tail_w == 0 && d.k == 3 && kw == 3 && d.s == 1 && d.pad == 1 && pad_x == 1 && eff >= 0.85 && p.chunks >= 3) {  // measured: +9% at 160 ch, 0 at 320, -10% at 80
           q.halo = 1;
           q.a_stages = 2;
           q.tw = kHaloTw;
           q.th = kHaloTh;
           make_act_tmap(&op->tmA[0], in, kc, kHaloTw, kHaloRows, -1, -1);
           op->tmA[1] = op->tmA[2] = op->tmA[3] = op->tmA[0];
+          for (int i = 0; i < 4; ++i) op->maps.a[i] = op->maps.at[i] = op->tmA[0];
+          op->maps.b = op->maps.bt = op->tmB;
           const size_t budget = 227 * 1024 - 4096 - 1024;
           const size_t a_bytes = static_cast<size_t>(q.a_stages) * 3 * kHaloBox;
           int stages = static_cast<int>(std::min<size_t>(kPairMaxStages, (budget - a_bytes) / b_chunk));
@@ -218,9 +239,22 @@ ConvOp* conv_build(const ConvDesc& d, int num_sms) {
       stages = std::max(2, std::min(stages, std::max(2, stage_iters * 2)));
       q.stages = stages;
       op->smem = stage * stages + 1024;
-      if (kc == 64) set_smem_attr_pair<64>(op->smem);
-      else if (kc == 32) set_smem_attr_pair<32>(op->smem);
-      else set_smem_attr_pair<16>(op->smem);
+      for (int i = 0; i < 4; ++i) op->maps.a[i] = op->maps.at[i] = op->tmA[i];
+      op->maps.b = op->maps.bt = op->tmB;
+      if (tail_w) {
+        if (op->flat) {
+          make_act_tmap_flat(&op->maps.at[0], in, tail_w);
+          op->maps.at[1] = op->maps.at[2] = op->maps.at[3] = op->maps.at[0];
+        } else if (d.s == 1) {
+          make_act_tmap(&op->maps.at[0], in, tail_w, p.tw, p.th, -1, -1);
+          op->maps.at[1] = op->maps.at[2] = op->maps.at[3] = op->maps.at[0];
+        } else {
+          for (int py = 0; py < 2; ++py)
+            for (int px = 0; px < 2; ++px) make_act_tmap(&op->maps.at[py * 2 + px], in, tail_w, p.tw, p.th, py, px);
+        }
+        make_wgt_tmap(&op->maps.bt, d.wgt, d.k * kw * d.cin_pad, d.cout_pad, tail_w, p.BN / 2);
+      }
+      set_smem_attr_pair<64>(op->smem);
       return op;
     }
     MDB_REQUIRE(kw == d.k && pad_x == d.pad, "the single-CTA fallback kernel handles square filters only");
@@ -272,12 +306,7 @@ static void conv_launch_pair(ConvOp* op, int n_img, cudaStream_t st) {
     MDB_CUDA(cudaMemsetAsync(d_dbg, 0, sizeof(long long) * 8 * grid, st));
   }
   p.dbg = d_dbg;
-  if (op->kc == 64)
-    conv_pair_kernel<64><<<grid, kPairThreads, op->smem, st>>>(op->tmA[0], op->tmA[1], op->tmA[2], op->tmA[3], op->tmB, p);
-  else if (op->kc == 32)
-    conv_pair_kernel<32><<<grid, kPairThreads, op->smem, st>>>(op->tmA[0], op->tmA[1], op->tmA[2], op->tmA[3], op->tmB, p);
-  else
-    conv_pair_kernel<16><<<grid, kPairThreads, op->smem, st>>>(op->tmA[0], op->tmA[1], op->tmA[2], op->tmA[3], op->tmB, p);
+  conv_pair_kernel<64><<<grid, kPairThreads, op->smem, st>>>(op->maps, p);
   MDB_CUDA(cudaGetLastError());
   if (debug) {
     std::vector<long long> h(static_cast<size_t>(8) * grid);

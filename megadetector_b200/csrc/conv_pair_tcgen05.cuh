@@ -55,6 +55,7 @@ struct PairParams {
   int res_c_off;
   int act;
   int wide;        // 1: every epilogue row segment is 32-byte aligned -> 256-bit global accesses
+  int tail_w;      // channels of the last chunk of every tap when C_in % 64 is 16 or 32 (own swizzle width), else 0
   int halo;        // 1: 3x3/s1 row-halo main loop (tile 8 x 16; A fetched per kw shift, reused across kh)
   int a_stages;    // halo mode: number of A (3-box) buffers
   uint32_t idesc;  // M = 256
@@ -178,11 +179,23 @@ __device__ __forceinline__ void mbar_wait_timed(uint64_t* bar, uint32_t parity, 
   acc += clock64() - t0;
 }
 
+// TMA descriptors of one convolution: activation maps (dense, or the four stride-2 parity views) and the weight
+// map, each in two box widths: 64 channels (128-byte swizzle rows) and the narrower tail chunk (16 / 32 channels).
+struct alignas(64) ConvMaps {
+  CUtensorMap a[4];
+  CUtensorMap b;
+  CUtensorMap at[4];
+  CUtensorMap bt;
+};
+
 template <int KC>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1)
-conv_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
-                 const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmA3,
-                 const __grid_constant__ CUtensorMap tmB, const PairParams p) {
+conv_pair_kernel(const __grid_constant__ ConvMaps maps, const PairParams p) {
+  const CUtensorMap& tmA0 = maps.a[0];
+  const CUtensorMap& tmA1 = maps.a[1];
+  const CUtensorMap& tmA2 = maps.a[2];
+  const CUtensorMap& tmA3 = maps.a[3];
+  const CUtensorMap& tmB = maps.b;
   constexpr uint32_t ROW_BYTES = KC * 2;
   constexpr uint32_t A_CHUNK = kTileM * ROW_BYTES;  // 128 rows of one K chunk
 
@@ -225,6 +238,10 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       tma_prefetch_desc(&tmA1);
       tma_prefetch_desc(&tmA2);
       tma_prefetch_desc(&tmA3);
+    }
+    if (p.tail_w) {
+      tma_prefetch_desc(&maps.at[0]);
+      tma_prefetch_desc(&maps.bt);
     }
     for (int s = 0; s < S; ++s) {
       mbar_init(&full_bar[s], 2);   // leader's instance is the one in use: both producers arrive
@@ -313,35 +330,46 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         const int nb0 = n_tile * p.BN + static_cast<int>(rank * half_n);
         int kh = 0, kw = 0, c = 0, kcol = 0;
         // coordinates of the current filter tap
-        const CUtensorMap* ma = &tmA0;
+        int par = 0;
         int x = 0, y = 0;
         auto set_tap = [&]() {
           if (p.stride == 1) {
             x = ox0 + kw - p.pad_x;
             y = oy0 + kh - p.pad;
-            ma = &tmA0;
+            par = 0;
           } else {
             const int ty_ = kh - p.pad, tx_ = kw - p.pad_x;
             const int py = ty_ & 1, px = tx_ & 1;
             y = oy0 + ((ty_ - py) >> 1);
             x = ox0 + ((tx_ - px) >> 1);
-            const int par = py * 2 + px;
-            ma = par == 0 ? &tmA0 : (par == 1 ? &tmA1 : (par == 2 ? &tmA2 : &tmA3));
+            par = py * 2 + px;
           }
         };
         set_tap();
+        const int last_c = p.chunks - 1;
+        const uint32_t tail_tx = static_cast<uint32_t>(p.tw * p.th + static_cast<int>(half_n)) * static_cast<uint32_t>(p.tail_w) * 2u;
         for (int done = 0; done < p.total_chunks;) {
           const int nch = min(p.cps, p.total_chunks - done);
           mbar_wait_timed(&empty_bar[s], ph ^ 1u, w_empty, dbg);
-          if (leader) mbar_arrive_expect_tx(&full_bar[s], p.probe == 1 ? 0u : static_cast<uint32_t>(nch) * tx_stage);
+          // bytes this stage brings into ONE CTA (full chunks: 128-byte rows; tail chunks: 32/64-byte rows)
+          uint32_t tx = 0;
+          {
+            int cc = c;
+            for (int j = 0; j < nch; ++j) {
+              tx += (p.tail_w && cc == last_c) ? tail_tx : tx_per_chunk;
+              if (++cc == p.chunks) cc = 0;
+            }
+          }
+          if (leader) mbar_arrive_expect_tx(&full_bar[s], p.probe == 1 ? 0u : 2u * tx);
           else mbar_arrive_remote(&full_bar[s], 0);
           uint32_t dst = smem_base + static_cast<uint32_t>(s) * stage_bytes;
           for (int j = 0; j < nch; ++j, dst += chunk_bytes) {
+            const bool tail = p.tail_w && c == last_c;
             if (p.probe != 1) {
-              tma2_load_4d(ma, &full_bar[s], dst, c * KC, x, y, img);
-              tma2_load_2d(&tmB, &full_bar[s], dst + A_CHUNK, kcol, nb0);
+              tma2_load_4d(tail ? &maps.at[par] : &maps.a[par], &full_bar[s], dst, c * KC, x, y, img);
+              tma2_load_2d(tail ? &maps.bt : &tmB, &full_bar[s], dst + A_CHUNK, kcol, nb0);
             }
-            kcol += KC;
+            kcol += tail ? p.tail_w : KC;
             if (++c == p.chunks) {
               c = 0;
               if (++kw == p.KW) { kw = 0; ++kh; }
@@ -372,6 +400,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       uint32_t aph = 0;
       // descriptor template: everything except the 14-bit start address is constant for the whole kernel
       const uint64_t desc_tmpl = make_kmajor_desc(0, ROW_BYTES);
+      const uint64_t desc_tail = make_kmajor_desc(0, p.tail_w ? static_cast<uint32_t>(p.tail_w) * 2u : ROW_BYTES);
       for (int tile = cluster_id; tile < total_tiles; tile += num_clusters, ++tcount) {
         const uint32_t acc = tcount & acc_mask;
         const uint32_t acc_ph = (tcount >> acc_shift) & 1u;
@@ -405,24 +434,36 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             if (++as == p.a_stages) { as = 0; aph ^= 1u; }
           }
         } else
-        for (int done = 0; done < p.total_chunks;) {
-          const int nch = min(p.cps, p.total_chunks - done);
-          mbar_wait_timed(&full_bar[s], ph, w_full, dbg);
-          tc_fence_after();
-          uint32_t a_addr = smem_base + static_cast<uint32_t>(s) * stage_bytes;
-          for (int j = 0; j < nch; ++j, a_addr += chunk_bytes) {
-            const uint64_t da = desc_tmpl | static_cast<uint64_t>((a_addr & 0x3FFFFu) >> 4);
-            const uint64_t db = desc_tmpl | static_cast<uint64_t>(((a_addr + A_CHUNK) & 0x3FFFFu) >> 4);
-            if (p.probe != 2) {
+        {
+          int c = 0;
+          const int last_c = p.chunks - 1;
+          for (int done = 0; done < p.total_chunks;) {
+            const int nch = min(p.cps, p.total_chunks - done);
+            mbar_wait_timed(&full_bar[s], ph, w_full, dbg);
+            tc_fence_after();
+            uint32_t a_addr = smem_base + static_cast<uint32_t>(s) * stage_bytes;
+            for (int j = 0; j < nch; ++j, a_addr += chunk_bytes) {
+              const bool tail = p.tail_w && c == last_c;
+              const uint64_t tmpl = tail ? desc_tail : desc_tmpl;
+              const uint64_t da = tmpl | static_cast<uint64_t>((a_addr & 0x3FFFFu) >> 4);
+              const uint64_t db = tmpl | static_cast<uint64_t>(((a_addr + A_CHUNK) & 0x3FFFFu) >> 4);
+              if (p.probe != 2) {
+                if (!tail) {
 #pragma unroll
-              for (int k = 0; k < KC / 16; ++k)
-                umma2_f16(d_tmem, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), p.idesc,
-                          (done > 0 || j > 0 || k > 0) ? 1u : 0u);
+                  for (int k = 0; k < KC / 16; ++k)
+                    umma2_f16(d_tmem, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), p.idesc,
+                              (done > 0 || j > 0 || k > 0) ? 1u : 0u);
+                } else {
+                  umma2_f16(d_tmem, da, db, p.idesc, (done > 0 || j > 0) ? 1u : 0u);
+                  if (p.tail_w == 32) umma2_f16(d_tmem, da + 2ull, db + 2ull, p.idesc, 1u);
+                }
+              }
+              if (++c == p.chunks) c = 0;
             }
+            umma2_commit_mc(&empty_bar[s]);
+            done += nch;
+            if (++s == S) { s = 0; ph ^= 1u; }
           }
-          umma2_commit_mc(&empty_bar[s]);
-          done += nch;
-          if (++s == S) { s = 0; ph ^= 1u; }
         }
         umma2_commit_mc(&acc_full_bar[acc]);
       }

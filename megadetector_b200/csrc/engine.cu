@@ -897,7 +897,7 @@ int mdb_load_weights(mdb_engine* e, const mdb_tensor_desc* tensors, int32_t n) {
         pack_weights_stem_s2d(tw->data, co, cw.cout_pad, cw.cin_pad, packed);
       } else {
         MDB_REQUIRE(ci % 16 == 0, "conv input channels must be a multiple of 16");
-        cw.cin = ci; cw.cin_pad = ((ci + 63) / 64) * 64; cw.k = k;
+        cw.cin = ci; cw.cin_pad = conv_cin_pad(ci); cw.k = k;
         pack_weights_khwc(tw->data, co, ci, k, cw.cout_pad, cw.cin_pad, packed);
       }
       std::vector<float> bias(cw.cout_pad, 0.f);
@@ -1171,7 +1171,7 @@ int mdb_op_conv2d(mdb_engine* e, const void* x_fp16, int32_t n, int32_t h, int32
     const int cstore = out_fp32 ? ((cout + 3) / 4) * 4 : ((cout + 7) / 8) * 8;
     MDB_REQUIRE(cstore == cout, "cout must be a multiple of 8 (fp16) / 4 (fp32) for this test entry point");
     std::vector<__half> packed;
-    const int cin_pad = ((cin + 63) / 64) * 64;
+    const int cin_pad = conv_cin_pad(cin);
     pack_weights_khwc(wgt, cout, cin, k, cout_pad, cin_pad, packed);
     std::vector<float> bp(cout_pad, 0.f);
     memcpy(bp.data(), bias, sizeof(float) * cout);
