@@ -124,7 +124,7 @@ MDB_API int mdb_set_image_size(mdb_engine* e, int32_t img_size);
 MDB_API int mdb_letterbox_geometry(const mdb_config* cfg, int32_t h, int32_t w, int32_t* out8, double* ratio_pad3);
 
 /* ---- parity / profiling hooks (not used by the product path) ---- */
-#define MDB_FETCH_STEM_INPUT 1 /* K1 output of the last batch: fp16 [n][H/2][W/2][64]            */
+#define MDB_FETCH_STEM_INPUT 1 /* K1 output of the last batch: fp16 [n][H/2][W/2][48]            */
 #define MDB_FETCH_PRED 2       /* decoded predictions of the last batch: fp32 [n][anchors][5+nc]  */
 #define MDB_FETCH_LAYER 3      /* fp16 NHWC output of conv #index (order of oracle.yolov5.conv_specs) */
 MDB_API int mdb_debug_fetch(mdb_engine* e, int32_t what, int32_t index, void* host_dst, size_t bytes, int64_t* shape4);
@@ -147,7 +147,7 @@ MDB_API int mdb_set_pipeline_split(mdb_engine* e, int32_t parts);
 MDB_API int64_t mdb_launch_count(const mdb_engine* e);
 
 /* ---- single-kernel entry points on HOST buffers, for the parity tests (tests/ -m gpu) ---- */
-/* K1: letterbox + pad(114) + /255 + space-to-depth NHWC fp16.  dst: [out_h/2][out_w/2][64] fp16
+/* K1: letterbox + pad(114) + /255 + space-to-depth NHWC fp16.  dst: [out_h/2][out_w/2][48] fp16
  * (three column taps of the stem packed into the channel dimension, see csrc/preprocess.cu). */
 MDB_API int mdb_op_letterbox(mdb_engine* e, const uint8_t* rgb_hwc, int32_t h, int32_t w, int64_t row_stride, void* dst_fp16,
                      int32_t* out_hw2);

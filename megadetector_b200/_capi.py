@@ -376,7 +376,7 @@ class Engine:
     def op_letterbox(self, img):
         g = letterbox_geometry(self.cfg, img.shape[0], img.shape[1])
         oh, ow = g['out_hw']
-        out = np.empty((oh // 2, ow // 2, 64), np.float16)
+        out = np.empty((oh // 2, ow // 2, 48), np.float16)
         hw = (C.c_int32 * 2)()
         img = np.ascontiguousarray(img)
         self._check(self.lib.mdb_op_letterbox(self.h, img.ctypes.data, img.shape[0], img.shape[1], img.strides[0],

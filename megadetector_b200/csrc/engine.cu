@@ -250,7 +250,7 @@ void build_graph(Plan& P, const mdb_arch& A) {
   int h2, w2, h4, w4, h8, w8, h16, w16, h32, w32, h64, w64;
   dim(2, &h2, &w2); dim(4, &h4, &w4); dim(8, &h8, &w8); dim(16, &h16, &w16); dim(32, &h32, &w32); dim(64, &h64, &w64);
 
-  P.stem_buf = B.newbuf(h2, w2, 64);
+  P.stem_buf = B.newbuf(h2, w2, 48);
   // concat buffers that several producers write into
   const int cat22 = B.newbuf(h8, w8, 2 * c[2]);    // [up(x20), x4]
   const int cat18 = B.newbuf(h16, w16, 2 * c[3]);  // [up(x16), x6]
@@ -261,7 +261,7 @@ void build_graph(Plan& P, const mdb_arch& A) {
   const int sppf_cat = B.newbuf(h64, w64, 2 * c[5]);  // [s1, p1, p2, p3], each c5/2
 
   // NB: the stem consumes K1's tap-packed space-to-depth image: 3x1 / s1 / pad (1,0) over 64 channels
-  // (see preprocess.cu and pack_weights_stem_s2d)
+  // (48 stored; the 64-channel TMA box zero-fills the rest; see preprocess.cu and pack_weights_stem_s2d)
   const int x0 = B.newbuf(h2, w2, c[0]);
   B.conv("model.0.conv", B.whole(P.stem_buf), B.whole(x0), c[0], 3, 1, 1);
   P.steps.back().kw = 1;
@@ -509,7 +509,7 @@ void stage_compute(mdb_engine* e, Plan* P, int n, int slot, float conf_thres, in
   const int no = e->cfg.arch.nc + 5;
   if (timing) MDB_CUDA(cudaEventRecord(e->ev_tt[slot][0], st));
   if (stages_mask & 1) {
-    View stem = P->view(VView{P->stem_buf, 0, 64});
+    View stem = P->view(VView{P->stem_buf, 0, 48});
     preprocess_launch(e->d_pre[slot], n, P->H, P->W, static_cast<__half*>(stem.base), e->slot_max_scale[slot], st);
     e->launches++;
   }
@@ -893,7 +893,7 @@ int mdb_load_weights(mdb_engine* e, const mdb_tensor_desc* tensors, int32_t n) {
       std::vector<__half> packed;
       if (base == "model.0.conv") {
         MDB_REQUIRE(ci == 3 && k == 6, "stem must be a 6x6 conv over 3 channels");
-        cw.cin = 64; cw.cin_pad = 64; cw.k = 3;
+        cw.cin = 48; cw.cin_pad = 64; cw.k = 3;
         pack_weights_stem_s2d(tw->data, co, cw.cout_pad, cw.cin_pad, packed);
       } else {
         MDB_REQUIRE(ci % 16 == 0, "conv input channels must be a multiple of 16");
@@ -1076,9 +1076,9 @@ int mdb_debug_fetch(mdb_engine* e, int32_t what, int32_t index, void* host_dst, 
     size_t need = 0;
     int64_t shp[4] = {0, 0, 0, 0};
     if (what == MDB_FETCH_STEM_INPUT) {
-      View v = P->view(VView{P->stem_buf, 0, 64});
-      src = v.base; shp[0] = n; shp[1] = v.H; shp[2] = v.W; shp[3] = 64;
-      need = static_cast<size_t>(n) * v.H * v.W * 64 * 2;
+      View v = P->view(VView{P->stem_buf, 0, 48});
+      src = v.base; shp[0] = n; shp[1] = v.H; shp[2] = v.W; shp[3] = 48;
+      need = static_cast<size_t>(n) * v.H * v.W * 48 * 2;
     } else if (what == MDB_FETCH_PRED) {
       const int no = e->cfg.arch.nc + 5;
       src = P->pred; shp[0] = n; shp[1] = P->anchors; shp[2] = no; shp[3] = 1;
@@ -1128,7 +1128,7 @@ int mdb_op_letterbox(mdb_engine* e, const uint8_t* rgb_hwc, int32_t h, int32_t w
     uint8_t* d_src = nullptr;
     __half* d_dst = nullptr;
     PreImage* d_pi = nullptr;
-    const size_t out_elems = static_cast<size_t>(g.out_h / 2) * (g.out_w / 2) * 64;
+    const size_t out_elems = static_cast<size_t>(g.out_h / 2) * (g.out_w / 2) * 48;
     MDB_CUDA(cudaMalloc(&d_src, row * h + 256));
     MDB_CUDA(cudaMalloc(&d_dst, out_elems * 2));
     MDB_CUDA(cudaMalloc(&d_pi, sizeof(PreImage)));

@@ -8,12 +8,12 @@
 // coefficient tables are built on the host with the same float/double operations cv::resize uses, the
 // kernel is pure integer.  The output is what the first convolution wants to read: the 6x6/s2 stem equals a 3x3/s1
 // convolution over the 2x2 space-to-depth image (channel (py*2+px)*3+c); K1 also packs the three COLUMN taps
-// into the channel dimension, [H/2][W/2][64] fp16 (3 x (12 used + 4 zero) + 16 zero), so that the stem becomes a
+// into the channel dimension, [H/2][W/2][48] fp16 (3 x (12 used + 4 zero)), so that the stem becomes a
 // 3x1 convolution whose operand rows are full 128-byte swizzle rows (measured: 9 mostly zero-filled 64-channel
 // chunks cost as much shared-memory fill as 9 real ones; 3 real chunks cost a third).
 //
 // HBM traffic per 1920x1080 -> 768x1280 image: 6.22 MB read (each source byte once, staged through shared
-// memory with 128-bit loads) + 31.5 MB written.
+// memory with 128-bit loads) + 23.6 MB written.
 #include <algorithm>
 #include <cmath>
 
@@ -84,13 +84,14 @@ constexpr int kPreThreads = 256;
 constexpr int kTileW2 = 64;  // s2d columns per CTA  (128 output columns)
 constexpr int kTileH2 = 8;   // s2d rows per CTA     (16 output rows)
 constexpr int kHaloW2 = kTileW2 + 2;  // one extra s2d column on each side: the stem's column taps
+constexpr int kStemChannels = 48;     // 3 taps x 16 (12 used); the conv's TMA zero-fills channels 48..63
 
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
-// Output layout (what the stem convolution reads, see pack_weights_stem_s2d): per s2d pixel (y, x) 64 fp16 channels,
+// Output layout (what the stem convolution reads, see pack_weights_stem_s2d): per s2d pixel (y, x) 48 fp16 channels,
 //   [t*16 + (py*2+px)*3 + c]  = normalised letterboxed pixel (2y+py, 2(x+t-1)+px), channel c, for t = 0,1,2
 // i.e. the three column taps of the stem packed into the channel dimension (zero outside the image = the conv's
-// zero padding; channels 12..15 of every tap and 48..63 are zero).  One 128-byte row per thread, fully coalesced.
+// zero padding; channels 12..15 of every tap are zero; the conv reads 64-channel boxes, 48..63 zero-filled by TMA).
 // STAGED: the source window of the tile is first copied to shared memory with 16-byte loads.
 template <bool STAGED>
 __global__ void __launch_bounds__(kPreThreads) letterbox_s2d_kernel(const PreImage* __restrict__ imgs, int out_h,
@@ -195,20 +196,17 @@ __global__ void __launch_bounds__(kPreThreads) letterbox_s2d_kernel(const PreIma
   }
   __syncthreads();
 
-  // ---- phase 2: one packed 128-byte row per s2d pixel: taps x-1, x, x+1, then 32 zero bytes ----
-  for (int t = threadIdx.x; t < kTileW2 * kTileH2; t += kPreThreads) {
-    const int lx = t % kTileW2, ly = t / kTileW2;
+  // ---- phase 2: one packed 96-byte row per s2d pixel (taps x-1, x, x+1).  Consecutive lanes write consecutive
+  // 16-byte pieces, so a warp store covers 512 contiguous bytes.
+  constexpr int kPieces = 6;
+  for (int i = threadIdx.x; i < kTileW2 * kTileH2 * kPieces; i += kPreThreads) {
+    const int piece = i % kPieces, pxl = i / kPieces;
+    const int lx = pxl % kTileW2, ly = pxl / kTileW2;
     const int sx2 = sx2_0 + lx, sy2 = sy2_0 + ly;
     if (sx2 >= W2 || sy2 >= H2) continue;
-    uint4* o = reinterpret_cast<uint4*>(dst + ((static_cast<size_t>(blockIdx.z) * H2 + sy2) * W2 + sx2) * 64);
-    const uint4* e = s_tile + (ly * kHaloW2 + lx) * 2;  // entry of column x-1
-#pragma unroll
-    for (int tap = 0; tap < 3; ++tap) {
-      o[2 * tap] = e[2 * tap];
-      o[2 * tap + 1] = e[2 * tap + 1];
-    }
-    o[6] = make_uint4(0, 0, 0, 0);
-    o[7] = make_uint4(0, 0, 0, 0);
+    // piece p = half (p & 1) of the entry of column x - 1 + p / 2
+    const uint4 v = s_tile[(ly * kHaloW2 + lx + (piece >> 1)) * 2 + (piece & 1)];
+    reinterpret_cast<uint4*>(dst + ((static_cast<size_t>(blockIdx.z) * H2 + sy2) * W2 + sx2) * kStemChannels)[piece] = v;
   }
 }
 

@@ -119,8 +119,8 @@ def to_stem_layout_fp16(img_letterboxed):
     """
     The engine's K1 output layout, derived from the oracle image: 2x2 space-to-depth (channel (py*2+px)*3+c, 12
     values) with the stem's three column taps packed into the channel dimension:
-        out[y, x, t*16 + k] = s2d[y, x + t - 1, k]   (zero outside the image, channels 12..15 of each tap and
-        48..63 zero)                                   -> [H/2][W/2][64] fp16
+        out[y, x, t*16 + k] = s2d[y, x + t - 1, k]   (zero outside the image, channels 12..15 of each tap zero)
+                                                       -> [H/2][W/2][48] fp16
     """
     x = (img_letterboxed.astype(np.float32) / np.float32(255.0)).astype(np.float16)
     h, w, c = x.shape
@@ -128,7 +128,7 @@ def to_stem_layout_fp16(img_letterboxed):
     for py in range(2):
         for px in range(2):
             s2d[:, 1:-1, (py * 2 + px) * 3:(py * 2 + px) * 3 + 3] = x[py::2, px::2, :]
-    out = np.zeros((h // 2, w // 2, 64), np.float16)
+    out = np.zeros((h // 2, w // 2, 48), np.float16)
     for t in range(3):
         out[:, :, t * 16:t * 16 + 12] = s2d[:, t:t + w // 2, :]
     return out
