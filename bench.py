@@ -50,6 +50,19 @@ def _peaks():
     return {'tflops': 1400.0, 'hbm_gbs': 6650.0, 'source': 'fallback (B200_PROFILING.md)'}
 
 
+def _conv_dram_traffic():
+    """DRAM bytes (read + write) of the conv kernels over one forward pass of 64 images, from the committed ncu pass
+    (profiles/*_dram_traffic_step_bs64.csv: `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum`)."""
+    import glob
+    best = None
+    for path in sorted(glob.glob(os.path.join(ROOT, 'profiles', '*_dram_traffic_step_bs64.csv'))):
+        for ln in open(path):
+            if ln.startswith('conv_pair_kernel,'):
+                _, n, rd, wr = ln.strip().split(',')
+                best = (float(rd) + float(wr)) * 1e9 * 163.0 / float(n), os.path.basename(path)  # 163 launches = 1 pass
+    return best
+
+
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
 
@@ -241,8 +254,10 @@ def main():
             'gpu_launches': int(launches_res),
             'gpu_launches_e2e': int(launches_e2e),
             'roofline': {'bound': 'tensor', 'achieved': conv_tflops, 'peak': peaks['tflops'], 'unit': 'TFLOP/s',
-                         'frac': conv_tflops / peaks['tflops'], 'traffic': None, 'peak_source': peaks['source'],
-                         'kernel': 'conv_igemm_kernel<KC> family (163 launches/step) + 3 upsample + 1 SPPF pool launches',
+                         'frac': conv_tflops / peaks['tflops'],
+                         'traffic': (_conv_dram_traffic() or [None])[0] if B == 64 else None,
+                         'traffic_source': (_conv_dram_traffic() or [None, None])[1], 'peak_source': peaks['source'],
+                         'kernel': 'conv_pair_kernel<64> (163 launches/step; tcgen05.mma.cta_group::2) + 3 upsample + 1 SPPF pool launches',
                          'flops_per_step': B * GFLOP_PER_IMAGE * 1e9, 'ms_per_step': ms_net / args.steps},
             'stage_ms_per_step': {'preprocess_K1': ms_pre / args.steps, 'network_K2_K4': ms_net / args.steps,
                                   'decode_nms_K5_K8': ms_post / args.steps},

@@ -137,7 +137,8 @@ struct BatchState {
 struct mdb_engine {
   mdb_config cfg{};
   int num_sms = 148;
-  cudaStream_t st_compute = nullptr, st_copy = nullptr;
+  cudaStream_t st_compute = nullptr, st_copy = nullptr, st_post = nullptr;
+  cudaEvent_t ev_net_done[2] = {nullptr, nullptr}, ev_decode_done = nullptr, ev_post_done = nullptr;
   cudaEvent_t ev_copy_done[2] = {nullptr, nullptr}, ev_compute_done[2] = {nullptr, nullptr};
   cudaEvent_t ev_t[4] = {nullptr, nullptr, nullptr, nullptr};
   std::map<std::string, ConvWeights> weights;
@@ -514,18 +515,35 @@ void stage_compute(mdb_engine* e, Plan* P, int n, int slot, float conf_thres, in
     e->launches++;
   }
   if (timing) MDB_CUDA(cudaEventRecord(e->ev_tt[slot][1], st));
-  if (stages_mask & 2) run_network(e, P, n, st);
+  if (stages_mask & 2) {
+    // the Detect heads of this pass overwrite the raw buffers the previous pass's decode reads
+    MDB_CUDA(cudaStreamWaitEvent(st, e->ev_decode_done, 0));
+    run_network(e, P, n, st);
+  }
   if (timing) MDB_CUDA(cudaEventRecord(e->ev_tt[slot][2], st));
   if (stages_mask & 4) {
-    decode_launch(P->lv, n, no, P->anchors, P->pred, st);
+    // decode + NMS keep only a few SMs busy (one CTA per image): they run on their own stream so that the next
+    // chunk's K1 and convolutions overlap them
+    cudaStream_t sp = e->st_post;
+    MDB_CUDA(cudaEventRecord(e->ev_net_done[slot], st));
+    MDB_CUDA(cudaStreamWaitEvent(sp, e->ev_net_done[slot], 0));
+    decode_launch(P->lv, n, no, P->anchors, P->pred, sp);
+    MDB_CUDA(cudaEventRecord(e->ev_decode_done, sp));
     nms_launch(P->pred, n, P->anchors, no, conf_thres, float_floor_of_double(static_cast<double>(e->cfg.iou_thres)),
-               max_det, e->d_nmsp[slot], P->nms_scratch, e->d_det[slot], e->d_cnt[slot], e->d_anchor[slot], st);
+               max_det, e->d_nmsp[slot], P->nms_scratch, e->d_det[slot], e->d_cnt[slot], e->d_anchor[slot], sp);
     e->launches += 2;
-    MDB_CUDA(cudaMemcpyAsync(e->h_det[slot], e->d_det[slot], sizeof(float) * n * max_det * 6, cudaMemcpyDeviceToHost, st));
-    MDB_CUDA(cudaMemcpyAsync(e->h_cnt[slot], e->d_cnt[slot], sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
-    MDB_CUDA(cudaMemcpyAsync(e->h_anchor[slot], e->d_anchor[slot], sizeof(int32_t) * n * max_det, cudaMemcpyDeviceToHost, st));
+    MDB_CUDA(cudaMemcpyAsync(e->h_det[slot], e->d_det[slot], sizeof(float) * n * max_det * 6, cudaMemcpyDeviceToHost, sp));
+    MDB_CUDA(cudaMemcpyAsync(e->h_cnt[slot], e->d_cnt[slot], sizeof(int32_t) * n, cudaMemcpyDeviceToHost, sp));
+    MDB_CUDA(cudaMemcpyAsync(e->h_anchor[slot], e->d_anchor[slot], sizeof(int32_t) * n * max_det, cudaMemcpyDeviceToHost, sp));
+    if (timing) MDB_CUDA(cudaEventRecord(e->ev_tt[slot][3], sp));
+  } else if (timing) {
+    MDB_CUDA(cudaEventRecord(e->ev_tt[slot][3], st));
   }
-  if (timing) MDB_CUDA(cudaEventRecord(e->ev_tt[slot][3], st));
+}
+
+// the event that marks "everything of this slot's chunk is done" (staging buffers reusable, results on the host)
+void record_chunk_done(mdb_engine* e, int slot) {
+  MDB_CUDA(cudaEventRecord(e->ev_compute_done[slot], e->st_post));
 }
 
 void enqueue_chunk(mdb_engine* e, Plan* P, const std::vector<ImgIn>& imgs, const std::vector<LetterboxGeom>& geoms,
@@ -575,7 +593,7 @@ void enqueue_chunk(mdb_engine* e, Plan* P, const std::vector<ImgIn>& imgs, const
   e->last_slot = slot;
   MDB_CUDA(cudaStreamWaitEvent(e->st_compute, e->ev_copy_done[slot], 0));
   stage_compute(e, P, n, slot, conf_thres, 7, true);
-  MDB_CUDA(cudaEventRecord(e->ev_compute_done[slot], e->st_compute));
+  record_chunk_done(e, slot);
 }
 
 void finish_chunk(mdb_engine* e, const Pending& pd, float* det_out, int32_t* det_count, int32_t* kept_anchor) {
@@ -809,6 +827,10 @@ int mdb_create(mdb_engine** out, const mdb_config* cfg) {
     e->num_sms = prop.multiProcessorCount;
     MDB_CUDA(cudaStreamCreateWithFlags(&e->st_compute, cudaStreamNonBlocking));
     MDB_CUDA(cudaStreamCreateWithFlags(&e->st_copy, cudaStreamNonBlocking));
+    MDB_CUDA(cudaStreamCreateWithFlags(&e->st_post, cudaStreamNonBlocking));
+    MDB_CUDA(cudaEventCreateWithFlags(&e->ev_decode_done, cudaEventDisableTiming));
+    MDB_CUDA(cudaEventCreateWithFlags(&e->ev_post_done, cudaEventDisableTiming));
+    for (int i = 0; i < 2; ++i) MDB_CUDA(cudaEventCreateWithFlags(&e->ev_net_done[i], cudaEventDisableTiming));
     for (int i = 0; i < 2; ++i) {
       MDB_CUDA(cudaEventCreateWithFlags(&e->ev_copy_done[i], cudaEventDisableTiming));
       MDB_CUDA(cudaEventCreateWithFlags(&e->ev_compute_done[i], cudaEventDisableTiming));
@@ -867,6 +889,10 @@ void mdb_destroy(mdb_engine* e) {
   }
   if (e->st_compute) cudaStreamDestroy(e->st_compute);
   if (e->st_copy) cudaStreamDestroy(e->st_copy);
+  if (e->st_post) cudaStreamDestroy(e->st_post);
+  if (e->ev_decode_done) cudaEventDestroy(e->ev_decode_done);
+  if (e->ev_post_done) cudaEventDestroy(e->ev_post_done);
+  for (int i = 0; i < 2; ++i) if (e->ev_net_done[i]) cudaEventDestroy(e->ev_net_done[i]);
   delete e;
 }
 
@@ -972,7 +998,10 @@ int mdb_bench_resident(mdb_engine* e, int32_t iters, float conf_thres, int32_t s
     cudaStream_t st = e->st_compute;
     MDB_CUDA(cudaStreamSynchronize(st));
     MDB_CUDA(cudaEventRecord(e->ev_t[0], st));
+    MDB_CUDA(cudaStreamSynchronize(e->st_post));
     for (int i = 0; i < iters; ++i) stage_compute(e, P, e->slot_n[slot], slot, conf_thres, stages_mask, false);
+    MDB_CUDA(cudaEventRecord(e->ev_post_done, e->st_post));
+    MDB_CUDA(cudaStreamWaitEvent(st, e->ev_post_done, 0));
     MDB_CUDA(cudaEventRecord(e->ev_t[1], st));
     MDB_CUDA(cudaEventSynchronize(e->ev_t[1]));
     MDB_CUDA(cudaEventElapsedTime(ms_total, e->ev_t[0], e->ev_t[1]));
@@ -1104,6 +1133,7 @@ int mdb_debug_fetch(mdb_engine* e, int32_t what, int32_t index, void* host_dst, 
     if (host_dst) {
       if (bytes < need) return fail(e, MDB_ERR_ARG, "destination too small");
       MDB_CUDA(cudaStreamSynchronize(e->st_compute));
+      MDB_CUDA(cudaStreamSynchronize(e->st_post));
       MDB_CUDA(cudaMemcpy(host_dst, src, need, cudaMemcpyDeviceToHost));
     }
   } catch (const CudaError& ex) {

@@ -146,11 +146,19 @@ def synth_yolov5_weights(ch=YOLOV5X6['ch'], n_backbone=YOLOV5X6['n_backbone'], n
     for name, ci, co, k in _specs(ch, n_backbone, n_head, nc):
         w[name + '.weight'] = torch.randn(co, ci, k, k, generator=g) / (ci * k * k) ** 0.5
         w[name + '.bias'] = torch.randn(co, generator=g) * 0.1
+    # The calibration pass runs on the CPU on purpose: this module is a stand-in for a checkpoint file, and no
+    # library kernel (cuDNN) should ever appear on the GPU in a process that is measuring the engine.
     if device is None:
-        device = 'cuda' if torch.cuda.is_available() else 'cpu'
+        device = 'cpu'
     if device != 'cpu':
         torch.backends.cudnn.allow_tf32 = False
         torch.backends.cuda.matmul.allow_tf32 = False
-    wd = {k: v.to(device) for k, v in w.items()}
-    _Calibrator(wd, nc + 5, obj_logit).run(_calibration_input(*calib_hw).to(device), n_backbone, n_head)
+    threads = torch.get_num_threads()
+    try:
+        # oneDNN convolutions collapse when oversubscribed (128 threads: 100 GFLOP/s, 32 threads: 1.4 TFLOP/s, measured)
+        torch.set_num_threads(max(1, min(threads, 32)))
+        wd = {k: v.to(device) for k, v in w.items()}
+        _Calibrator(wd, nc + 5, obj_logit).run(_calibration_input(*calib_hw).to(device), n_backbone, n_head)
+    finally:
+        torch.set_num_threads(threads)
     return {k: v.float().cpu().contiguous() for k, v in wd.items()}
