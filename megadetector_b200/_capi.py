@@ -10,7 +10,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libmdb200.so')
+_VARIANT = os.environ.get('MDB_LIB_VARIANT', '')  # experiment builds only (see build.py)
+LIB_PATH = os.path.join(_HERE, 'libmdb200{}.so'.format('_' + _VARIANT if _VARIANT else ''))
 
 MDB_OK = 0
 MDB_IMG_OK, MDB_IMG_BAD_INPUT, MDB_IMG_INFER_FAILED = 0, 1, 2

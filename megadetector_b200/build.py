@@ -12,13 +12,23 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
-OUT = os.path.join(HERE, 'libmdb200.so')
-OBJ_DIR = os.path.join(HERE, 'csrc', 'build')
+# Experiment variants: MDB_LIB_VARIANT=<name> builds libmdb200_<name>.so with the extra flags in MDB_NVCC_FLAGS (and
+# _capi loads that file); the default build has neither.
+VARIANT = os.environ.get('MDB_LIB_VARIANT', '')
+OUT = os.path.join(HERE, 'libmdb200{}.so'.format('_' + VARIANT if VARIANT else ''))
+OBJ_DIR = os.path.join(HERE, 'csrc', 'build' + ('_' + VARIANT if VARIANT else ''))
 SOURCES = ['tmap.cu', 'conv_host.cu', 'preprocess.cu', 'aux.cu', 'nms.cu', 'engine.cu']
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 ARCH_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a']
 CFLAGS = ['-O3', '-std=c++17', '-lineinfo', '-Xcompiler', '-fPIC', '-Xcompiler', '-fvisibility=hidden',
           '--expt-relaxed-constexpr']
+if VARIANT:  # the variant's flags are remembered next to its objects, so a later load without the env rebuilds nothing
+    _flags_file = os.path.join(OBJ_DIR, 'flags')
+    if 'MDB_NVCC_FLAGS' in os.environ:
+        os.makedirs(OBJ_DIR, exist_ok=True)
+        with open(_flags_file, 'w') as _f:
+            _f.write(os.environ['MDB_NVCC_FLAGS'])
+    CFLAGS += open(_flags_file).read().split() if os.path.exists(_flags_file) else []
 
 
 def _stamp():

@@ -211,8 +211,10 @@ ConvOp* conv_build(const ConvDesc& d, int num_sms) {
       {
         static const char* eh = getenv("MDB_CONV_HALO");
         const bool allow = !(eh && eh[0] == '0');
+        static const char* ehm = getenv("MDB_CONV_HALO_MIN");
+        const int halo_min_chunks = ehm ? atoi(ehm) : 3;
         const double eff = static_cast<double>(Ho) * Wo / (static_cast<double>((Wo + 7) / 8 * 8) * ((Ho + 15) / 16 * 16));
-        if (allow && tail_w == 0 && d.k == 3 && kw == 3 && d.s == 1 && d.pad == 1 && pad_x == 1 && eff >= 0.85 && p.chunks >= 3) {  // measured: +9% at 160 ch, 0 at 320, -10% at 80
+        if (allow && tail_w == 0 && d.k == 3 && kw == 3 && d.s == 1 && d.pad == 1 && pad_x == 1 && eff >= 0.85 && p.chunks >= halo_min_chunks) {  // measured: +9% at 160 ch, 0 at 320, -10% at 80
           q.halo = 1;
           q.a_stages = 2;
           q.tw = kHaloTw;
@@ -302,28 +304,34 @@ static void conv_launch_pair(ConvOp* op, int n_img, cudaStream_t st) {
   static const bool debug = getenv("MDB_CONV_DEBUG") && getenv("MDB_CONV_DEBUG")[0] == '1';
   long long* d_dbg = nullptr;
   if (debug) {
-    MDB_CUDA(cudaMalloc(&d_dbg, sizeof(long long) * 8 * grid));
-    MDB_CUDA(cudaMemsetAsync(d_dbg, 0, sizeof(long long) * 8 * grid, st));
+    MDB_CUDA(cudaMalloc(&d_dbg, sizeof(long long) * 16 * grid));
+    MDB_CUDA(cudaMemsetAsync(d_dbg, 0, sizeof(long long) * 16 * grid, st));
   }
   p.dbg = d_dbg;
   conv_pair_kernel<64><<<grid, kPairThreads, op->smem, st>>>(op->maps, p);
   MDB_CUDA(cudaGetLastError());
   if (debug) {
-    std::vector<long long> h(static_cast<size_t>(8) * grid);
+    std::vector<long long> h(static_cast<size_t>(16) * grid);
     MDB_CUDA(cudaStreamSynchronize(st));
     MDB_CUDA(cudaMemcpy(h.data(), d_dbg, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost));
     cudaFree(d_dbg);
-    double prod_tot = 0, prod_wait = 0, its = 0, mma_tot = 0, mma_wfull = 0, mma_wacc = 0, tiles = 0;
+    double p_arr = 0, p_tma = 0, m_commit = 0, m_cacc = 0, m_fence = 0, e_wait = 0, e_proc = 0, e_tot = 0;
+    double prod_tot = 0, prod_wait = 0, its = 0, mma_tot = 0, mma_wfull = 0, mma_wacc = 0, tiles = 0, mma_issue = 0;
     int leaders = 0;
     for (int b = 0; b < grid; ++b) {
-      prod_tot += h[b * 8 + 0]; prod_wait += h[b * 8 + 1]; its += h[b * 8 + 2];
-      if (b % 2 == 0) { mma_tot += h[b * 8 + 4]; mma_wfull += h[b * 8 + 5]; mma_wacc += h[b * 8 + 6]; tiles += h[b * 8 + 7]; ++leaders; }
+      p_arr += h[b * 16 + 8]; p_tma += h[b * 16 + 9]; e_wait += h[b * 16 + 13]; e_proc += h[b * 16 + 14]; e_tot += h[b * 16 + 15];
+      if (b % 2 == 0) { m_commit += h[b * 16 + 10]; m_cacc += h[b * 16 + 11]; m_fence += h[b * 16 + 12]; }
+      prod_tot += h[b * 16 + 0]; prod_wait += h[b * 16 + 1]; its += h[b * 16 + 2];
+      if (b % 2 == 0) { mma_tot += h[b * 16 + 4]; mma_wfull += h[b * 16 + 5]; mma_wacc += h[b * 16 + 6]; tiles += h[b * 16 + 7]; mma_issue += h[b * 16 + 3]; ++leaders; }
     }
     fprintf(stderr,
             "[conv dbg] grid %d BN %d stages %d cps %d tiles/cluster %.1f | producer: %.0f cyc total, %.1f%% waiting on empty, "
-            "%.0f cyc/stage | mma thread: %.0f cyc total, %.1f%% waiting on full, %.1f%% waiting on acc_empty, %.0f cyc/tile\n",
+            "%.0f cyc/stage | mma thread: %.0f cyc total, %.1f%% waiting on full, %.1f%% waiting on acc_empty, %.1f%% in mma issue+commit, %.0f cyc/tile\n",
             grid, p.BN, p.stages, p.cps, tiles / leaders, prod_tot / grid, 100.0 * prod_wait / prod_tot, prod_tot / its,
-            mma_tot / leaders, 100.0 * mma_wfull / mma_tot, 100.0 * mma_wacc / mma_tot, mma_tot / tiles);
+            mma_tot / leaders, 100.0 * mma_wfull / mma_tot, 100.0 * mma_wacc / mma_tot, 100.0 * mma_issue / mma_tot, mma_tot / tiles);
+    fprintf(stderr, "[conv dbg]   per tile (cycles): producer arrive %.0f, tma issue %.0f | mma issue %.0f, commit(empty) %.0f, commit(acc) %.0f, fence %.0f | epilogue warp 0: wait acc_full %.0f, process %.0f, total %.0f\n",
+            p_arr / grid / (tiles / leaders), p_tma / grid / (tiles / leaders), mma_issue / tiles, m_commit / tiles, m_cacc / tiles, m_fence / tiles,
+            e_wait / grid / (tiles / leaders), e_proc / grid / (tiles / leaders), e_tot / grid / (tiles / leaders));
   }
 }
 

@@ -25,7 +25,20 @@
 
 namespace mdb {
 
-constexpr int kPairEpiWarps = 16;  // four per TMEM lane quadrant
+// Cycle counters of the role threads (MDB_CONV_DEBUG=1) exist only in -DMDB_CONV_TIMERS builds: even predicated off,
+// the extra instructions in the single-thread loops cost 17% on 1x1 layers.
+#ifdef MDB_CONV_TIMERS
+constexpr bool kTimers = true;
+#else
+constexpr bool kTimers = false;
+#endif
+#ifndef MDB_EPI_SLEEP
+#define MDB_EPI_SLEEP 0
+#endif
+#ifndef MDB_EPI_WARPS
+#define MDB_EPI_WARPS 16
+#endif
+constexpr int kPairEpiWarps = MDB_EPI_WARPS;  // a multiple of four: each TMEM lane quadrant gets kPairEpiWarps / 4
 constexpr int kPairThreads = 64 + 32 * kPairEpiWarps;
 constexpr int kPairMaxStages = 12;
 constexpr int kHaloRows = 18;                       // th + 2
@@ -60,7 +73,8 @@ struct PairParams {
   int a_stages;    // halo mode: number of A (3-box) buffers
   uint32_t idesc;  // M = 256
   long long* dbg;  // optional per-CTA cycle counters (MDB_CONV_DEBUG=1), null in production
-  int probe;       // timing probes only (results are garbage): 1 = skip TMA loads, 2 = skip MMAs
+  int probe;       // timing probes only (results are garbage), bit mask: 1 = skip TMA loads, 2 = skip MMAs, 4 = epilogue releases
+                   // the accumulator without reading it, 8 = no global stores/residual loads, 16 = no SiLU
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -274,8 +288,8 @@ conv_pair_kernel(const __grid_constant__ ConvMaps maps, const PairParams p) {
     // elect.sync (not `lane == 0`): inside an elected region ptxas knows a single thread is active and keeps TMA
     // operands in uniform registers instead of emitting a waterfall loop around every UTMALDG.
     if (elect_one()) {
-      const bool dbg = p.dbg != nullptr;
-      long long w_empty = 0;
+      const bool dbg = kTimers && p.dbg != nullptr;
+      long long w_empty = 0, w_arrive = 0, w_tma = 0;
       uint32_t it = 0;
       const long long t_start = clock64();
       int s = 0;
@@ -360,12 +374,14 @@ conv_pair_kernel(const __grid_constant__ ConvMaps maps, const PairParams p) {
               if (++cc == p.chunks) cc = 0;
             }
           }
-          if (leader) mbar_arrive_expect_tx(&full_bar[s], p.probe == 1 ? 0u : 2u * tx);
+          const long long tp0 = dbg ? clock64() : 0;
+          if (leader) mbar_arrive_expect_tx(&full_bar[s], (p.probe & 1) ? 0u : 2u * tx);
           else mbar_arrive_remote(&full_bar[s], 0);
+          const long long tp1 = dbg ? clock64() : 0;
           uint32_t dst = smem_base + static_cast<uint32_t>(s) * stage_bytes;
           for (int j = 0; j < nch; ++j, dst += chunk_bytes) {
             const bool tail = p.tail_w && c == last_c;
-            if (p.probe != 1) {
+            if (!(p.probe & 1)) {
               tma2_load_4d(tail ? &maps.at[par] : &maps.a[par], &full_bar[s], dst, c * KC, x, y, img);
               tma2_load_2d(tail ? &maps.bt : &tmB, &full_bar[s], dst + A_CHUNK, kcol, nb0);
             }
@@ -376,23 +392,26 @@ conv_pair_kernel(const __grid_constant__ ConvMaps maps, const PairParams p) {
               set_tap();
             }
           }
+          if (dbg) { w_arrive += tp1 - tp0; w_tma += clock64() - tp1; }
           done += nch;
           if (++s == S) { s = 0; ph ^= 1u; }
           ++it;
         }
       }
       if (dbg) {
-        p.dbg[blockIdx.x * 8 + 0] = clock64() - t_start;
-        p.dbg[blockIdx.x * 8 + 1] = w_empty;
-        p.dbg[blockIdx.x * 8 + 2] = it;
+        p.dbg[blockIdx.x * 16 + 8] = w_arrive;
+        p.dbg[blockIdx.x * 16 + 9] = w_tma;
+        p.dbg[blockIdx.x * 16 + 0] = clock64() - t_start;
+        p.dbg[blockIdx.x * 16 + 1] = w_empty;
+        p.dbg[blockIdx.x * 16 + 2] = it;
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
     if (leader && elect_one()) {
       uint32_t tcount = 0;
-      const bool dbg = p.dbg != nullptr;
-      long long w_full = 0, w_acc = 0;
+      const bool dbg = kTimers && p.dbg != nullptr;
+      long long w_full = 0, w_acc = 0, w_issue = 0, w_commit = 0, w_commit_acc = 0, w_fence = 0;
       const long long t_start = clock64();
       int s = 0;
       uint32_t ph = 0;
@@ -405,7 +424,9 @@ conv_pair_kernel(const __grid_constant__ ConvMaps maps, const PairParams p) {
         const uint32_t acc = tcount & acc_mask;
         const uint32_t acc_ph = (tcount >> acc_shift) & 1u;
         mbar_wait_timed(&acc_empty_bar[acc], acc_ph ^ 1u, w_acc, dbg);
+        const long long tf0 = dbg ? clock64() : 0;
         tc_fence_after();
+        if (dbg) w_fence += clock64() - tf0;
         const uint32_t d_tmem = tmem_base + acc * acc_stride;
         if (p.halo) {
           const uint32_t a_stage_bytes = 3u * kHaloBox;
@@ -441,13 +462,14 @@ conv_pair_kernel(const __grid_constant__ ConvMaps maps, const PairParams p) {
             const int nch = min(p.cps, p.total_chunks - done);
             mbar_wait_timed(&full_bar[s], ph, w_full, dbg);
             tc_fence_after();
+            const long long ti0 = dbg ? clock64() : 0;
             uint32_t a_addr = smem_base + static_cast<uint32_t>(s) * stage_bytes;
             for (int j = 0; j < nch; ++j, a_addr += chunk_bytes) {
               const bool tail = p.tail_w && c == last_c;
               const uint64_t tmpl = tail ? desc_tail : desc_tmpl;
               const uint64_t da = tmpl | static_cast<uint64_t>((a_addr & 0x3FFFFu) >> 4);
               const uint64_t db = tmpl | static_cast<uint64_t>(((a_addr + A_CHUNK) & 0x3FFFFu) >> 4);
-              if (p.probe != 2) {
+              if (!(p.probe & 2)) {
                 if (!tail) {
 #pragma unroll
                   for (int k = 0; k < KC / 16; ++k)
@@ -460,18 +482,26 @@ conv_pair_kernel(const __grid_constant__ ConvMaps maps, const PairParams p) {
               }
               if (++c == p.chunks) c = 0;
             }
+            const long long ti1 = dbg ? clock64() : 0;
             umma2_commit_mc(&empty_bar[s]);
+            if (dbg) { w_issue += ti1 - ti0; w_commit += clock64() - ti1; }
             done += nch;
             if (++s == S) { s = 0; ph ^= 1u; }
           }
         }
+        const long long tc0 = dbg ? clock64() : 0;
         umma2_commit_mc(&acc_full_bar[acc]);
+        if (dbg) w_commit_acc += clock64() - tc0;
       }
       if (dbg) {
-        p.dbg[blockIdx.x * 8 + 4] = clock64() - t_start;
-        p.dbg[blockIdx.x * 8 + 5] = w_full;
-        p.dbg[blockIdx.x * 8 + 6] = w_acc;
-        p.dbg[blockIdx.x * 8 + 7] = tcount;
+        p.dbg[blockIdx.x * 16 + 10] = w_commit;
+        p.dbg[blockIdx.x * 16 + 11] = w_commit_acc;
+        p.dbg[blockIdx.x * 16 + 12] = w_fence;
+        p.dbg[blockIdx.x * 16 + 3] = w_issue;
+        p.dbg[blockIdx.x * 16 + 4] = clock64() - t_start;
+        p.dbg[blockIdx.x * 16 + 5] = w_full;
+        p.dbg[blockIdx.x * 16 + 6] = w_acc;
+        p.dbg[blockIdx.x * 16 + 7] = tcount;
       }
     }
   } else {
@@ -488,6 +518,9 @@ conv_pair_kernel(const __grid_constant__ ConvMaps maps, const PairParams p) {
     uint32_t tcount = 0;
     int bias_tile = -1;
     uint32_t bias_buf = 0;
+    const bool edbg = kTimers && p.dbg != nullptr;
+    long long e_wait = 0, e_proc = 0;
+    const long long e_start = edbg ? clock64() : 0;
     for (int tile = cluster_id; tile < total_tiles; tile += num_clusters, ++tcount) {
       const uint32_t acc = tcount & acc_mask;
       const uint32_t acc_ph = (tcount >> acc_shift) & 1u;
@@ -511,15 +544,18 @@ conv_pair_kernel(const __grid_constant__ ConvMaps maps, const PairParams p) {
       }
       const float* bs = bias_s[bias_buf];
 
-      mbar_wait(&acc_full_bar[acc], acc_ph);
+      const long long te0 = edbg ? clock64() : 0;
+      if (MDB_EPI_SLEEP > 0) mbar_wait_backoff(&acc_full_bar[acc], acc_ph, MDB_EPI_SLEEP);
+      else mbar_wait(&acc_full_bar[acc], acc_ph);
       tc_fence_after();
+      const long long te1 = edbg ? clock64() : 0;
       const uint32_t taddr = tmem_base + ((quad * 32u) << 16) + acc * acc_stride;
       // one 16-column chunk: +bias -> SiLU -> (+residual) -> store.  Registers only (static indexing).
       auto process = [&](const uint32_t (&vv)[16], int jj) {
         const int col0 = n0 + jj * 16;
-        if (!(valid && col0 < p.Cout)) return;
+        if (!(valid && col0 < p.Cout) || (p.probe & 4)) return;
         uint4 r0 = make_uint4(0, 0, 0, 0), r1 = make_uint4(0, 0, 0, 0);
-        if (p.res != nullptr) {
+        if (p.res != nullptr && !(p.probe & 8)) {
           const __half* rp = p.res + pix * p.res_pix_stride + p.res_c_off + col0;
           if (p.wide) {
             ldg256(rp, r0, r1);
@@ -538,7 +574,7 @@ conv_pair_kernel(const __grid_constant__ ConvMaps maps, const PairParams p) {
           f[4 * q + 2] = __uint_as_float(vv[4 * q + 2]) + bb.z;
           f[4 * q + 3] = __uint_as_float(vv[4 * q + 3]) + bb.w;
         }
-        if (p.act) {
+        if (p.act && !(p.probe & 16)) {
 #pragma unroll
           for (int e = 0; e < 16; e += 4) silu4(f[e], f[e + 1], f[e + 2], f[e + 3]);
         }
@@ -587,7 +623,9 @@ conv_pair_kernel(const __grid_constant__ ConvMaps maps, const PairParams p) {
               q0[e] = __floats2half2_rn(f[2 * e], f[2 * e + 1]);
               q1[e] = __floats2half2_rn(f[8 + 2 * e], f[8 + 2 * e + 1]);
             }
-            if (p.wide) {
+            if (p.probe & 8) {
+              if (o0.x == 0x7fff7fffu && o1.w == 0x7fff7fffu) stg256(op, o0, o1);  // keeps the math alive, never true
+            } else if (p.wide) {
               stg256(op, o0, o1);
             } else {
               reinterpret_cast<uint4*>(op)[0] = o0;
@@ -618,10 +656,16 @@ conv_pair_kernel(const __grid_constant__ ConvMaps maps, const PairParams p) {
       // all TMEM reads of this warp have completed (tcgen05.wait::ld): hand the accumulator stage back
       tc_fence_before();
       __syncwarp();
+      if (edbg) { e_wait += te1 - te0; e_proc += clock64() - te1; }
       if (lane == 0) {
         if (leader) mbar_arrive(&acc_empty_bar[acc]);
         else mbar_arrive_remote(&acc_empty_bar[acc], 0);
       }
+    }
+    if (edbg && ew == 0 && lane == 0) {
+      p.dbg[blockIdx.x * 16 + 13] = e_wait;
+      p.dbg[blockIdx.x * 16 + 14] = e_proc;
+      p.dbg[blockIdx.x * 16 + 15] = clock64() - e_start;
     }
   }
 

@@ -1,5 +1,6 @@
 // TMA descriptor construction.  libcuda is not linked (this library must dlopen on a CPU-only box for the
 // symbol checks), so cuTensorMapEncodeTiled is resolved through the runtime's driver entry-point query.
+#include <cstdlib>
 #include <cudaTypedefs.h>
 
 #include "common.h"
@@ -19,6 +20,14 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
 
 static CUtensorMapSwizzle swizzle_for(int kc) {
   return kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (kc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+}
+
+// L2 promotion of activation maps (MDB_TMAP_PROMO=128|256|64|0)
+static CUtensorMapL2promotion act_promotion() {
+  static const char* e = getenv("MDB_TMAP_PROMO");
+  const int v = e ? atoi(e) : 128;
+  return v == 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B
+                  : (v == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : (v == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : CU_TENSOR_MAP_L2_PROMOTION_L2_128B));
 }
 
 static void encode(CUtensorMap* m, void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
@@ -52,7 +61,7 @@ void make_act_tmap(CUtensorMap* m, const View& v, int kc, int tw, int th, int pa
     strides[0] = px * 2; strides[1] = px * v.W * 2; strides[2] = px * v.W * v.H;
   }
   cuuint32_t box[4] = {static_cast<cuuint32_t>(kc), static_cast<cuuint32_t>(tw), static_cast<cuuint32_t>(th), 1};
-  encode(m, base, 4, dims, strides, box, kc, CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
+  encode(m, base, 4, dims, strides, box, kc, act_promotion());
 }
 
 void make_act_tmap_flat(CUtensorMap* m, const View& v, int kc) {
@@ -62,7 +71,7 @@ void make_act_tmap_flat(CUtensorMap* m, const View& v, int kc) {
   cuuint64_t dims[4] = {static_cast<cuuint64_t>(v.C), npix, 1, 1};
   cuuint64_t strides[3] = {px, px * npix, px * npix};
   cuuint32_t box[4] = {static_cast<cuuint32_t>(kc), 128, 1, 1};
-  encode(m, v.ptr(), 4, dims, strides, box, kc, CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
+  encode(m, v.ptr(), 4, dims, strides, box, kc, act_promotion());
 }
 
 void make_wgt_tmap(CUtensorMap* m, const void* w, int K, int cout_pad, int kc, int bn) {

@@ -23,10 +23,15 @@ CASES = {
     'p2_c80': (16, 192, 320, 80, 80, 3, 1, 1, False),
     'p2_c128': (16, 192, 320, 128, 80, 3, 1, 1, False),
     'stem_c64': (16, 384, 640, 64, 80, 3, 1, 1, False),
+    'b64_c1x1_80': (64, 192, 320, 80, 80, 1, 1, 0, False),
+    'b64_c1x1_160': (64, 96, 160, 160, 160, 1, 1, 0, False),
+    'b64_c1x1_160_80': (64, 192, 320, 160, 80, 1, 1, 0, False),
+    'b64_c3x3_80': (64, 192, 320, 80, 80, 3, 1, 1, True),
+    'b64_c1x1_320': (64, 48, 80, 320, 320, 1, 1, 0, False),
 }
 names = sys.argv[1].split(',') if len(sys.argv) > 1 else list(CASES)
 iters = int(sys.argv[2]) if len(sys.argv) > 2 else 10
-e = _capi.Engine(_capi.make_config(max_batch=16))
+e = _capi.Engine(_capi.make_config(max_batch=64))
 rng = np.random.default_rng(0)
 for nm in names:
     n, h, w, ci, co, k, s, p, res = CASES[nm]
