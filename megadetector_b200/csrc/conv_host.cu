@@ -34,13 +34,10 @@ int conv_pick_bn(int cout_pad) {
 }
 
 int conv_cin_pad(int cin) {
-  // Narrow tail chunks are implemented and tested (MDB_CONV_TAIL=1) but OFF by default: measured on B200 they cost
-  // as much shared-memory fill time as a zero-filled 64-channel chunk (the TMA unit is bound by rows, not bytes:
-  // profiles/r01_conv_tail_probe.txt), and padded chunks keep the 3x3 row-halo main loop applicable.
-  static const char* e = getenv("MDB_CONV_TAIL");
-  const bool tails = e && e[0] == '1';
-  const int r = cin % 64;
-  if (tails && (r == 0 || r == 16 || r == 32)) return cin;
+  // Whole 64-channel chunks: channels beyond the tensor's are zero-filled by the TMA unit and meet zero weights.  Narrow
+  // tail chunks (16 / 32-channel boxes with their own swizzle width) were implemented and measured in round 1: they
+  // cost as much shared-memory fill time as a zero-filled 64-channel chunk (the TMA unit is bound by rows, not bytes:
+  // profiles/r01_conv_tail_probe.txt), so they were removed again.
   return ((cin + 63) / 64) * 64;
 }
 
@@ -111,9 +108,8 @@ ConvOp* conv_build(const ConvDesc& d, int num_sms) {
     // "tail" chunk with its own swizzle width (32 / 64-byte rows) instead of a mostly zero-filled 64-channel one:
     // shared-memory fill, not the tensor pipe, bounds these layers (profiles/r01_conv_oob_probe.txt).
     const bool pair = use_pair_kernel();
-    const int tail_w = (pair && (d.cin_pad % 64 == 16 || d.cin_pad % 64 == 32)) ? d.cin_pad % 64 : 0;
     const int kc = pair ? 64 : (d.cin_pad % 64 == 0 ? 64 : (d.cin_pad % 32 == 0 ? 32 : 16));
-    MDB_REQUIRE(!pair || tail_w || d.cin_pad % 64 == 0, "pair kernel: C_in per tap must be 64k, 64k+16 or 64k+32");
+    MDB_REQUIRE(!pair || d.cin_pad % 64 == 0, "pair kernel: C_in per tap must be padded to a multiple of 64");
     op->kc = kc;
     op->num_sms = num_sms;
     ConvParams& p = op->p;
@@ -176,9 +172,27 @@ ConvOp* conv_build(const ConvDesc& d, int num_sms) {
       PairParams& q = op->pp;
       q.H_out = p.H_out; q.W_out = p.W_out; q.tw = p.tw; q.th = p.th;
       q.n_tiles = p.n_tiles; q.BN = p.BN; q.Cout = p.Cout;
-      q.KH = p.KH; q.KW = p.KW; q.stride = p.stride; q.pad = p.pad; q.pad_x = pad_x;
-      q.chunks = p.chunks; q.Cin = p.Cin;
-      q.total_chunks = d.k * kw * p.chunks;
+      q.taps = d.k * kw;
+      q.chunks = p.chunks;
+      q.total_chunks = q.taps * p.chunks;
+      MDB_REQUIRE(q.taps <= 9, "pair kernel: at most 9 filter taps");
+      for (int i = 0; i < 10; ++i) q.tap_word[i] = 0;
+      for (int kh = 0; kh < d.k; ++kh)
+        for (int kx = 0; kx < kw; ++kx) {
+          int dx, dy, par = 0;
+          if (d.s == 1) {
+            dx = kx - pad_x;
+            dy = kh - d.pad;
+          } else {  // the tap reads one of the four parity views of the input, at half resolution
+            const int ty = kh - d.pad, tx = kx - pad_x;
+            const int py = ty & 1, px = tx & 1;
+            dy = (ty - py) >> 1;
+            dx = (tx - px) >> 1;
+            par = py * 2 + px;
+          }
+          MDB_REQUIRE(dx >= -8 && dx < 120 && dy >= -8 && dy < 120, "filter tap offset out of range");
+          q.tap_word[kh * kw + kx] = static_cast<uint32_t>(dx + 8) | static_cast<uint32_t>(dy + 8) << 8 | static_cast<uint32_t>(par) << 16;
+        }
       // chunks per pipeline stage: enough MMA time per mbarrier round trip (>= ~320 tensor cycles)
       {
         static const char* e = getenv("MDB_CONV_CPS");
@@ -193,7 +207,6 @@ ConvOp* conv_build(const ConvDesc& d, int num_sms) {
       q.dbg = nullptr;
       q.halo = 0;
       q.a_stages = 0;
-      q.tail_w = tail_w;
       {
         static const char* ep = getenv("MDB_CONV_PROBE");
         q.probe = ep ? atoi(ep) : 0;
@@ -204,6 +217,7 @@ ConvOp* conv_build(const ConvDesc& d, int num_sms) {
         if (d.res.base)
           wide = wide && (d.res.Ctot % 16 == 0) && (d.res.c_off % 16 == 0) && (reinterpret_cast<uintptr_t>(d.res.base) % 32 == 0);
         q.wide = wide ? 1 : 0;
+        q.fast = (wide && !out.fp32 && d.cout % 16 == 0 && d.cout_pad == d.cout) ? 1 : 0;
       }
       const size_t a_chunk = static_cast<size_t>(kTileM) * kc * 2;
       const size_t b_chunk = (static_cast<size_t>(p.BN / 2) * kc * 2 + 1023) & ~static_cast<size_t>(1023);
@@ -214,15 +228,15 @@ ConvOp* conv_build(const ConvDesc& d, int num_sms) {
         static const char* ehm = getenv("MDB_CONV_HALO_MIN");
         const int halo_min_chunks = ehm ? atoi(ehm) : 3;
         const double eff = static_cast<double>(Ho) * Wo / (static_cast<double>((Wo + 7) / 8 * 8) * ((Ho + 15) / 16 * 16));
-        if (allow && tail_w == 0 && d.k == 3 && kw == 3 && d.s == 1 && d.pad == 1 && pad_x == 1 && eff >= 0.85 && p.chunks >= halo_min_chunks) {  // measured: +9% at 160 ch, 0 at 320, -10% at 80
+        if (allow && d.k == 3 && kw == 3 && d.s == 1 && d.pad == 1 && pad_x == 1 && eff >= 0.85 && p.chunks >= halo_min_chunks) {  // measured: +9% at 160 ch, 0 at 320, -10% at 80
           q.halo = 1;
           q.a_stages = 2;
           q.tw = kHaloTw;
           q.th = kHaloTh;
           make_act_tmap(&op->tmA[0], in, kc, kHaloTw, kHaloRows, -1, -1);
           op->tmA[1] = op->tmA[2] = op->tmA[3] = op->tmA[0];
-          for (int i = 0; i < 4; ++i) op->maps.a[i] = op->maps.at[i] = op->tmA[0];
-          op->maps.b = op->maps.bt = op->tmB;
+          for (int i = 0; i < 4; ++i) op->maps.a[i] = op->tmA[0];
+          op->maps.b = op->tmB;
           const size_t budget = 227 * 1024 - 4096 - 1024;
           const size_t a_bytes = static_cast<size_t>(q.a_stages) * 3 * kHaloBox;
           int stages = static_cast<int>(std::min<size_t>(kPairMaxStages, (budget - a_bytes) / b_chunk));
@@ -241,21 +255,8 @@ ConvOp* conv_build(const ConvDesc& d, int num_sms) {
       stages = std::max(2, std::min(stages, std::max(2, stage_iters * 2)));
       q.stages = stages;
       op->smem = stage * stages + 1024;
-      for (int i = 0; i < 4; ++i) op->maps.a[i] = op->maps.at[i] = op->tmA[i];
-      op->maps.b = op->maps.bt = op->tmB;
-      if (tail_w) {
-        if (op->flat) {
-          make_act_tmap_flat(&op->maps.at[0], in, tail_w);
-          op->maps.at[1] = op->maps.at[2] = op->maps.at[3] = op->maps.at[0];
-        } else if (d.s == 1) {
-          make_act_tmap(&op->maps.at[0], in, tail_w, p.tw, p.th, -1, -1);
-          op->maps.at[1] = op->maps.at[2] = op->maps.at[3] = op->maps.at[0];
-        } else {
-          for (int py = 0; py < 2; ++py)
-            for (int px = 0; px < 2; ++px) make_act_tmap(&op->maps.at[py * 2 + px], in, tail_w, p.tw, p.th, py, px);
-        }
-        make_wgt_tmap(&op->maps.bt, d.wgt, d.k * kw * d.cin_pad, d.cout_pad, tail_w, p.BN / 2);
-      }
+      for (int i = 0; i < 4; ++i) op->maps.a[i] = op->tmA[i];
+      op->maps.b = op->tmB;
       set_smem_attr_pair<64>(op->smem);
       return op;
     }
@@ -299,6 +300,14 @@ static void conv_launch_pair(ConvOp* op, int n_img, cudaStream_t st) {
   p.pair_m = (p.m_tiles + 1) / 2;
   const long long total = static_cast<long long>(p.pair_m) * p.n_tiles;
   if (total <= 0) return;
+  // division-free tile decode: floor(x * ceil(2^32 / d) / 2^32) == x / d for every x with x * d < 2^32
+  auto magic = [&](int d, long long max_x) -> uint32_t {
+    MDB_REQUIRE(d >= 1 && max_x * d < (1ll << 32), "tile count too large for the 32-bit division-free decode");
+    return d == 1 ? 0u : static_cast<uint32_t>(((1ull << 32) + static_cast<uint64_t>(d) - 1) / static_cast<uint64_t>(d));
+  };
+  p.mg_ntiles = magic(p.n_tiles, total);
+  p.mg_tx = magic(p.tiles_x, 2ll * p.pair_m + 1);
+  p.mg_ty = magic(p.tiles_y, 2ll * p.pair_m + 1);
   const int clusters = static_cast<int>(std::min<long long>(total, op->num_sms / 2));
   const int grid = clusters * 2;
   static const bool debug = getenv("MDB_CONV_DEBUG") && getenv("MDB_CONV_DEBUG")[0] == '1';

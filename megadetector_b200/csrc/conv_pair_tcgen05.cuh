@@ -51,14 +51,16 @@ struct PairParams {
   int tw, th;
   int tiles_x, tiles_y;
   int m_tiles, pair_m, n_tiles;
+  uint32_t mg_ntiles, mg_tx, mg_ty;  // ceil(2^32 / d) for d = n_tiles, tiles_x, tiles_y (0 when d == 1): tile decode without division
   int BN, Cout;
-  int KH, KW, stride, pad;  // pad = rows (y)
-  int pad_x;                // columns; differs from pad only for the 3x1 stem
-  int chunks;        // C_in / KC
-  int Cin;
-  int total_chunks;  // KH*KW*chunks
-  int cps;           // chunks per stage (64 / KC)
+  int taps;          // KH*KW
+  int chunks;        // 64-channel chunks per tap
+  int total_chunks;  // taps * chunks
+  int cps;           // chunks per pipeline stage
   int stages;
+  // per filter tap: (dx + 8) | (dy + 8) << 8 | parity_map << 16 -- input offset of the tap relative to the output tile
+  // origin (stride 2: in the coordinates of the parity view the tap reads).  One spare entry: the producer reads one ahead.
+  uint32_t tap_word[10];
   const float* bias;
   void* out;
   long long out_pix_stride;
@@ -68,11 +70,11 @@ struct PairParams {
   int res_c_off;
   int act;
   int wide;        // 1: every epilogue row segment is 32-byte aligned -> 256-bit global accesses
-  int tail_w;      // channels of the last chunk of every tap when C_in % 64 is 16 or 32 (own swizzle width), else 0
+  int fast;        // 1: half output, wide, every 16-column chunk full -> the branch-free epilogue path
   int halo;        // 1: 3x3/s1 row-halo main loop (tile 8 x 16; A fetched per kw shift, reused across kh)
   int a_stages;    // halo mode: number of A (3-box) buffers
   uint32_t idesc;  // M = 256
-  long long* dbg;  // optional per-CTA cycle counters (MDB_CONV_DEBUG=1), null in production
+  long long* dbg;  // per-CTA cycle counters (MDB_CONV_DEBUG=1 in a -DMDB_CONV_TIMERS build), null otherwise
   int probe;       // timing probes only (results are garbage), bit mask: 1 = skip TMA loads, 2 = skip MMAs, 4 = epilogue releases
                    // the accumulator without reading it, 8 = no global stores/residual loads, 16 = no SiLU
 };
@@ -193,23 +195,112 @@ __device__ __forceinline__ void mbar_wait_timed(uint64_t* bar, uint32_t parity, 
   acc += clock64() - t0;
 }
 
-// TMA descriptors of one convolution: activation maps (dense, or the four stride-2 parity views) and the weight
-// map, each in two box widths: 64 channels (128-byte swizzle rows) and the narrower tail chunk (16 / 32 channels).
+// TMA descriptors of one convolution: activation maps (dense, or the four stride-2 parity views) and the weight map
 struct alignas(64) ConvMaps {
   CUtensorMap a[4];
   CUtensorMap b;
-  CUtensorMap at[4];
-  CUtensorMap bt;
 };
 
+__device__ __forceinline__ uint32_t fastdiv(uint32_t x, uint32_t magic) { return magic ? __umulhi(x, magic) : x; }
+
+// pair tile index -> N tile and the (x, y, image) position of THIS CTA's 128-row half
+__device__ __forceinline__ void decode_tile(const PairParams& p, int tile, uint32_t rank, int& n_tile, int& txi, int& tyi,
+                                            int& img) {
+  const uint32_t mt = fastdiv(static_cast<uint32_t>(tile), p.mg_ntiles);
+  n_tile = tile - static_cast<int>(mt) * p.n_tiles;
+  const uint32_t m_tile = 2u * mt + rank;
+  const uint32_t t2 = fastdiv(m_tile, p.mg_tx);
+  txi = static_cast<int>(m_tile) - static_cast<int>(t2) * p.tiles_x;
+  const uint32_t t3 = fastdiv(t2, p.mg_ty);
+  tyi = static_cast<int>(t2) - static_cast<int>(t3) * p.tiles_y;
+  img = static_cast<int>(t3);  // >= n_img for the padding tile of an odd tile count: TMA zero-fills, stores are masked
+}
+
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster_addr(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx_addr(uint32_t addr, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(addr), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma2_load_2d_addr(const CUtensorMap* m, uint32_t leader_bar, uint32_t dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(leader_bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma2_load_4d_addr(const CUtensorMap* m, uint32_t leader_bar, uint32_t dst, int c0, int c1,
+                                                  int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, "
+      "%6}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+// M=256 MMA with the two shared-memory descriptors given as (low word, common high word): the high word (SBO, version,
+// swizzle) never changes, so advancing K or the stage is one 32-bit add
+__device__ __forceinline__ void umma2_f16_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "mov.b64 da, {%1, %3};\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma2_commit_mc_addr(uint32_t bar_addr) {
+  const uint16_t mask = 3;
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar_addr),
+      "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_addr(uint32_t addr, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, P1;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(addr), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// spin on a phase parity; the watchdog counts polls (try_wait suspends the thread for a hardware-defined time, so 2^24
+// failed polls are seconds) and turns a protocol bug into a trap instead of a hung GPU
+__device__ __forceinline__ void mbar_wait_addr(uint32_t addr, uint32_t parity) {
+  if (mbar_try_wait_addr(addr, parity)) return;
+  uint32_t polls = 0;
+  while (!mbar_try_wait_addr(addr, parity)) {
+    if (++polls > (1u << 24)) { asm volatile("trap;"); }
+  }
+}
+__device__ __forceinline__ void mbar_wait_addr_timed(uint32_t addr, uint32_t parity, long long& acc) {
+  if (!kTimers) { mbar_wait_addr(addr, parity); return; }
+  const long long t0 = clock64();
+  mbar_wait_addr(addr, parity);
+  acc += clock64() - t0;
+}
+
+// The three roles run WARP-UNIFORM loops: every lane executes the loop control, the barrier waits and the coordinate
+// arithmetic (which ptxas then keeps on the uniform datapath, next to the TMA / MMA operands), and only the instructions
+// with side effects are issued by the elected lane.  The first version ran the whole loop inside `if (elect_one())`:
+// its ~110 dependent per-thread instructions per stage (R2UR round trips, re-loaded parameters) took 800-1100 cycles
+// per stage and bounded every layer with short stages (profiles/r01_conv_skeleton_probe.txt).
 template <int KC>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1)
-conv_pair_kernel(const __grid_constant__ ConvMaps maps, const PairParams p) {
-  const CUtensorMap& tmA0 = maps.a[0];
-  const CUtensorMap& tmA1 = maps.a[1];
-  const CUtensorMap& tmA2 = maps.a[2];
-  const CUtensorMap& tmA3 = maps.a[3];
-  const CUtensorMap& tmB = maps.b;
+conv_pair_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ PairParams p) {
   constexpr uint32_t ROW_BYTES = KC * 2;
   constexpr uint32_t A_CHUNK = kTileM * ROW_BYTES;  // 128 rows of one K chunk
 
@@ -236,7 +327,7 @@ conv_pair_kernel(const __grid_constant__ ConvMaps maps, const PairParams p) {
   // bytes that land in ONE CTA per chunk (A box + half-B box); the leader's barrier expects both CTAs' bytes
   const uint32_t tx_per_chunk = static_cast<uint32_t>(p.tw * p.th) * ROW_BYTES + half_n * ROW_BYTES;
 
-  const int S = p.stages;
+  const uint32_t S = static_cast<uint32_t>(p.stages);
   // TMEM accumulator ring: 512 columns hold 2 stages of up to 256 columns or 4 stages of up to 128
   const uint32_t acc_shift = p.BN <= 128 ? 2u : 1u;
   const uint32_t acc_mask = (1u << acc_shift) - 1u;
@@ -246,18 +337,14 @@ conv_pair_kernel(const __grid_constant__ ConvMaps maps, const PairParams p) {
   const int cluster_id = blockIdx.x >> 1;
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmA0);
-    tma_prefetch_desc(&tmB);
-    if (p.stride == 2) {
-      tma_prefetch_desc(&tmA1);
-      tma_prefetch_desc(&tmA2);
-      tma_prefetch_desc(&tmA3);
+    tma_prefetch_desc(&maps.a[0]);
+    tma_prefetch_desc(&maps.b);
+    if (p.tap_word[p.taps - 1] >> 16) {  // stride 2: the parity views
+      tma_prefetch_desc(&maps.a[1]);
+      tma_prefetch_desc(&maps.a[2]);
+      tma_prefetch_desc(&maps.a[3]);
     }
-    if (p.tail_w) {
-      tma_prefetch_desc(&maps.at[0]);
-      tma_prefetch_desc(&maps.bt);
-    }
-    for (int s = 0; s < S; ++s) {
+    for (uint32_t s = 0; s < S; ++s) {
       mbar_init(&full_bar[s], 2);   // leader's instance is the one in use: both producers arrive
       mbar_init(&empty_bar[s], 1);  // multicast commit of the leader's MMA thread
     }
@@ -280,224 +367,177 @@ conv_pair_kernel(const __grid_constant__ ConvMaps maps, const PairParams p) {
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
 
+  const uint32_t full0 = smem_u32(&full_bar[0]);
+  const uint32_t empty0 = smem_u32(&empty_bar[0]);
+  const uint32_t a_full0 = smem_u32(&a_full_bar[0]);
+  const uint32_t a_empty0 = smem_u32(&a_empty_bar[0]);
+  const uint32_t acc_full0 = smem_u32(&acc_full_bar[0]);
+  const uint32_t acc_empty0 = smem_u32(&acc_empty_bar[0]);
+
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================
-    // One thread; the loop body is kept to a few dozen instructions per stage: no integer division inside
-    // (running stage/phase counters, incremental tap/chunk counters) -- with ~150 dependent scalar instructions
-    // per stage this thread, not the memory system, was the bottleneck (profiles/r01_conv_dbg_v2b.txt).
-    // elect.sync (not `lane == 0`): inside an elected region ptxas knows a single thread is active and keeps TMA
-    // operands in uniform registers instead of emitting a waterfall loop around every UTMALDG.
-    if (elect_one()) {
-      const bool dbg = kTimers && p.dbg != nullptr;
-      long long w_empty = 0, w_arrive = 0, w_tma = 0;
-      uint32_t it = 0;
-      const long long t_start = clock64();
-      int s = 0;
-      uint32_t ph = 0;
-      const uint32_t tx_stage = 2u * tx_per_chunk;  // both CTAs' bytes of one chunk
-      if (p.halo) {
-        // ---- 3x3 / stride 1: per 64-channel chunk, three {64 ch, 8 px, 18 rows} boxes (one per kw shift) are
-        // fetched once and serve all three kh taps (the kh shift is a 1024-byte offset in shared memory);
-        // weights stream through their own ring, one tap per stage.  A bytes per chunk: 55 KB instead of 147 KB.
-        const uint32_t a_region = smem_base;
-        const uint32_t a_stage_bytes = 3u * kHaloBox;
-        const uint32_t b_region = smem_base + static_cast<uint32_t>(p.a_stages) * a_stage_bytes;
-        const uint32_t b_bytes = half_n * ROW_BYTES;
-        int as = 0;
-        uint32_t aph = 0;
-        for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
-          const int n_tile = tile % p.n_tiles;
-          const int m_tile = 2 * (tile / p.n_tiles) + static_cast<int>(rank);
-          const int txi = m_tile % p.tiles_x;
-          const int tyi = (m_tile / p.tiles_x) % p.tiles_y;
-          const int img = m_tile / (p.tiles_x * p.tiles_y);
-          const int ox0 = txi * kHaloTw, oy0 = tyi * kHaloTh;
-          const int nb0 = n_tile * p.BN + static_cast<int>(rank * half_n);
-          for (int c = 0; c < p.chunks; ++c) {
-            mbar_wait_timed(&a_empty_bar[as], aph ^ 1u, w_empty, dbg);
-            if (leader) mbar_arrive_expect_tx(&a_full_bar[as], 2u * a_stage_bytes);
-            else mbar_arrive_remote(&a_full_bar[as], 0);
-            const uint32_t abase = a_region + static_cast<uint32_t>(as) * a_stage_bytes;
+    const bool el = elect_one();
+    long long w_empty = 0;
+    uint32_t it = 0;
+    const long long t_start = kTimers ? clock64() : 0;
+    uint32_t s = 0, ph = 0;
+    // the LEADER's full barriers: as the mbarrier operand of a cta_group::2 TMA load (peer bit cleared) and as the
+    // shared::cluster address the non-leader arrives on
+    const uint32_t full0_tma = full0 & kPeerBitMask;
+    const uint32_t a_full0_tma = a_full0 & kPeerBitMask;
+    const uint32_t full0_remote = mapa_rank(full0, 0);
+    const uint32_t a_full0_remote = mapa_rank(a_full0, 0);
+    const bool loads = !(p.probe & 1);
+    if (p.halo) {
+      // ---- 3x3 / stride 1: per 64-channel chunk, three {64 ch, 8 px, 18 rows} boxes (one per kw shift) are
+      // fetched once and serve all three kh taps (the kh shift is a 1024-byte offset in shared memory);
+      // weights stream through their own ring, one tap per stage.  A bytes per chunk: 55 KB instead of 147 KB.
+      const uint32_t a_stage_bytes = 3u * kHaloBox;
+      const uint32_t b_region = smem_base + static_cast<uint32_t>(p.a_stages) * a_stage_bytes;
+      const uint32_t b_bytes = half_n * ROW_BYTES;
+      uint32_t as = 0, aph = 0;
+      for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
+        int n_tile, txi, tyi, img;
+        decode_tile(p, tile, rank, n_tile, txi, tyi, img);
+        const int ox0 = txi * kHaloTw - 1, oy0 = tyi * kHaloTh - 1;
+        const int nb0 = n_tile * p.BN + static_cast<int>(rank * half_n);
+        for (int c = 0; c < p.chunks; ++c) {
+          mbar_wait_addr_timed(a_empty0 + 8u * as, aph ^ 1u, w_empty);
+          if (el) {
+            if (leader) mbar_arrive_expect_tx_addr(a_full0 + 8u * as, loads ? 2u * a_stage_bytes : 0u);
+            else mbar_arrive_cluster_addr(a_full0_remote + 8u * as);
+            const uint32_t abase = smem_base + as * a_stage_bytes;
+            if (loads) {
 #pragma unroll
-            for (int kw = 0; kw < 3; ++kw)
-              tma2_load_4d(&tmA0, &a_full_bar[as], abase + static_cast<uint32_t>(kw) * kHaloBox, c * KC, ox0 + kw - 1,
-                           oy0 - 1, img);
-            if (++as == p.a_stages) { as = 0; aph ^= 1u; }
-            for (int tap = 0; tap < 9; ++tap) {
-              mbar_wait_timed(&empty_bar[s], ph ^ 1u, w_empty, dbg);
-              if (leader) mbar_arrive_expect_tx(&full_bar[s], 2u * b_bytes);
-              else mbar_arrive_remote(&full_bar[s], 0);
-              tma2_load_2d(&tmB, &full_bar[s], b_region + static_cast<uint32_t>(s) * b_chunk, tap * p.Cin + c * KC, nb0);
-              if (++s == S) { s = 0; ph ^= 1u; }
-              ++it;
+              for (int kw = 0; kw < 3; ++kw)
+                tma2_load_4d_addr(&maps.a[0], a_full0_tma + 8u * as, abase + static_cast<uint32_t>(kw) * kHaloBox, c * KC,
+                                  ox0 + kw, oy0, img);
             }
+          }
+          if (++as == static_cast<uint32_t>(p.a_stages)) { as = 0; aph ^= 1u; }
+          int kcol = c * KC;
+          for (int tap = 0; tap < 9; ++tap, kcol += p.chunks * KC) {
+            mbar_wait_addr_timed(empty0 + 8u * s, ph ^ 1u, w_empty);
+            if (el) {
+              if (leader) mbar_arrive_expect_tx_addr(full0 + 8u * s, loads ? 2u * b_bytes : 0u);
+              else mbar_arrive_cluster_addr(full0_remote + 8u * s);
+              if (loads) tma2_load_2d_addr(&maps.b, full0_tma + 8u * s, b_region + s * b_chunk, kcol, nb0);
+            }
+            if (++s == S) { s = 0; ph ^= 1u; }
+            ++it;
           }
         }
-      } else
+      }
+    } else {
+      const uint32_t tx_stage = 2u * tx_per_chunk;  // both CTAs' bytes of one chunk
       for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
-        const int n_tile = tile % p.n_tiles;
-        const int m_tile = 2 * (tile / p.n_tiles) + static_cast<int>(rank);
-        const int txi = m_tile % p.tiles_x;
-        const int tyi = (m_tile / p.tiles_x) % p.tiles_y;
-        const int img = m_tile / (p.tiles_x * p.tiles_y);  // >= n_img for the padding tile: TMA zero-fills
-        const int ox0 = txi * p.tw, oy0 = tyi * p.th;
+        int n_tile, txi, tyi, img;
+        decode_tile(p, tile, rank, n_tile, txi, tyi, img);
+        const int ox0 = txi * p.tw - 8, oy0 = tyi * p.th - 8;  // the tap words carry dx + 8, dy + 8
         const int nb0 = n_tile * p.BN + static_cast<int>(rank * half_n);
-        int kh = 0, kw = 0, c = 0, kcol = 0;
-        // coordinates of the current filter tap
-        int par = 0;
-        int x = 0, y = 0;
-        auto set_tap = [&]() {
-          if (p.stride == 1) {
-            x = ox0 + kw - p.pad_x;
-            y = oy0 + kh - p.pad;
-            par = 0;
-          } else {
-            const int ty_ = kh - p.pad, tx_ = kw - p.pad_x;
-            const int py = ty_ & 1, px = tx_ & 1;
-            y = oy0 + ((ty_ - py) >> 1);
-            x = ox0 + ((tx_ - px) >> 1);
-            par = py * 2 + px;
+        int tap = 0, c = 0, kcol = 0;
+        uint32_t w = p.tap_word[0];
+        for (int q0 = 0; q0 < p.total_chunks; q0 += p.cps) {
+          const int nch = min(p.cps, p.total_chunks - q0);
+          mbar_wait_addr_timed(empty0 + 8u * s, ph ^ 1u, w_empty);
+          if (el) {
+            if (leader) mbar_arrive_expect_tx_addr(full0 + 8u * s, loads ? static_cast<uint32_t>(nch) * tx_stage : 0u);
+            else mbar_arrive_cluster_addr(full0_remote + 8u * s);
           }
-        };
-        set_tap();
-        const int last_c = p.chunks - 1;
-        const uint32_t tail_tx = static_cast<uint32_t>(p.tw * p.th + static_cast<int>(half_n)) * static_cast<uint32_t>(p.tail_w) * 2u;
-        for (int done = 0; done < p.total_chunks;) {
-          const int nch = min(p.cps, p.total_chunks - done);
-          mbar_wait_timed(&empty_bar[s], ph ^ 1u, w_empty, dbg);
-          // bytes this stage brings into ONE CTA (full chunks: 128-byte rows; tail chunks: 32/64-byte rows)
-          uint32_t tx = 0;
-          {
-            int cc = c;
-            for (int j = 0; j < nch; ++j) {
-              tx += (p.tail_w && cc == last_c) ? tail_tx : tx_per_chunk;
-              if (++cc == p.chunks) cc = 0;
+          uint32_t dst = smem_base + s * stage_bytes;
+          for (int j = 0; j < nch; ++j, dst += chunk_bytes, kcol += KC) {
+            if (el && loads) {
+              tma2_load_4d_addr(&maps.a[w >> 16], full0_tma + 8u * s, dst, c * KC, ox0 + static_cast<int>(w & 0xffu),
+                                oy0 + static_cast<int>((w >> 8) & 0xffu), img);
+              tma2_load_2d_addr(&maps.b, full0_tma + 8u * s, dst + A_CHUNK, kcol, nb0);
             }
-          }
-          const long long tp0 = dbg ? clock64() : 0;
-          if (leader) mbar_arrive_expect_tx(&full_bar[s], (p.probe & 1) ? 0u : 2u * tx);
-          else mbar_arrive_remote(&full_bar[s], 0);
-          const long long tp1 = dbg ? clock64() : 0;
-          uint32_t dst = smem_base + static_cast<uint32_t>(s) * stage_bytes;
-          for (int j = 0; j < nch; ++j, dst += chunk_bytes) {
-            const bool tail = p.tail_w && c == last_c;
-            if (!(p.probe & 1)) {
-              tma2_load_4d(tail ? &maps.at[par] : &maps.a[par], &full_bar[s], dst, c * KC, x, y, img);
-              tma2_load_2d(tail ? &maps.bt : &tmB, &full_bar[s], dst + A_CHUNK, kcol, nb0);
-            }
-            kcol += tail ? p.tail_w : KC;
             if (++c == p.chunks) {
               c = 0;
-              if (++kw == p.KW) { kw = 0; ++kh; }
-              set_tap();
+              ++tap;
+              w = p.tap_word[tap];
             }
           }
-          if (dbg) { w_arrive += tp1 - tp0; w_tma += clock64() - tp1; }
-          done += nch;
           if (++s == S) { s = 0; ph ^= 1u; }
           ++it;
         }
       }
-      if (dbg) {
-        p.dbg[blockIdx.x * 16 + 8] = w_arrive;
-        p.dbg[blockIdx.x * 16 + 9] = w_tma;
-        p.dbg[blockIdx.x * 16 + 0] = clock64() - t_start;
-        p.dbg[blockIdx.x * 16 + 1] = w_empty;
-        p.dbg[blockIdx.x * 16 + 2] = it;
-      }
+    }
+    if (kTimers && p.dbg != nullptr && el) {
+      p.dbg[blockIdx.x * 16 + 0] = clock64() - t_start;
+      p.dbg[blockIdx.x * 16 + 1] = w_empty;
+      p.dbg[blockIdx.x * 16 + 2] = it;
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
-    if (leader && elect_one()) {
+    if (leader) {
+      const bool el = elect_one();
       uint32_t tcount = 0;
-      const bool dbg = kTimers && p.dbg != nullptr;
-      long long w_full = 0, w_acc = 0, w_issue = 0, w_commit = 0, w_commit_acc = 0, w_fence = 0;
-      const long long t_start = clock64();
-      int s = 0;
-      uint32_t ph = 0;
-      int as = 0;
-      uint32_t aph = 0;
-      // descriptor template: everything except the 14-bit start address is constant for the whole kernel
+      long long w_full = 0, w_acc = 0;
+      const long long t_start = kTimers ? clock64() : 0;
+      uint32_t s = 0, ph = 0;
+      uint32_t as = 0, aph = 0;  // halo mode: position in the A ring (continues across tiles)
       const uint64_t desc_tmpl = make_kmajor_desc(0, ROW_BYTES);
-      const uint64_t desc_tail = make_kmajor_desc(0, p.tail_w ? static_cast<uint32_t>(p.tail_w) * 2u : ROW_BYTES);
+      const uint32_t desc_hi = static_cast<uint32_t>(desc_tmpl >> 32);
+      const uint32_t desc_lo = static_cast<uint32_t>(desc_tmpl);  // LBO field; the start address is added per use
+      const bool mmas = !(p.probe & 2);
       for (int tile = cluster_id; tile < total_tiles; tile += num_clusters, ++tcount) {
         const uint32_t acc = tcount & acc_mask;
         const uint32_t acc_ph = (tcount >> acc_shift) & 1u;
-        mbar_wait_timed(&acc_empty_bar[acc], acc_ph ^ 1u, w_acc, dbg);
-        const long long tf0 = dbg ? clock64() : 0;
+        mbar_wait_addr_timed(acc_empty0 + 8u * acc, acc_ph ^ 1u, w_acc);
         tc_fence_after();
-        if (dbg) w_fence += clock64() - tf0;
         const uint32_t d_tmem = tmem_base + acc * acc_stride;
         if (p.halo) {
           const uint32_t a_stage_bytes = 3u * kHaloBox;
           const uint32_t b_region = smem_base + static_cast<uint32_t>(p.a_stages) * a_stage_bytes;
           for (int c = 0; c < p.chunks; ++c) {
-            mbar_wait_timed(&a_full_bar[as], aph, w_full, dbg);
-            tc_fence_after();
-            const uint32_t abase = smem_base + static_cast<uint32_t>(as) * a_stage_bytes;
-            for (int tap = 0; tap < 9; ++tap) {
-              const int kh = tap / 3, kw = tap - 3 * kh;
-              mbar_wait_timed(&full_bar[s], ph, w_full, dbg);
-              tc_fence_after();
-              // rows of the tile for this tap: halo rows kh .. kh+15 of the kw-shifted box (8 px = 1024 B per row)
-              const uint32_t a_addr = abase + static_cast<uint32_t>(kw) * kHaloBox + static_cast<uint32_t>(kh) * 1024u;
-              const uint32_t b_addr = b_region + static_cast<uint32_t>(s) * b_chunk;
-              const uint64_t da = desc_tmpl | static_cast<uint64_t>((a_addr & 0x3FFFFu) >> 4);
-              const uint64_t db = desc_tmpl | static_cast<uint64_t>((b_addr & 0x3FFFFu) >> 4);
+            mbar_wait_addr_timed(a_full0 + 8u * as, aph, w_full);
+            const uint32_t abase = smem_base + as * a_stage_bytes;
+#pragma unroll 1
+            for (int kh = 0; kh < 3; ++kh) {
 #pragma unroll
-              for (int k = 0; k < KC / 16; ++k)
-                umma2_f16(d_tmem, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), p.idesc,
-                          (c > 0 || tap > 0 || k > 0) ? 1u : 0u);
-              umma2_commit_mc(&empty_bar[s]);
-              if (++s == S) { s = 0; ph ^= 1u; }
+              for (int kw = 0; kw < 3; ++kw) {
+                mbar_wait_addr_timed(full0 + 8u * s, ph, w_full);
+                tc_fence_after();
+                // rows of the tile for this tap: halo rows kh .. kh+15 of the kw-shifted box (8 px = 1024 B per row)
+                const uint32_t a_lo = desc_lo | ((abase + static_cast<uint32_t>(kw) * kHaloBox + static_cast<uint32_t>(kh) * 1024u) >> 4);
+                const uint32_t b_lo = desc_lo | ((b_region + s * b_chunk) >> 4);
+                if (el) {
+                  if (mmas) {
+#pragma unroll
+                    for (int k = 0; k < KC / 16; ++k)
+                      umma2_f16_lo(d_tmem, a_lo + 2u * k, b_lo + 2u * k, desc_hi, p.idesc, (c | kh | kw | k) != 0 ? 1u : 0u);
+                  }
+                  umma2_commit_mc_addr(empty0 + 8u * s);
+                }
+                if (++s == S) { s = 0; ph ^= 1u; }
+              }
             }
-            umma2_commit_mc(&a_empty_bar[as]);
-            if (++as == p.a_stages) { as = 0; aph ^= 1u; }
+            if (el) umma2_commit_mc_addr(a_empty0 + 8u * as);
+            if (++as == static_cast<uint32_t>(p.a_stages)) { as = 0; aph ^= 1u; }
           }
-        } else
-        {
-          int c = 0;
-          const int last_c = p.chunks - 1;
-          for (int done = 0; done < p.total_chunks;) {
-            const int nch = min(p.cps, p.total_chunks - done);
-            mbar_wait_timed(&full_bar[s], ph, w_full, dbg);
+        } else {
+          for (int q0 = 0; q0 < p.total_chunks; q0 += p.cps) {
+            const int nch = min(p.cps, p.total_chunks - q0);
+            mbar_wait_addr_timed(full0 + 8u * s, ph, w_full);
             tc_fence_after();
-            const long long ti0 = dbg ? clock64() : 0;
-            uint32_t a_addr = smem_base + static_cast<uint32_t>(s) * stage_bytes;
-            for (int j = 0; j < nch; ++j, a_addr += chunk_bytes) {
-              const bool tail = p.tail_w && c == last_c;
-              const uint64_t tmpl = tail ? desc_tail : desc_tmpl;
-              const uint64_t da = tmpl | static_cast<uint64_t>((a_addr & 0x3FFFFu) >> 4);
-              const uint64_t db = tmpl | static_cast<uint64_t>(((a_addr + A_CHUNK) & 0x3FFFFu) >> 4);
-              if (!(p.probe & 2)) {
-                if (!tail) {
+            uint32_t a_lo = desc_lo | ((smem_base + s * stage_bytes) >> 4);
+            if (el) {
+              for (int j = 0; j < nch; ++j, a_lo += chunk_bytes >> 4) {
+                if (mmas) {
 #pragma unroll
                   for (int k = 0; k < KC / 16; ++k)
-                    umma2_f16(d_tmem, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), p.idesc,
-                              (done > 0 || j > 0 || k > 0) ? 1u : 0u);
-                } else {
-                  umma2_f16(d_tmem, da, db, p.idesc, (done > 0 || j > 0) ? 1u : 0u);
-                  if (p.tail_w == 32) umma2_f16(d_tmem, da + 2ull, db + 2ull, p.idesc, 1u);
+                    umma2_f16_lo(d_tmem, a_lo + 2u * k, a_lo + (A_CHUNK >> 4) + 2u * k, desc_hi, p.idesc,
+                                 (q0 | j | k) != 0 ? 1u : 0u);
                 }
               }
-              if (++c == p.chunks) c = 0;
+              umma2_commit_mc_addr(empty0 + 8u * s);
             }
-            const long long ti1 = dbg ? clock64() : 0;
-            umma2_commit_mc(&empty_bar[s]);
-            if (dbg) { w_issue += ti1 - ti0; w_commit += clock64() - ti1; }
-            done += nch;
             if (++s == S) { s = 0; ph ^= 1u; }
           }
         }
-        const long long tc0 = dbg ? clock64() : 0;
-        umma2_commit_mc(&acc_full_bar[acc]);
-        if (dbg) w_commit_acc += clock64() - tc0;
+        if (el) umma2_commit_mc_addr(acc_full0 + 8u * acc);
       }
-      if (dbg) {
-        p.dbg[blockIdx.x * 16 + 10] = w_commit;
-        p.dbg[blockIdx.x * 16 + 11] = w_commit_acc;
-        p.dbg[blockIdx.x * 16 + 12] = w_fence;
-        p.dbg[blockIdx.x * 16 + 3] = w_issue;
+      if (kTimers && p.dbg != nullptr && el) {
         p.dbg[blockIdx.x * 16 + 4] = clock64() - t_start;
         p.dbg[blockIdx.x * 16 + 5] = w_full;
         p.dbg[blockIdx.x * 16 + 6] = w_acc;
@@ -505,7 +545,7 @@ conv_pair_kernel(const __grid_constant__ ConvMaps maps, const PairParams p) {
       }
     }
   } else {
-    // ===================== epilogue (warps 2..9 of both CTAs) =====================
+    // ===================== epilogue (warps 2.. of both CTAs) =====================
     const uint32_t ew = warp - 2;          // 0..kPairEpiWarps-1
     const uint32_t quad = warp & 3u;       // TMEM lane quadrant this warp may read
     const uint32_t part = ew >> 2;         // which interleaved set of 16-column chunks
@@ -515,20 +555,17 @@ conv_pair_kernel(const __grid_constant__ ConvMaps maps, const PairParams p) {
     const int tx = static_cast<int>(row) - ty * p.tw;
     const int et = static_cast<int>(threadIdx.x) - 64;  // 0..32*kPairEpiWarps-1
     const int nchunks = p.BN >> 4;
+    const uint32_t acc_empty_remote = mapa_rank(acc_empty0, 0);
     uint32_t tcount = 0;
     int bias_tile = -1;
     uint32_t bias_buf = 0;
-    const bool edbg = kTimers && p.dbg != nullptr;
     long long e_wait = 0, e_proc = 0;
-    const long long e_start = edbg ? clock64() : 0;
+    const long long e_start = kTimers ? clock64() : 0;
     for (int tile = cluster_id; tile < total_tiles; tile += num_clusters, ++tcount) {
       const uint32_t acc = tcount & acc_mask;
       const uint32_t acc_ph = (tcount >> acc_shift) & 1u;
-      const int n_tile = tile % p.n_tiles;
-      const int m_tile = 2 * (tile / p.n_tiles) + static_cast<int>(rank);
-      const int txi = m_tile % p.tiles_x;
-      const int tyi = (m_tile / p.tiles_x) % p.tiles_y;
-      const int img = m_tile / (p.tiles_x * p.tiles_y);
+      int n_tile, txi, tyi, img;
+      decode_tile(p, tile, rank, n_tile, txi, tyi, img);
       const int ox = txi * p.tw + tx, oy = tyi * p.th + ty;
       const int n0 = n_tile * p.BN;
       const bool valid = (img < p.n_img) && (ty < p.th) && (ox < p.W_out) && (oy < p.H_out);
@@ -544,26 +581,19 @@ conv_pair_kernel(const __grid_constant__ ConvMaps maps, const PairParams p) {
       }
       const float* bs = bias_s[bias_buf];
 
-      const long long te0 = edbg ? clock64() : 0;
-      if (MDB_EPI_SLEEP > 0) mbar_wait_backoff(&acc_full_bar[acc], acc_ph, MDB_EPI_SLEEP);
-      else mbar_wait(&acc_full_bar[acc], acc_ph);
+      const long long te0 = kTimers ? clock64() : 0;
+      mbar_wait_addr(acc_full0 + 8u * acc, acc_ph);
       tc_fence_after();
-      const long long te1 = edbg ? clock64() : 0;
+      const long long te1 = kTimers ? clock64() : 0;
       const uint32_t taddr = tmem_base + ((quad * 32u) << 16) + acc * acc_stride;
-      // one 16-column chunk: +bias -> SiLU -> (+residual) -> store.  Registers only (static indexing).
-      auto process = [&](const uint32_t (&vv)[16], int jj) {
-        const int col0 = n0 + jj * 16;
-        if (!(valid && col0 < p.Cout) || (p.probe & 4)) return;
+
+      // ---- fast path: half output, 32-byte aligned row segments, every chunk full (all but the Detect heads)
+      __half* const orow = reinterpret_cast<__half*>(p.out) + pix * p.out_pix_stride + p.out_c_off + n0;
+      const __half* const rrow = p.res != nullptr ? p.res + pix * p.res_pix_stride + p.res_c_off + n0 : nullptr;
+      auto process_fast = [&](const uint32_t (&vv)[16], int jj) {
+        if (!valid || (p.probe & 4)) return;
         uint4 r0 = make_uint4(0, 0, 0, 0), r1 = make_uint4(0, 0, 0, 0);
-        if (p.res != nullptr && !(p.probe & 8)) {
-          const __half* rp = p.res + pix * p.res_pix_stride + p.res_c_off + col0;
-          if (p.wide) {
-            ldg256(rp, r0, r1);
-          } else {
-            r0 = __ldg(reinterpret_cast<const uint4*>(rp));
-            r1 = __ldg(reinterpret_cast<const uint4*>(rp) + 1);
-          }
-        }
+        if (rrow != nullptr && !(p.probe & 8)) ldg256(rrow + jj * 16, r0, r1);
         float f[16];
         const float4* b4 = reinterpret_cast<const float4*>(bs + jj * 16);
 #pragma unroll
@@ -575,6 +605,57 @@ conv_pair_kernel(const __grid_constant__ ConvMaps maps, const PairParams p) {
           f[4 * q + 3] = __uint_as_float(vv[4 * q + 3]) + bb.w;
         }
         if (p.act && !(p.probe & 16)) {
+#pragma unroll
+          for (int e = 0; e < 16; e += 4) silu4(f[e], f[e + 1], f[e + 2], f[e + 3]);
+        }
+        if (rrow != nullptr) {
+          const __half2* h0 = reinterpret_cast<const __half2*>(&r0);
+          const __half2* h1 = reinterpret_cast<const __half2*>(&r1);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 a = __half22float2(h0[e]);
+            const float2 b = __half22float2(h1[e]);
+            f[2 * e] += a.x;
+            f[2 * e + 1] += a.y;
+            f[8 + 2 * e] += b.x;
+            f[8 + 2 * e + 1] += b.y;
+          }
+        }
+        uint4 o0, o1;
+        __half2* q0 = reinterpret_cast<__half2*>(&o0);
+        __half2* q1 = reinterpret_cast<__half2*>(&o1);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          q0[e] = __floats2half2_rn(f[2 * e], f[2 * e + 1]);
+          q1[e] = __floats2half2_rn(f[8 + 2 * e], f[8 + 2 * e + 1]);
+        }
+        if (p.probe & 8) {
+          if (o0.x == 0x7fff7fffu && o1.w == 0x7fff7fffu) stg256(orow + jj * 16, o0, o1);  // keeps the math alive, never true
+        } else {
+          stg256(orow + jj * 16, o0, o1);
+        }
+      };
+      // ---- general path: fp32 outputs, partial chunks, unaligned views
+      auto process = [&](const uint32_t (&vv)[16], int jj) {
+        const int col0 = n0 + jj * 16;
+        if (!(valid && col0 < p.Cout) || (p.probe & 4)) return;
+        uint4 r0 = make_uint4(0, 0, 0, 0), r1 = make_uint4(0, 0, 0, 0);
+        if (p.res != nullptr) {
+          const __half* rp = p.res + pix * p.res_pix_stride + p.res_c_off + col0;
+          r0 = __ldg(reinterpret_cast<const uint4*>(rp));
+          r1 = __ldg(reinterpret_cast<const uint4*>(rp) + 1);
+        }
+        float f[16];
+        const float4* b4 = reinterpret_cast<const float4*>(bs + jj * 16);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 bb = b4[q];
+          f[4 * q + 0] = __uint_as_float(vv[4 * q + 0]) + bb.x;
+          f[4 * q + 1] = __uint_as_float(vv[4 * q + 1]) + bb.y;
+          f[4 * q + 2] = __uint_as_float(vv[4 * q + 2]) + bb.z;
+          f[4 * q + 3] = __uint_as_float(vv[4 * q + 3]) + bb.w;
+        }
+        if (p.act) {
 #pragma unroll
           for (int e = 0; e < 16; e += 4) silu4(f[e], f[e + 1], f[e + 2], f[e + 3]);
         }
@@ -593,17 +674,7 @@ conv_pair_kernel(const __grid_constant__ ConvMaps maps, const PairParams p) {
         }
         if (p.out_fp32) {
           float* op = reinterpret_cast<float*>(p.out) + pix * p.out_pix_stride + p.out_c_off + col0;
-          if (col0 + 16 <= p.Cout && p.wide) {
-            uint4 w0, w1;
-#pragma unroll
-            for (int hh = 0; hh < 2; ++hh) {
-              w0 = make_uint4(__float_as_uint(f[8 * hh]), __float_as_uint(f[8 * hh + 1]), __float_as_uint(f[8 * hh + 2]),
-                              __float_as_uint(f[8 * hh + 3]));
-              w1 = make_uint4(__float_as_uint(f[8 * hh + 4]), __float_as_uint(f[8 * hh + 5]),
-                              __float_as_uint(f[8 * hh + 6]), __float_as_uint(f[8 * hh + 7]));
-              stg256(op + 8 * hh, w0, w1);
-            }
-          } else if (col0 + 16 <= p.Cout) {
+          if (col0 + 16 <= p.Cout) {
 #pragma unroll
             for (int e = 0; e < 4; ++e)
               reinterpret_cast<float4*>(op)[e] = make_float4(f[4 * e], f[4 * e + 1], f[4 * e + 2], f[4 * e + 3]);
@@ -623,14 +694,8 @@ conv_pair_kernel(const __grid_constant__ ConvMaps maps, const PairParams p) {
               q0[e] = __floats2half2_rn(f[2 * e], f[2 * e + 1]);
               q1[e] = __floats2half2_rn(f[8 + 2 * e], f[8 + 2 * e + 1]);
             }
-            if (p.probe & 8) {
-              if (o0.x == 0x7fff7fffu && o1.w == 0x7fff7fffu) stg256(op, o0, o1);  // keeps the math alive, never true
-            } else if (p.wide) {
-              stg256(op, o0, o1);
-            } else {
-              reinterpret_cast<uint4*>(op)[0] = o0;
-              reinterpret_cast<uint4*>(op)[1] = o1;
-            }
+            reinterpret_cast<uint4*>(op)[0] = o0;
+            reinterpret_cast<uint4*>(op)[1] = o1;
           } else {
 #pragma unroll
             for (int e = 0; e < 16; ++e)
@@ -642,27 +707,41 @@ conv_pair_kernel(const __grid_constant__ ConvMaps maps, const PairParams p) {
       uint32_t va[16], vb[16];
       int j = static_cast<int>(part);
       if (j < nchunks) tmem_ld16(taddr + static_cast<uint32_t>(j * 16), va);
-      while (j < nchunks) {
-        tmem_ld_wait();
-        if (j + kParts < nchunks) tmem_ld16(taddr + static_cast<uint32_t>((j + kParts) * 16), vb);
-        process(va, j);
-        j += kParts;
-        if (j >= nchunks) break;
-        tmem_ld_wait();
-        if (j + kParts < nchunks) tmem_ld16(taddr + static_cast<uint32_t>((j + kParts) * 16), va);
-        process(vb, j);
-        j += kParts;
+      if (p.fast) {
+        while (j < nchunks) {
+          tmem_ld_wait();
+          if (j + kParts < nchunks) tmem_ld16(taddr + static_cast<uint32_t>((j + kParts) * 16), vb);
+          process_fast(va, j);
+          j += kParts;
+          if (j >= nchunks) break;
+          tmem_ld_wait();
+          if (j + kParts < nchunks) tmem_ld16(taddr + static_cast<uint32_t>((j + kParts) * 16), va);
+          process_fast(vb, j);
+          j += kParts;
+        }
+      } else {
+        while (j < nchunks) {
+          tmem_ld_wait();
+          if (j + kParts < nchunks) tmem_ld16(taddr + static_cast<uint32_t>((j + kParts) * 16), vb);
+          process(va, j);
+          j += kParts;
+          if (j >= nchunks) break;
+          tmem_ld_wait();
+          if (j + kParts < nchunks) tmem_ld16(taddr + static_cast<uint32_t>((j + kParts) * 16), va);
+          process(vb, j);
+          j += kParts;
+        }
       }
       // all TMEM reads of this warp have completed (tcgen05.wait::ld): hand the accumulator stage back
       tc_fence_before();
       __syncwarp();
-      if (edbg) { e_wait += te1 - te0; e_proc += clock64() - te1; }
+      if (kTimers) { e_wait += te1 - te0; e_proc += clock64() - te1; }
       if (lane == 0) {
         if (leader) mbar_arrive(&acc_empty_bar[acc]);
-        else mbar_arrive_remote(&acc_empty_bar[acc], 0);
+        else mbar_arrive_cluster_addr(acc_empty_remote + 8u * acc);
       }
     }
-    if (edbg && ew == 0 && lane == 0) {
+    if (kTimers && p.dbg != nullptr && ew == 0 && lane == 0) {
       p.dbg[blockIdx.x * 16 + 13] = e_wait;
       p.dbg[blockIdx.x * 16 + 14] = e_proc;
       p.dbg[blockIdx.x * 16 + 15] = clock64() - e_start;
