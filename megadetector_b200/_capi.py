@@ -48,8 +48,9 @@ def load_library():
     if _lib is not None:
         return _lib
     try:  # rebuild when the sources changed and nvcc is here (a no-op stamp check otherwise)
-        from .build import build as _build
-        _build()
+        if not (_VARIANT and os.path.exists(LIB_PATH)):  # an experiment variant is frozen once built (A/B against the tree)
+            from .build import build as _build
+            _build()
     except Exception as e:  # an up-to-date prebuilt .so is fine without nvcc
         if not os.path.exists(LIB_PATH):
             raise RuntimeError('libmdb200.so is missing and could not be built: {}'.format(e))

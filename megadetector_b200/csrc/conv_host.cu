@@ -176,6 +176,7 @@ ConvOp* conv_build(const ConvDesc& d, int num_sms) {
       q.chunks = p.chunks;
       q.total_chunks = q.taps * p.chunks;
       MDB_REQUIRE(q.taps <= 9, "pair kernel: at most 9 filter taps");
+      MDB_REQUIRE(d.cout_pad <= kPairMaxCout, "pair kernel: at most 1280 (padded) output channels");
       for (int i = 0; i < 10; ++i) q.tap_word[i] = 0;
       for (int kh = 0; kh < d.k; ++kh)
         for (int kx = 0; kx < kw; ++kx) {
@@ -208,7 +209,7 @@ ConvOp* conv_build(const ConvDesc& d, int num_sms) {
       q.halo = 0;
       q.a_stages = 0;
       {
-        static const char* ep = getenv("MDB_CONV_PROBE");
+        static const char* ep = getenv("MDB_CONV_PROBE");  // honoured by -DMDB_CONV_PROBES builds only
         q.probe = ep ? atoi(ep) : 0;
       }
       {
@@ -226,9 +227,9 @@ ConvOp* conv_build(const ConvDesc& d, int num_sms) {
         static const char* eh = getenv("MDB_CONV_HALO");
         const bool allow = !(eh && eh[0] == '0');
         static const char* ehm = getenv("MDB_CONV_HALO_MIN");
-        const int halo_min_chunks = ehm ? atoi(ehm) : 3;
+        const int halo_min_chunks = ehm ? atoi(ehm) : 2;
         const double eff = static_cast<double>(Ho) * Wo / (static_cast<double>((Wo + 7) / 8 * 8) * ((Ho + 15) / 16 * 16));
-        if (allow && d.k == 3 && kw == 3 && d.s == 1 && d.pad == 1 && pad_x == 1 && eff >= 0.85 && p.chunks >= halo_min_chunks) {  // measured: +9% at 160 ch, 0 at 320, -10% at 80
+        if (allow && d.k == 3 && kw == 3 && d.s == 1 && d.pad == 1 && pad_x == 1 && eff >= 0.85 && p.chunks >= halo_min_chunks) {  // measured (one filter row per weight stage): -26% time at 80 ch, -16% at 160, -9% at 320
           q.halo = 1;
           q.a_stages = 2;
           q.tw = kHaloTw;
@@ -237,19 +238,19 @@ ConvOp* conv_build(const ConvDesc& d, int num_sms) {
           op->tmA[1] = op->tmA[2] = op->tmA[3] = op->tmA[0];
           for (int i = 0; i < 4; ++i) op->maps.a[i] = op->tmA[0];
           op->maps.b = op->tmB;
-          const size_t budget = 227 * 1024 - 4096 - 1024;
+          const size_t budget = 227 * 1024 - 8192 - 1024;  // static: barriers + the bias vector; alignment slack
           const size_t a_bytes = static_cast<size_t>(q.a_stages) * 3 * kHaloBox;
-          int stages = static_cast<int>(std::min<size_t>(kPairMaxStages, (budget - a_bytes) / b_chunk));
-          MDB_REQUIRE(stages >= 4, "not enough shared memory for the halo pipeline");
+          int stages = static_cast<int>(std::min<size_t>(kPairMaxStages, (budget - a_bytes) / (3 * b_chunk)));  // a stage = one filter row
+          MDB_REQUIRE(stages >= 2, "not enough shared memory for the halo pipeline");
           q.stages = stages;
           q.cps = 1;
-          op->smem = a_bytes + b_chunk * stages + 1024;
+          op->smem = a_bytes + 3 * b_chunk * stages + 1024;
           set_smem_attr_pair<64>(op->smem);
           return op;
         }
       }
       const size_t stage = static_cast<size_t>(q.cps) * (a_chunk + b_chunk);
-      const size_t budget = 227 * 1024 - 4096;  // static: barriers + bias staging; alignment slack
+      const size_t budget = 227 * 1024 - 8192;  // static: barriers + the bias vector; alignment slack
       const int stage_iters = (q.total_chunks + q.cps - 1) / q.cps;
       int stages = static_cast<int>(std::min<size_t>(kPairMaxStages, (budget - 1024) / stage));
       stages = std::max(2, std::min(stages, std::max(2, stage_iters * 2)));

@@ -32,6 +32,12 @@ constexpr bool kTimers = true;
 #else
 constexpr bool kTimers = false;
 #endif
+// Timing probes (PairParams::probe) exist only in -DMDB_CONV_PROBES builds
+#ifdef MDB_CONV_PROBES
+constexpr bool kProbes = true;
+#else
+constexpr bool kProbes = false;
+#endif
 #ifndef MDB_EPI_SLEEP
 #define MDB_EPI_SLEEP 0
 #endif
@@ -41,6 +47,7 @@ constexpr bool kTimers = false;
 constexpr int kPairEpiWarps = MDB_EPI_WARPS;  // a multiple of four: each TMEM lane quadrant gets kPairEpiWarps / 4
 constexpr int kPairThreads = 64 + 32 * kPairEpiWarps;
 constexpr int kPairMaxStages = 12;
+constexpr int kPairMaxCout = 1280;  // padded output channels per layer (bias staging in shared memory)
 constexpr int kHaloRows = 18;                       // th + 2
 constexpr int kHaloTw = 8, kHaloTh = 16;
 constexpr uint32_t kHaloBox = kHaloRows * kHaloTw * 128;  // bytes of one {64 ch, 8 px, 18 rows} box
@@ -264,6 +271,9 @@ __device__ __forceinline__ void umma2_commit_mc_addr(uint32_t bar_addr) {
       "h"(mask)
       : "memory");
 }
+// try_wait WITHOUT a suspend-time hint on purpose: with a hint (1 ms, as CUTLASS passes) the hardware parks the thread and
+// the wake-up latency cost 5-8% on the 1x1 layers (measured A/B, profiles/r01_conv_ab_suspend_hint.txt), although the
+// polling loops are ~20% of all issued instructions there.
 __device__ __forceinline__ bool mbar_try_wait_addr(uint32_t addr, uint32_t parity) {
   uint32_t ok;
   asm volatile(
@@ -277,13 +287,13 @@ __device__ __forceinline__ bool mbar_try_wait_addr(uint32_t addr, uint32_t parit
       : "memory");
   return ok != 0;
 }
-// spin on a phase parity; the watchdog counts polls (try_wait suspends the thread for a hardware-defined time, so 2^24
-// failed polls are seconds) and turns a protocol bug into a trap instead of a hung GPU
+// wait on a phase parity; the watchdog counts expired hints and turns a protocol bug into a trap instead of a hung GPU
 __device__ __forceinline__ void mbar_wait_addr(uint32_t addr, uint32_t parity) {
   if (mbar_try_wait_addr(addr, parity)) return;
+  const long long t0 = clock64();
   uint32_t polls = 0;
   while (!mbar_try_wait_addr(addr, parity)) {
-    if (++polls > (1u << 24)) { asm volatile("trap;"); }
+    if ((++polls & 63u) == 0 && clock64() - t0 > 4000000000LL) { asm volatile("trap;"); }  // ~2 s of SM clocks
   }
 }
 __device__ __forceinline__ void mbar_wait_addr_timed(uint32_t addr, uint32_t parity, long long& acc) {
@@ -312,7 +322,7 @@ conv_pair_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
   __shared__ __align__(8) uint64_t a_full_bar[kHaloMaxA];
   __shared__ __align__(8) uint64_t a_empty_bar[kHaloMaxA];
   __shared__ uint32_t tmem_base_smem;
-  __shared__ __align__(16) float bias_s[2][256];
+  __shared__ __align__(16) float bias_all[kPairMaxCout];  // the layer's whole (padded) bias vector
 
   const uint32_t warp = threadIdx.x >> 5;
   const uint32_t lane = threadIdx.x & 31;
@@ -362,6 +372,7 @@ conv_pair_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
     tmem_alloc2(&tmem_base_smem, kTmemCols);
     tmem_relinquish2();
   }
+  for (int i = static_cast<int>(threadIdx.x); i < p.n_tiles * p.BN; i += kPairThreads) bias_all[i] = __ldg(p.bias + i);
   tc_fence_before();
   cluster_sync_all();
   tc_fence_after();
@@ -387,11 +398,11 @@ conv_pair_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
     const uint32_t a_full0_tma = a_full0 & kPeerBitMask;
     const uint32_t full0_remote = mapa_rank(full0, 0);
     const uint32_t a_full0_remote = mapa_rank(a_full0, 0);
-    const bool loads = !(p.probe & 1);
+    const bool loads = !(kProbes && (p.probe & 1));
     if (p.halo) {
       // ---- 3x3 / stride 1: per 64-channel chunk, three {64 ch, 8 px, 18 rows} boxes (one per kw shift) are
       // fetched once and serve all three kh taps (the kh shift is a 1024-byte offset in shared memory);
-      // weights stream through their own ring, one tap per stage.  A bytes per chunk: 55 KB instead of 147 KB.
+      // weights stream through their own ring, one filter row per stage.  A bytes per chunk: 55 KB instead of 147 KB.
       const uint32_t a_stage_bytes = 3u * kHaloBox;
       const uint32_t b_region = smem_base + static_cast<uint32_t>(p.a_stages) * a_stage_bytes;
       const uint32_t b_bytes = half_n * ROW_BYTES;
@@ -415,13 +426,21 @@ conv_pair_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
             }
           }
           if (++as == static_cast<uint32_t>(p.a_stages)) { as = 0; aph ^= 1u; }
+          // weights: one stage per filter row (three taps, 12 MMAs): a stage per tap (4 MMAs, ~160-320 tensor cycles)
+          // left the two single-thread roles no slack per barrier round trip
           int kcol = c * KC;
-          for (int tap = 0; tap < 9; ++tap, kcol += p.chunks * KC) {
+          const int tap_cols = p.chunks * KC;
+          for (int kh = 0; kh < 3; ++kh, kcol += 3 * tap_cols) {
             mbar_wait_addr_timed(empty0 + 8u * s, ph ^ 1u, w_empty);
             if (el) {
-              if (leader) mbar_arrive_expect_tx_addr(full0 + 8u * s, loads ? 2u * b_bytes : 0u);
+              if (leader) mbar_arrive_expect_tx_addr(full0 + 8u * s, loads ? 6u * b_bytes : 0u);
               else mbar_arrive_cluster_addr(full0_remote + 8u * s);
-              if (loads) tma2_load_2d_addr(&maps.b, full0_tma + 8u * s, b_region + s * b_chunk, kcol, nb0);
+              if (loads) {
+                const uint32_t bdst = b_region + s * 3u * b_chunk;
+#pragma unroll
+                for (int kw = 0; kw < 3; ++kw)
+                  tma2_load_2d_addr(&maps.b, full0_tma + 8u * s, bdst + static_cast<uint32_t>(kw) * b_chunk, kcol + kw * tap_cols, nb0);
+              }
             }
             if (++s == S) { s = 0; ph ^= 1u; }
             ++it;
@@ -479,7 +498,7 @@ conv_pair_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
       const uint64_t desc_tmpl = make_kmajor_desc(0, ROW_BYTES);
       const uint32_t desc_hi = static_cast<uint32_t>(desc_tmpl >> 32);
       const uint32_t desc_lo = static_cast<uint32_t>(desc_tmpl);  // LBO field; the start address is added per use
-      const bool mmas = !(p.probe & 2);
+      const bool mmas = !(kProbes && (p.probe & 2));
       for (int tile = cluster_id; tile < total_tiles; tile += num_clusters, ++tcount) {
         const uint32_t acc = tcount & acc_mask;
         const uint32_t acc_ph = (tcount >> acc_shift) & 1u;
@@ -494,23 +513,23 @@ conv_pair_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
             const uint32_t abase = smem_base + as * a_stage_bytes;
 #pragma unroll 1
             for (int kh = 0; kh < 3; ++kh) {
+              mbar_wait_addr_timed(full0 + 8u * s, ph, w_full);
+              tc_fence_after();
+              if (el) {
 #pragma unroll
-              for (int kw = 0; kw < 3; ++kw) {
-                mbar_wait_addr_timed(full0 + 8u * s, ph, w_full);
-                tc_fence_after();
-                // rows of the tile for this tap: halo rows kh .. kh+15 of the kw-shifted box (8 px = 1024 B per row)
-                const uint32_t a_lo = desc_lo | ((abase + static_cast<uint32_t>(kw) * kHaloBox + static_cast<uint32_t>(kh) * 1024u) >> 4);
-                const uint32_t b_lo = desc_lo | ((b_region + s * b_chunk) >> 4);
-                if (el) {
+                for (int kw = 0; kw < 3; ++kw) {
+                  // rows of the tile for this tap: halo rows kh .. kh+15 of the kw-shifted box (8 px = 1024 B per row)
+                  const uint32_t a_lo = desc_lo | ((abase + static_cast<uint32_t>(kw) * kHaloBox + static_cast<uint32_t>(kh) * 1024u) >> 4);
+                  const uint32_t b_lo = desc_lo | ((b_region + (s * 3u + static_cast<uint32_t>(kw)) * b_chunk) >> 4);
                   if (mmas) {
 #pragma unroll
                     for (int k = 0; k < KC / 16; ++k)
                       umma2_f16_lo(d_tmem, a_lo + 2u * k, b_lo + 2u * k, desc_hi, p.idesc, (c | kh | kw | k) != 0 ? 1u : 0u);
                   }
-                  umma2_commit_mc_addr(empty0 + 8u * s);
                 }
-                if (++s == S) { s = 0; ph ^= 1u; }
+                umma2_commit_mc_addr(empty0 + 8u * s);
               }
+              if (++s == S) { s = 0; ph ^= 1u; }
             }
             if (el) umma2_commit_mc_addr(a_empty0 + 8u * as);
             if (++as == static_cast<uint32_t>(p.a_stages)) { as = 0; aph ^= 1u; }
@@ -553,12 +572,9 @@ conv_pair_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
     const uint32_t row = quad * 32u + lane;
     const int ty = static_cast<int>(row) / p.tw;
     const int tx = static_cast<int>(row) - ty * p.tw;
-    const int et = static_cast<int>(threadIdx.x) - 64;  // 0..32*kPairEpiWarps-1
     const int nchunks = p.BN >> 4;
     const uint32_t acc_empty_remote = mapa_rank(acc_empty0, 0);
     uint32_t tcount = 0;
-    int bias_tile = -1;
-    uint32_t bias_buf = 0;
     long long e_wait = 0, e_proc = 0;
     const long long e_start = kTimers ? clock64() : 0;
     for (int tile = cluster_id; tile < total_tiles; tile += num_clusters, ++tcount) {
@@ -571,15 +587,7 @@ conv_pair_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
       const bool valid = (img < p.n_img) && (ty < p.th) && (ox < p.W_out) && (oy < p.H_out);
       const long long pix = (static_cast<long long>(img) * p.H_out + oy) * p.W_out + ox;
 
-      // bias of this N tile -> shared memory, only when the N tile changes (layers with a single N tile load it
-      // once per kernel); double-buffered by load count, one named barrier per load
-      if (n_tile != bias_tile) {
-        bias_tile = n_tile;
-        bias_buf ^= 1u;
-        if (et < p.BN) bias_s[bias_buf][et] = __ldg(p.bias + n0 + et);  // BN <= 256 <= epilogue threads
-        named_bar_sync(1, kPairEpiWarps * 32);
-      }
-      const float* bs = bias_s[bias_buf];
+      const float* bs = bias_all + n0;
 
       const long long te0 = kTimers ? clock64() : 0;
       mbar_wait_addr(acc_full0 + 8u * acc, acc_ph);
@@ -591,9 +599,9 @@ conv_pair_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
       __half* const orow = reinterpret_cast<__half*>(p.out) + pix * p.out_pix_stride + p.out_c_off + n0;
       const __half* const rrow = p.res != nullptr ? p.res + pix * p.res_pix_stride + p.res_c_off + n0 : nullptr;
       auto process_fast = [&](const uint32_t (&vv)[16], int jj) {
-        if (!valid || (p.probe & 4)) return;
+        if (!valid || (kProbes && p.probe & 4)) return;
         uint4 r0 = make_uint4(0, 0, 0, 0), r1 = make_uint4(0, 0, 0, 0);
-        if (rrow != nullptr && !(p.probe & 8)) ldg256(rrow + jj * 16, r0, r1);
+        if (rrow != nullptr && !(kProbes && (p.probe & 8))) ldg256(rrow + jj * 16, r0, r1);
         float f[16];
         const float4* b4 = reinterpret_cast<const float4*>(bs + jj * 16);
 #pragma unroll
@@ -604,7 +612,7 @@ conv_pair_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
           f[4 * q + 2] = __uint_as_float(vv[4 * q + 2]) + bb.z;
           f[4 * q + 3] = __uint_as_float(vv[4 * q + 3]) + bb.w;
         }
-        if (p.act && !(p.probe & 16)) {
+        if (p.act && !(kProbes && p.probe & 16)) {
 #pragma unroll
           for (int e = 0; e < 16; e += 4) silu4(f[e], f[e + 1], f[e + 2], f[e + 3]);
         }
@@ -629,7 +637,7 @@ conv_pair_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
           q0[e] = __floats2half2_rn(f[2 * e], f[2 * e + 1]);
           q1[e] = __floats2half2_rn(f[8 + 2 * e], f[8 + 2 * e + 1]);
         }
-        if (p.probe & 8) {
+        if (kProbes && p.probe & 8) {
           if (o0.x == 0x7fff7fffu && o1.w == 0x7fff7fffu) stg256(orow + jj * 16, o0, o1);  // keeps the math alive, never true
         } else {
           stg256(orow + jj * 16, o0, o1);
@@ -638,7 +646,7 @@ conv_pair_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
       // ---- general path: fp32 outputs, partial chunks, unaligned views
       auto process = [&](const uint32_t (&vv)[16], int jj) {
         const int col0 = n0 + jj * 16;
-        if (!(valid && col0 < p.Cout) || (p.probe & 4)) return;
+        if (!(valid && col0 < p.Cout) || (kProbes && p.probe & 4)) return;
         uint4 r0 = make_uint4(0, 0, 0, 0), r1 = make_uint4(0, 0, 0, 0);
         if (p.res != nullptr) {
           const __half* rp = p.res + pix * p.res_pix_stride + p.res_c_off + col0;
@@ -708,6 +716,32 @@ conv_pair_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
       int j = static_cast<int>(part);
       if (j < nchunks) tmem_ld16(taddr + static_cast<uint32_t>(j * 16), va);
       if (p.fast) {
+#ifdef MDB_EPI_EARLY_RELEASE
+        // hand the accumulator back as soon as the warp's LAST load from it has landed, before that chunk's math
+        auto give_back = [&]() {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (leader) mbar_arrive(&acc_empty_bar[acc]);
+            else mbar_arrive_cluster_addr(acc_empty_remote + 8u * acc);
+          }
+        };
+        if (j >= nchunks) give_back();
+        while (j < nchunks) {
+          tmem_ld_wait();
+          if (j + kParts < nchunks) tmem_ld16(taddr + static_cast<uint32_t>((j + kParts) * 16), vb);
+          else give_back();
+          process_fast(va, j);
+          j += kParts;
+          if (j >= nchunks) break;
+          tmem_ld_wait();
+          if (j + kParts < nchunks) tmem_ld16(taddr + static_cast<uint32_t>((j + kParts) * 16), va);
+          else give_back();
+          process_fast(vb, j);
+          j += kParts;
+        }
+        continue;
+#else
         while (j < nchunks) {
           tmem_ld_wait();
           if (j + kParts < nchunks) tmem_ld16(taddr + static_cast<uint32_t>((j + kParts) * 16), vb);
@@ -719,6 +753,7 @@ conv_pair_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
           process_fast(vb, j);
           j += kParts;
         }
+#endif
       } else {
         while (j < nchunks) {
           tmem_ld_wait();

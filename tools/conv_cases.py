@@ -28,6 +28,8 @@ CASES = {
     'b64_c1x1_160_80': (64, 192, 320, 160, 80, 1, 1, 0, False),
     'b64_c3x3_80': (64, 192, 320, 80, 80, 3, 1, 1, True),
     'b64_c1x1_320': (64, 48, 80, 320, 320, 1, 1, 0, False),
+    'b64_c3x3_160': (64, 96, 160, 160, 160, 3, 1, 1, True),
+    'b64_c3x3_320': (64, 48, 80, 320, 320, 3, 1, 1, True),
 }
 names = sys.argv[1].split(',') if len(sys.argv) > 1 else list(CASES)
 iters = int(sys.argv[2]) if len(sys.argv) > 2 else 10
