@@ -59,7 +59,7 @@ def _conv_dram_traffic():
         for ln in open(path):
             if ln.startswith('conv_pair_kernel,'):
                 _, n, rd, wr = ln.strip().split(',')
-                best = (float(rd) + float(wr)) * 1e9 * 163.0 / float(n), os.path.basename(path)  # 163 launches = 1 pass
+                best = (float(rd) + float(wr)) * 1e9, os.path.basename(path), int(n)  # the file holds exactly one pass
     return best
 
 
@@ -257,7 +257,7 @@ def main():
                          'frac': conv_tflops / peaks['tflops'],
                          'traffic': (_conv_dram_traffic() or [None])[0] if B == 64 else None,
                          'traffic_source': (_conv_dram_traffic() or [None, None])[1], 'peak_source': peaks['source'],
-                         'kernel': 'conv_pair_kernel<64> (163 launches/step; tcgen05.mma.cta_group::2) + 3 upsample + 1 SPPF pool launches',
+                         'kernel': 'conv_pair_kernel<64> ({} launches/step; tcgen05.mma.cta_group::2) + 3 upsample + 1 SPPF pool launches'.format(int(launches_res) // max(1, args.steps) - 7),
                          'flops_per_step': B * GFLOP_PER_IMAGE * 1e9, 'ms_per_step': ms_net / args.steps},
             'stage_ms_per_step': {'preprocess_K1': ms_pre / args.steps, 'network_K2_K4': ms_net / args.steps,
                                   'decode_nms_K5_K8': ms_post / args.steps},

@@ -38,9 +38,6 @@ constexpr bool kProbes = true;
 #else
 constexpr bool kProbes = false;
 #endif
-#ifndef MDB_EPI_SLEEP
-#define MDB_EPI_SLEEP 0
-#endif
 #ifndef MDB_EPI_WARPS
 #define MDB_EPI_WARPS 16
 #endif
@@ -716,32 +713,6 @@ conv_pair_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
       int j = static_cast<int>(part);
       if (j < nchunks) tmem_ld16(taddr + static_cast<uint32_t>(j * 16), va);
       if (p.fast) {
-#ifdef MDB_EPI_EARLY_RELEASE
-        // hand the accumulator back as soon as the warp's LAST load from it has landed, before that chunk's math
-        auto give_back = [&]() {
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) {
-            if (leader) mbar_arrive(&acc_empty_bar[acc]);
-            else mbar_arrive_cluster_addr(acc_empty_remote + 8u * acc);
-          }
-        };
-        if (j >= nchunks) give_back();
-        while (j < nchunks) {
-          tmem_ld_wait();
-          if (j + kParts < nchunks) tmem_ld16(taddr + static_cast<uint32_t>((j + kParts) * 16), vb);
-          else give_back();
-          process_fast(va, j);
-          j += kParts;
-          if (j >= nchunks) break;
-          tmem_ld_wait();
-          if (j + kParts < nchunks) tmem_ld16(taddr + static_cast<uint32_t>((j + kParts) * 16), va);
-          else give_back();
-          process_fast(vb, j);
-          j += kParts;
-        }
-        continue;
-#else
         while (j < nchunks) {
           tmem_ld_wait();
           if (j + kParts < nchunks) tmem_ld16(taddr + static_cast<uint32_t>((j + kParts) * 16), vb);
@@ -753,7 +724,6 @@ conv_pair_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
           process_fast(vb, j);
           j += kParts;
         }
-#endif
       } else {
         while (j < nchunks) {
           tmem_ld_wait();

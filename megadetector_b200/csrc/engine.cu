@@ -188,6 +188,7 @@ int fail(mdb_engine* e, int code, const std::string& msg) {
 struct Builder {
   Plan& P;
   const mdb_arch& A;
+  const std::map<std::string, ConvWeights>* weights = nullptr;  // to see which fused C3 entry convs exist
   explicit Builder(Plan& p, const mdb_arch& a) : P(p), A(a) {}
   int newbuf(int H, int W, int C, bool fp32 = false) {
     VBuf b; b.H = H; b.W = W; b.C = C; b.fp32 = fp32;
@@ -225,10 +226,20 @@ struct Builder {
     const int H = ib.H, W = ib.W;
     const std::string pre = "model." + std::to_string(idx);
     const int cat = newbuf(H, W, 2 * h);
-    int cur = (n == 0) ? -1 : newbuf(H, W, h);
-    VView a = (n == 0) ? slice(cat, 0, h) : whole(cur);
-    conv(pre + ".cv1.conv", in, a, h, 1, 1, 0);
-    conv(pre + ".cv2.conv", in, slice(cat, h, h), h, 1, 1, 0);
+    VView a;
+    if (weights != nullptr && weights->count(pre + ".cv12.conv")) {
+      // cv1 and cv2 read the same tensor: ONE 1x1 conv with the two weight sets stacked along C_out writes
+      // [cv1(x) | cv2(x)] straight into the concat buffer (bit-identical per channel; the input is read once instead
+      // of twice).  The bottleneck chain then starts from the buffer's first half, and its last member overwrites
+      // that half with m(cv1(x)) -- element-wise in place for n == 1 (the residual is read by the thread that stores).
+      a = slice(cat, 0, h);
+      conv(pre + ".cv12.conv", in, whole(cat), 2 * h, 1, 1, 0);
+    } else {
+      const int cur = (n == 0) ? -1 : newbuf(H, W, h);
+      a = (n == 0) ? slice(cat, 0, h) : whole(cur);
+      conv(pre + ".cv1.conv", in, a, h, 1, 1, 0);
+      conv(pre + ".cv2.conv", in, slice(cat, h, h), h, 1, 1, 0);
+    }
     const int tmp = n > 0 ? newbuf(H, W, h) : -1;
     for (int j = 0; j < n; ++j) {
       const std::string m = pre + ".m." + std::to_string(j);
@@ -241,8 +252,9 @@ struct Builder {
   }
 };
 
-void build_graph(Plan& P, const mdb_arch& A) {
+void build_graph(Plan& P, const mdb_arch& A, const std::map<std::string, ConvWeights>* weights) {
   Builder B(P, A);
+  B.weights = weights;
   const int* c = A.ch;
   const int* nb = A.n_backbone;
   const int nh = A.n_head;
@@ -376,7 +388,7 @@ Plan* get_plan(mdb_engine* e, int H, int W) {
   MDB_REQUIRE(H % 64 == 0 && W % 64 == 0 && H >= 64 && W >= 64, "letterboxed shape must be a multiple of 64");
   std::unique_ptr<Plan> P(new Plan());
   P->H = H; P->W = W; P->nb = e->cfg.max_batch;
-  build_graph(*P, e->cfg.arch);
+  build_graph(*P, e->cfg.arch, &e->weights);
   assign_offsets(*P, true);
   MDB_CUDA(cudaMalloc(&P->arena, P->arena_bytes));
   MDB_CUDA(cudaMemsetAsync(P->arena, 0, P->arena_bytes, e->st_compute));
@@ -935,6 +947,41 @@ int mdb_load_weights(mdb_engine* e, const mdb_tensor_desc* tensors, int32_t n) {
       MDB_CUDA(cudaMemcpy(cw.w, packed.data(), packed.size() * sizeof(__half), cudaMemcpyHostToDevice));
       MDB_CUDA(cudaMemcpy(cw.b, bias.data(), bias.size() * sizeof(float), cudaMemcpyHostToDevice));
       e->weights[base] = cw;
+    }
+    // C3 entry convs: cv1 and cv2 share their input -> one stacked weight set "<block>.cv12.conv" (MDB_FUSE_C3=0 keeps
+    // them separate).  Needs cv1's rows unpadded so that cv2's channels follow directly.
+    {
+      const char* ef = getenv("MDB_FUSE_C3");
+      const bool fuse = !(ef && ef[0] == '0');
+      std::vector<std::string> bases;
+      for (auto& kv : e->weights) {
+        const std::string suffix = ".cv1.conv";
+        const std::string& nm = kv.first;
+        if (nm.size() > suffix.size() && nm.compare(nm.size() - suffix.size(), suffix.size(), suffix) == 0 &&
+            nm.find(".m.") == std::string::npos)
+          bases.push_back(nm.substr(0, nm.size() - suffix.size()));
+      }
+      for (const std::string& b : bases) {
+        auto old = e->weights.find(b + ".cv12.conv");
+        if (old != e->weights.end()) { cudaFree(old->second.w); cudaFree(old->second.b); e->weights.erase(old); }
+        auto i2 = e->weights.find(b + ".cv2.conv");
+        if (!fuse || i2 == e->weights.end()) continue;
+        const ConvWeights& w1 = e->weights[b + ".cv1.conv"];
+        const ConvWeights& w2 = i2->second;
+        if (w1.k != 1 || w2.k != 1 || w1.cin != w2.cin || w1.cin_pad != w2.cin_pad || w1.cout != w1.cout_pad ||
+            w1.cout_pad + w2.cout_pad > 1280)
+          continue;
+        ConvWeights cw;
+        cw.cout = w1.cout + w2.cout; cw.cout_pad = w1.cout_pad + w2.cout_pad; cw.cin = w1.cin; cw.cin_pad = w1.cin_pad; cw.k = 1;
+        const size_t row = static_cast<size_t>(cw.cin_pad) * sizeof(__half);
+        MDB_CUDA(cudaMalloc(&cw.w, row * cw.cout_pad + 256));
+        MDB_CUDA(cudaMalloc(&cw.b, sizeof(float) * cw.cout_pad));
+        MDB_CUDA(cudaMemcpy(cw.w, w1.w, row * w1.cout_pad, cudaMemcpyDeviceToDevice));
+        MDB_CUDA(cudaMemcpy(reinterpret_cast<char*>(cw.w) + row * w1.cout_pad, w2.w, row * w2.cout_pad, cudaMemcpyDeviceToDevice));
+        MDB_CUDA(cudaMemcpy(cw.b, w1.b, sizeof(float) * w1.cout_pad, cudaMemcpyDeviceToDevice));
+        MDB_CUDA(cudaMemcpy(cw.b + w1.cout_pad, w2.b, sizeof(float) * w2.cout_pad, cudaMemcpyDeviceToDevice));
+        e->weights[b + ".cv12.conv"] = cw;
+      }
     }
     e->plans.clear();  // plans hold weight pointers
     e->last_plan = nullptr;

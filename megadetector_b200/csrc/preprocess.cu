@@ -98,6 +98,11 @@ __global__ void __launch_bounds__(kPreThreads) letterbox_s2d_kernel(const PreIma
                                                                    int out_w, __half* __restrict__ dst,
                                                                    int smem_row_bytes, int smem_rows) {
   extern __shared__ __align__(16) uint8_t s_dyn[];
+  // u8 -> half(v / 255) table in shared memory: the lanes of a warp look up DIFFERENT entries, which the constant cache
+  // serialises (up to 32 replays per lookup, 12 lookups per s2d pixel); shared memory serves them with few conflicts
+  __shared__ __half s_lut[256];
+  if (threadIdx.x < 256) s_lut[threadIdx.x] = c_norm_lut[threadIdx.x];
+  if (!STAGED) __syncthreads();
   // [kTileH2][kHaloW2] entries of 16 halves (12 used): the letterboxed, normalised s2d tile with column halo
   uint4* s_tile = reinterpret_cast<uint4*>(s_dyn);
   uint8_t* s_src = s_dyn + static_cast<size_t>(kTileH2) * kHaloW2 * 32;
@@ -187,7 +192,7 @@ __global__ void __launch_bounds__(kPreThreads) letterbox_s2d_kernel(const PreIma
             }
           }
 #pragma unroll
-          for (int c = 0; c < 3; ++c) px[(py * 2 + pxx) * 3 + c] = c_norm_lut[v[c] & 255];
+          for (int c = 0; c < 3; ++c) px[(py * 2 + pxx) * 3 + c] = s_lut[v[c] & 255];
         }
       }
     }

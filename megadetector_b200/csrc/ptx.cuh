@@ -66,17 +66,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (clock64() - t0 > 4000000000LL) { asm volatile("trap;"); }
   }
 }
-// The same for warps that are NOT on the critical path (the epilogue waiting for an accumulator): back off between
-// polls so that the spinning warps do not take issue slots from the single-thread TMA / MMA roles that share
-// their scheduler.  The watchdog counts polls instead of reading the clock.
-__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity, uint32_t ns) {
-  if (mbar_try_wait(bar, parity)) return;
-  uint32_t polls = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if (ns) __nanosleep(ns);
-    if (++polls > (1u << 26)) { asm volatile("trap;"); }
-  }
-}
 
 // ----------------------------------------------------------------------------------------------
 // TMA

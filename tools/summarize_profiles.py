@@ -67,15 +67,20 @@ def traffic():
         if r['Metric Name'].startswith('dram__bytes'):
             v *= {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}.get(unit, 1)
         d[r['Metric Name']] = v
+    # keep exactly ONE forward pass: from the first letterbox launch to the first NMS launch
+    ordered = [per[k] for k in sorted(per, key=lambda x: int(x))]
+    first = next((i for i, d in enumerate(ordered) if d['name'] == 'letterbox_s2d_kernel'), 0)
+    last = next((i for i, d in enumerate(ordered) if i >= first and d['name'] == 'nms_image_kernel'), len(ordered) - 1)
+    ordered = ordered[first:last + 1]
     agg = {}
-    for d in per.values():
+    for d in ordered:
         a = agg.setdefault(d['name'], [0, 0.0, 0.0])
         a[0] += 1
         a[1] += d.get('dram__bytes_read.sum', 0.0)
         a[2] += d.get('dram__bytes_write.sum', 0.0)
     with open(os.path.join(OUT, TAG + '_dram_traffic_step_bs64.csv'), 'w') as f:
-        f.write('# ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum -k <our kernels> -c 171  python tools/profile_layers.py 64\n')
-        f.write('# = the first (eager) pass over one batch of 64 images: K1, 163 convs, 3 upsamples, SPPF pools, decode, NMS\n')
+        f.write('# ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum -k <our kernels>  python tools/profile_layers.py 64 (MDB_NO_GRAPHS=1)\n')
+        f.write('# = ONE eager forward pass over a batch of 64 images: K1, every conv launch, upsamples, SPPF pools, decode, NMS\n')
         f.write('kernel,launches,dram_read_GB,dram_write_GB\n')
         for k, (n, rd, wr) in sorted(agg.items(), key=lambda kv: -(kv[1][1] + kv[1][2])):
             f.write('{},{},{:.3f},{:.3f}\n'.format(k, n, rd / 1e9, wr / 1e9))
