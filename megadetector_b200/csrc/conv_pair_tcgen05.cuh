@@ -710,7 +710,11 @@ conv_pair_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
       };
       // TMEM loads run one chunk ahead of the math (two register buffers, statically indexed)
       uint32_t va[16], vb[16];
-      int j = static_cast<int>(part);
+      // When the chunk count is not a multiple of the parts (10 chunks at BN = 160, 5 at BN = 80), some warps of a
+      // quadrant get one chunk more than the others.  Rotating the assignment from tile to tile by that remainder
+      // evens the work out over consecutive tiles; the accumulator ring (2-4 stages) lets the early warps run ahead.
+      static_assert(kParts == 4, "the rotation below assumes four parts");
+      int j = static_cast<int>((part + tcount * static_cast<uint32_t>(nchunks & 3)) & 3u);
       if (j < nchunks) tmem_ld16(taddr + static_cast<uint32_t>(j * 16), va);
       if (p.fast) {
         while (j < nchunks) {
