@@ -29,6 +29,13 @@ CASES = [
     ('detect_c320_fp32', 2, 24, 40, 320, 24, 1, 1, 0, 0, False, True),
     ('3x3_c320_real', 4, 48, 80, 320, 320, 3, 1, 1, 1, True, False),
     ('1x1_c1280_bn256', 2, 12, 20, 1280, 1280, 1, 1, 0, 1, False, False),
+    # several tiles per CTA pair (persistent loop, accumulator ring phases, rotating epilogue chunk assignment)
+    ('1x1_c80_many_tiles', 4, 96, 160, 80, 80, 1, 1, 0, 1, False, False),
+    ('1x1_c160_many_tiles', 4, 96, 160, 160, 160, 1, 1, 0, 1, True, False),
+    ('1x1_c320_two_ntiles', 4, 48, 80, 320, 320, 1, 1, 0, 1, False, False),
+    # row-halo main loop from 80 channels (two chunks per tap, the second mostly zero-filled), filter-row weight stages
+    ('3x3_c80_halo_many', 4, 96, 160, 80, 80, 3, 1, 1, 1, True, False),
+    ('3x3_c160_halo_many', 4, 48, 80, 160, 160, 3, 1, 1, 1, True, False),
 ]
 
 

@@ -8,9 +8,10 @@ from megadetector_b200 import checkpoint
 from megadetector_b200.synth import synth_image
 
 torch.set_num_threads(32)
-weights, arch = checkpoint.load_model('synthetic://yolov5x6?seed=0')
+weights, _arch_dict = checkpoint.load_model('synthetic://yolov5x6?seed=0')
 w = {k: (v if torch.is_tensor(v) else torch.from_numpy(v)).float() for k, v in weights.items()}
 img = synth_image(3)
+arch = oy.Arch()
 lb, _, _ = olb.letterbox(img, 1280, 64, True, True)
 x = torch.from_numpy(olb.to_model_input(lb))[None]
 
