@@ -19,6 +19,13 @@ from helpers import assert_anchors_equal_modulo_ties, assert_dets_equal_modulo_t
 
 pytestmark = pytest.mark.gpu
 
+# The calibrated random-init network is chaotic in the last bits: the SAME fp16 contract evaluated by PyTorch with fp32 and
+# with fp64 accumulation differs by 0.072 (max) / 1.1e-4 (mean) in the scores of synth_image(1) -- as much as either differs
+# from the fp32 oracle (profiles/r01_conv_ab_experiments.txt par. 9).  End-to-end score errors are therefore compared with
+# those of two independent 10-bit-operand evaluations (TF32 cuDNN, and a PyTorch model of the engine's contract), with a
+# factor of 3; the tight per-layer check (3e-3 relative) is tests/test_gpu_conv.py.
+E2E_FACTOR = 3.0
+
 CONF_TOL = 5e-3   # md_tests.py:96  max abs conf difference across environments
 COORD_TOL = 2e-3  # md_tests.py:100 is 1e-3; one rounded pixel of a 1080p image is 9.3e-4 -> allow two
 
@@ -80,6 +87,63 @@ def _incumbent_tf32_error(ora, raw, groups):
     return {'max_score_err': score, 'max_box_err_px': box}
 
 
+def _fp16_contract_model(ora, raw, groups):
+    """
+    The engine's arithmetic contract evaluated by stock PyTorch: every convolution sees fp16-rounded activations and
+    weights, accumulates in fp32 (cuDNN fp32, TF32 off), adds the fp32 bias, applies SiLU in fp32 and stores its result
+    rounded to fp16 (the residual add, as in the oracle graph, on the stored values).  Returns {image index: pred}.
+    What is left between this model and the engine is accumulation order (which occasionally flips an fp16 rounding)
+    and the 1e-6 relative error of ex2.approx / rcp.approx.
+    """
+    import torch
+    import torch.nn.functional as F
+    from oracle import letterbox as olb
+    from oracle import yolov5 as oy
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    dev = torch.device('cuda')
+    wd = {k: v.to(dev) for k, v in ora.w.items()}
+
+    def h(t):
+        return t.half().float()
+
+    def conv_model(x, w, name, s=1, p=0, act=True, trace=None):
+        y = F.conv2d(h(x), h(w[name + '.weight']), w[name + '.bias'], stride=s, padding=p)
+        if act:
+            y = y * torch.sigmoid(y)
+        # the Detect heads are the only convs without activation: the engine keeps their output in fp32
+        return h(y) if act else y
+
+    def c3_model(x, w, i, n, shortcut, trace):
+        # as oracle.yolov5._c3, but the bottleneck's residual is added BEFORE the single rounding to fp16 (the engine
+        # fuses the add into the 3x3 conv's epilogue)
+        pre = 'model.%d' % i
+        a = conv_model(x, w, pre + '.cv1.conv')
+        for j in range(n):
+            b = conv_model(a, w, '%s.m.%d.cv1.conv' % (pre, j))
+            nm = '%s.m.%d.cv2.conv' % (pre, j)
+            y = F.conv2d(h(b), h(w[nm + '.weight']), w[nm + '.bias'], stride=1, padding=1)
+            y = y * torch.sigmoid(y)
+            a = h(a + y) if shortcut else h(y)
+        c = conv_model(x, w, pre + '.cv2.conv')
+        return conv_model(torch.cat((a, c), 1), w, pre + '.cv3.conv')
+
+    out = {}
+    orig, orig_c3 = oy._conv, oy._c3
+    oy._conv = conv_model
+    oy._c3 = c3_model
+    try:
+        for shape, idxs in groups.items():
+            x = torch.from_numpy(np.stack([olb.to_model_input(raw[i]['letterboxed']) for i in idxs])).to(dev)
+            pred = oy.forward(x, wd, ora.arch).cpu().numpy()
+            for j, i in enumerate(idxs):
+                out[i] = pred[j]
+    finally:
+        oy._conv = orig
+        oy._c3 = orig_c3
+    return out
+
+
 def _run_case(model_spec, oracle_arch, sizes, n_imgs, max_batch):
     from megadetector_b200 import _capi
     from megadetector_b200.detector import B200Detector
@@ -100,6 +164,10 @@ def _run_case(model_spec, oracle_arch, sizes, n_imgs, max_batch):
     for i, im in enumerate(imgs):
         groups.setdefault(raw[i]['letterboxed'].shape, []).append(i)
     worst_pred = 0.0
+    model_pred = _fp16_contract_model(ora, raw, groups)
+    worst_model, mean_model, mean_fp32 = 0.0, [], []
+    model_vs_fp32_max = max(float(np.abs(model_pred[i] - raw[i]['pred'])[:, 4:].max()) for i in model_pred)
+    model_vs_fp32_mean = float(np.mean([np.abs(model_pred[i] - raw[i]['pred'])[:, 4:].mean() for i in model_pred]))
     for shape, idxs in groups.items():
         sub = [imgs[i] for i in idxs]
         d2, c2, a2, st = det.engine.infer_batch(sub, 1e-5)
@@ -120,14 +188,35 @@ def _run_case(model_spec, oracle_arch, sizes, n_imgs, max_batch):
             # conv-stack error vs the fp32 oracle
             err = np.abs(pred[j] - raw[i]['pred'])
             worst_pred = max(worst_pred, float(err[:, 4:].max()))
+            mean_fp32.append(float(err[:, 4:].mean()))
+            # ... and vs the engine's own arithmetic contract evaluated by PyTorch (fp16 operands and storage)
+            merr = np.abs(pred[j] - model_pred[i])
+            worst_model = max(worst_model, float(merr[:, 4:].max()))
+            mean_model.append(float(merr[:, 4:].mean()))
+            report.setdefault('box_err_vs_fp16_model_px', []).append(float(merr[:, :4].max()))
             report.setdefault('box_err_px', []).append(float(err[:, :4].max()))
             report.setdefault('cands', []).append(int((pred[j][:, 4] > 1e-5).sum()))
     report['max_score_err'] = worst_pred
+    report['mean_score_err'] = float(np.mean(mean_fp32))
+    report['max_score_err_vs_fp16_model'] = worst_model
+    report['mean_score_err_vs_fp16_model'] = float(np.mean(mean_model))
+    report['fp16_model_vs_fp32'] = {'max_score_err': model_vs_fp32_max, 'mean_score_err': model_vs_fp32_mean}
     report['incumbent_tf32'] = _incumbent_tf32_error(ora, raw, groups)
     stats = compare_records(ref, got)
     report.update(stats)
     det.close()
     return report, ref, got
+
+
+def _check_against_10bit_evaluations(report):
+    """The engine's distance to the fp32 oracle, and to the PyTorch model of its own contract, must be of the size that
+    separates other 10-bit-operand evaluations from the oracle (max and mean over all scores)."""
+    peers_max = max(report['incumbent_tf32']['max_score_err'], report['fp16_model_vs_fp32']['max_score_err'])
+    peers_mean = report['fp16_model_vs_fp32']['mean_score_err']
+    assert report['max_score_err'] <= max(0.05, E2E_FACTOR * peers_max), report
+    assert report['mean_score_err'] <= max(2e-4, E2E_FACTOR * peers_mean), report
+    assert report['max_score_err_vs_fp16_model'] <= max(0.05, E2E_FACTOR * peers_max), report
+    assert report['mean_score_err_vs_fp16_model'] <= max(2e-4, E2E_FACTOR * peers_mean), report
 
 
 def test_tiny_model_mixed_shapes_end_to_end():
@@ -136,6 +225,7 @@ def test_tiny_model_mixed_shapes_end_to_end():
     print('\n[tiny e2e]', report)
     # conv-stack precision: same class as the reference's own GPU default (TF32 cuDNN), see DESIGN.md par. 4
     assert report['max_score_err'] <= max(0.05, 3.0 * report['incumbent_tf32']['max_score_err']), report
+    _check_against_10bit_evaluations(report)
 
 
 def test_yolov5x6_benchmark_shape_end_to_end():
@@ -143,6 +233,7 @@ def test_yolov5x6_benchmark_shape_end_to_end():
     report, ref, got = _run_case('synthetic://yolov5x6?seed=0', oy.Arch(), [(1080, 1920)], 2, 2)
     print('\n[yolov5x6 e2e]', report)
     assert report['max_score_err'] <= max(0.05, 3.0 * report['incumbent_tf32']['max_score_err']), report
+    _check_against_10bit_evaluations(report)
 
 
 def test_failure_isolation_and_dict_inputs():
