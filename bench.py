@@ -126,8 +126,10 @@ def run_reference(args, rank, world):
         'impl': 'reference', 'metric': 'images/sec (MDv5a 1280px bs=64)', 'value': v, 'unit': 'images/s', 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1000.0 * dt / max(1, args.steps), 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': 'MDv5a-shape YOLOv5x6 (calibrated random init), 1920x1080 -> 768x1280, bs=1 on CPU',
-                   'sample_images_per_step': per_step},
+        # the same workload as the engine's arm; each step is a bounded sample of it (the reference forces bs=1 on a CPU)
+        'config': {'workload': 'MDv5a-shape YOLOv5x6 (calibrated random init, no checkpoint offline), bs={} per GPU, '
+                               '1920x1080 RGB u8 -> letterbox 768x1280, conf_thres 1e-5, image-sharded'.format(args.batch),
+                   'sample_images_per_step': per_step, 'reference_batch_size': 1},
         'cpu_baseline': {'value': v, 'unit': 'images/s', 'cores': cores, 'kind': 'port',
                          'sample': '{} steps x {} synthetic 1920x1080 images, full path (letterbox, fp32 forward, nms, formatting), '
                                    'torch {} threads'.format(args.steps, per_step, torch.get_num_threads())},
