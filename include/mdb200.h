@@ -129,6 +129,16 @@ MDB_API int mdb_letterbox_geometry(const mdb_config* cfg, int32_t h, int32_t w, 
 #define MDB_FETCH_LAYER 3      /* fp16 NHWC output of conv #index (order of oracle.yolov5.conv_specs) */
 MDB_API int mdb_debug_fetch(mdb_engine* e, int32_t what, int32_t index, void* host_dst, size_t bytes, int64_t* shape4);
 
+/* Parity harness: while a trace is set, the forward pass runs eagerly and keeps dense copies of the input (which=0),
+ * output (1) and residual (2) tensors of the selected steps, taken right before / after each step runs (so in-place steps
+ * and the liveness-packed arena do not matter).  names: NULL or "" = off, "*" = every step, else a comma-separated list of
+ * step names (conv names of oracle.yolov5.conv_specs; "model.N.cv12.conv" for the fused C3 entry pair; "upsample.13|17|21";
+ * "sppf_pool.11").  This is what lets tests compare every one of the 163 convolutions of pytorch_detector.py:1313 with a
+ * PyTorch evaluation of the same layer on the engine's own input.  shape5 = N, H, W, C, is_fp32. */
+MDB_API int mdb_debug_set_trace(mdb_engine* e, const char* names);
+MDB_API int mdb_debug_trace_names(mdb_engine* e, char* names_out, size_t cap, int32_t* n_steps);
+MDB_API int mdb_debug_fetch_trace(mdb_engine* e, const char* name, int32_t which, void* host_dst, size_t bytes, int64_t* shape5);
+
 /* device timing of the last infer call, milliseconds: [0]=h2d+preprocess [1]=network [2]=decode+nms [3]=total */
 MDB_API int mdb_last_timing(mdb_engine* e, float* ms4);
 /* Device-resident throughput measurement (bench.py `value`): re-runs the batch that the last infer call left
@@ -157,6 +167,15 @@ MDB_API int mdb_op_letterbox(mdb_engine* e, const uint8_t* rgb_hwc, int32_t h, i
 MDB_API int mdb_op_conv2d(mdb_engine* e, const void* x_fp16, int32_t n, int32_t h, int32_t w, int32_t cin, const float* wgt,
                   const float* bias, int32_t cout, int32_t k, int32_t s, int32_t pad, int32_t act,
                   const void* residual_fp16, int32_t out_fp32, void* y, int32_t iters, float* ms);
+/* K3: nn.Upsample(scale_factor=2, mode="nearest") (yolov5x6.yaml idx 13/17/21).  src fp16 NHWC [n][h][w][c] -> dst [n][2h][2w][c] */
+MDB_API int mdb_op_upsample2x(mdb_engine* e, const void* src_fp16, int32_t n, int32_t h, int32_t w, int32_t c, void* dst_fp16);
+/* K4: the three chained MaxPool2d(5,1,2) of SPPF (yolov5 models/common.py) in one pass.  s1 fp16 NHWC [n][h][w][c] ->
+ * cat [n][h][w][4c] = [s1 | p1 | p2 | p3] */
+MDB_API int mdb_op_sppf_pool(mdb_engine* e, const void* s1_fp16, int32_t n, int32_t h, int32_t w, int32_t c, void* cat_fp16);
+/* K5: Detect inference decode (yolov5 models/yolo.py Detect.forward; oracle/yolov5.py::decode_level) of the four raw head
+ * outputs raw4[l]: fp32 NHWC [n][ny4[l]][nx4[l]][round_up(3*(5+nc), 4)] with the anchors of the engine's config ->
+ * pred fp32 [n][sum_l 3*ny*nx][5+nc] */
+MDB_API int mdb_op_decode(mdb_engine* e, const float* const* raw4, const int32_t* ny4, const int32_t* nx4, int32_t n, float* pred);
 /* K5-K8: threshold + per-class NMS + top-k on a prediction tensor fp32 [n][anchors][5+nc] (the reference's
  * nms(), pytorch_detector.py:502-610).  det_out boxes stay in letterbox pixels (no rescale). */
 MDB_API int mdb_op_nms(mdb_engine* e, const float* pred, int32_t n, int32_t anchors, int32_t nc, float conf_thres,

@@ -21,6 +21,7 @@ EXPORTS = [
     'mdb_create', 'mdb_load_weights', 'mdb_destroy', 'mdb_last_error', 'mdb_infer_batch', 'mdb_batch_begin', 'mdb_batch_next', 'mdb_infer_preprocessed',
     'mdb_letterbox_geometry', 'mdb_set_image_size', 'mdb_debug_fetch', 'mdb_last_timing', 'mdb_bench_resident', 'mdb_profile_steps', 'mdb_set_pipeline_split', 'mdb_launch_count', 'mdb_op_letterbox',
     'mdb_op_conv2d', 'mdb_op_nms', 'mdb_alloc_pinned', 'mdb_free_pinned', 'mdb_version',
+    'mdb_debug_set_trace', 'mdb_debug_trace_names', 'mdb_debug_fetch_trace', 'mdb_op_upsample2x', 'mdb_op_sppf_pool', 'mdb_op_decode',
 ]
 
 
@@ -47,13 +48,17 @@ def load_library():
     global _lib
     if _lib is not None:
         return _lib
-    try:  # rebuild when the sources changed and nvcc is here (a no-op stamp check otherwise)
-        if not (_VARIANT and os.path.exists(LIB_PATH)):  # an experiment variant is frozen once built (A/B against the tree)
-            from .build import build as _build
-            _build()
-    except Exception as e:  # an up-to-date prebuilt .so is fine without nvcc
-        if not os.path.exists(LIB_PATH):
-            raise RuntimeError('libmdb200.so is missing and could not be built: {}'.format(e))
+    if not (_VARIANT and os.path.exists(LIB_PATH)):  # an experiment variant is frozen once built (A/B against the tree)
+        from . import build as _b
+        try:  # rebuild when the sources changed and nvcc is here (a no-op stamp check otherwise)
+            _b.build()
+        except Exception as e:
+            # Never load a library that is older than the sources it is bound against: without nvcc a prebuilt .so
+            # whose stamp matches is fine, anything else is an error.
+            stamp_file = os.path.join(_b.OBJ_DIR, 'stamp')
+            ok = os.path.exists(LIB_PATH) and os.path.exists(stamp_file) and open(stamp_file).read() == _b._stamp()
+            if not ok:
+                raise RuntimeError('libmdb200.so is missing or stale and could not be rebuilt: {}'.format(e))
     if not os.path.exists(LIB_PATH):
         raise RuntimeError(
             'libmdb200.so is missing ({}): build it with `python -m megadetector_b200.build`. '
@@ -102,6 +107,18 @@ def load_library():
     lib.mdb_op_conv2d.restype = C.c_int
     lib.mdb_op_nms.argtypes = [vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_double, C.c_int32, vp, vp, vp]
     lib.mdb_op_nms.restype = C.c_int
+    lib.mdb_debug_set_trace.argtypes = [vp, C.c_char_p]
+    lib.mdb_debug_set_trace.restype = C.c_int
+    lib.mdb_debug_trace_names.argtypes = [vp, vp, C.c_size_t, P(C.c_int32)]
+    lib.mdb_debug_trace_names.restype = C.c_int
+    lib.mdb_debug_fetch_trace.argtypes = [vp, C.c_char_p, C.c_int32, vp, C.c_size_t, P(C.c_int64)]
+    lib.mdb_debug_fetch_trace.restype = C.c_int
+    lib.mdb_op_upsample2x.argtypes = [vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp]
+    lib.mdb_op_upsample2x.restype = C.c_int
+    lib.mdb_op_sppf_pool.argtypes = [vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp]
+    lib.mdb_op_sppf_pool.restype = C.c_int
+    lib.mdb_op_decode.argtypes = [vp, P(vp), P(C.c_int32), P(C.c_int32), C.c_int32, vp]
+    lib.mdb_op_decode.restype = C.c_int
     lib.mdb_alloc_pinned.argtypes = [C.c_size_t]
     lib.mdb_alloc_pinned.restype = vp
     lib.mdb_free_pinned.argtypes = [vp]
@@ -374,7 +391,61 @@ class Engine:
             return out[:, shp[2]:shp[2] + shp[3]]
         return out
 
+    # ---- parity harness: per-step trace ----
+    def set_trace(self, names):
+        """names: None (off), '*' (every step) or an iterable of step names."""
+        if names is None:
+            arg = None
+        elif isinstance(names, str):
+            arg = names.encode()
+        else:
+            arg = ','.join(names).encode()
+        self._check(self.lib.mdb_debug_set_trace(self.h, arg), 'mdb_debug_set_trace')
+
+    def trace_names(self):
+        buf = C.create_string_buffer(1 << 16)
+        n = C.c_int32(0)
+        self._check(self.lib.mdb_debug_trace_names(self.h, buf, len(buf), C.byref(n)), 'mdb_debug_trace_names')
+        return [x for x in buf.value.decode().split('\n') if x]
+
+    def fetch_trace(self, name, which):
+        """which: 0 input, 1 output, 2 residual -> numpy [N,H,W,C] (fp16, or fp32 for the Detect heads' output) or None."""
+        shp = (C.c_int64 * 5)()
+        self._check(self.lib.mdb_debug_fetch_trace(self.h, name.encode(), which, None, 0, shp), 'mdb_debug_fetch_trace')
+        if shp[0] == 0:
+            return None
+        out = np.empty([int(shp[i]) for i in range(4)], np.float32 if shp[4] else np.float16)
+        self._check(self.lib.mdb_debug_fetch_trace(self.h, name.encode(), which, out.ctypes.data, out.nbytes, shp),
+                    'mdb_debug_fetch_trace')
+        return out
+
     # ---- single-kernel entry points (parity tests) ----
+    def op_upsample2x(self, x):
+        x = np.ascontiguousarray(x, np.float16)
+        n, h, w, c = x.shape
+        y = np.empty((n, 2 * h, 2 * w, c), np.float16)
+        self._check(self.lib.mdb_op_upsample2x(self.h, x.ctypes.data, n, h, w, c, y.ctypes.data), 'mdb_op_upsample2x')
+        return y
+
+    def op_sppf_pool(self, s1):
+        s1 = np.ascontiguousarray(s1, np.float16)
+        n, h, w, c = s1.shape
+        y = np.empty((n, h, w, 4 * c), np.float16)
+        self._check(self.lib.mdb_op_sppf_pool(self.h, s1.ctypes.data, n, h, w, c, y.ctypes.data), 'mdb_op_sppf_pool')
+        return y
+
+    def op_decode(self, raws):
+        """raws: four fp32 arrays [n][ny][nx][round_up(3*no, 4)] (P3..P6) -> pred [n][anchors][no]."""
+        raws = [np.ascontiguousarray(r, np.float32) for r in raws]
+        n = raws[0].shape[0]
+        ptrs = (C.c_void_p * 4)(*[r.ctypes.data for r in raws])
+        ny = (C.c_int32 * 4)(*[r.shape[1] for r in raws])
+        nx = (C.c_int32 * 4)(*[r.shape[2] for r in raws])
+        rows = sum(3 * r.shape[1] * r.shape[2] for r in raws)
+        pred = np.empty((n, rows, self.no), np.float32)
+        self._check(self.lib.mdb_op_decode(self.h, ptrs, ny, nx, n, pred.ctypes.data), 'mdb_op_decode')
+        return pred
+
     def op_letterbox(self, img):
         g = letterbox_geometry(self.cfg, img.shape[0], img.shape[1])
         oh, ow = g['out_hw']

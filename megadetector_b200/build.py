@@ -45,12 +45,32 @@ def _stamp():
 
 
 def build(force=False, verbose=False):
-    """Compile every .cu for sm_100a and link the shared library.  Returns the path of the .so."""
+    """Compile every .cu for sm_100a and link the shared library.  Returns the path of the .so.
+
+    Safe against concurrent callers (torchrun ranks, producer workers): the build runs under an exclusive file lock, the
+    objects go to a per-process scratch directory and the library is moved into place with an atomic rename, so no process
+    can dlopen a half-written file."""
+    import fcntl
     os.makedirs(OBJ_DIR, exist_ok=True)
     stamp_file = os.path.join(OBJ_DIR, 'stamp')
     stamp = _stamp()
-    if not force and os.path.exists(OUT) and os.path.exists(stamp_file) and open(stamp_file).read() == stamp:
+
+    def fresh():
+        return os.path.exists(OUT) and os.path.exists(stamp_file) and open(stamp_file).read() == stamp
+
+    if not force and fresh():
         return OUT
+    with open(os.path.join(OBJ_DIR, 'lock'), 'w') as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and fresh():  # another process built it while we waited
+                return OUT
+            return _build_locked(stamp, stamp_file, verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(stamp, stamp_file, verbose):
     if not os.path.exists(NVCC):
         raise RuntimeError('nvcc not found at {} and no up-to-date prebuilt libmdb200.so'.format(NVCC))
     objs = []
@@ -69,11 +89,15 @@ def build(force=False, verbose=False):
         failed = failed or p.returncode != 0
     if failed:
         raise RuntimeError('nvcc failed')
-    cmd = [NVCC] + ARCH_FLAGS + ['-shared', '-cudart', 'static', '-Xcompiler', '-fPIC', '-o', OUT] + objs + ['-ldl', '-lpthread', '-lrt']
+    tmp_out = OUT + '.tmp.{}'.format(os.getpid())
+    cmd = [NVCC] + ARCH_FLAGS + ['-shared', '-cudart', 'static', '-Xcompiler', '-fPIC', '-o', tmp_out] + objs + ['-ldl', '-lpthread', '-lrt']
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout)
+        if os.path.exists(tmp_out):
+            os.remove(tmp_out)
         raise RuntimeError('link failed')
+    os.replace(tmp_out, OUT)
     with open(stamp_file, 'w') as f:
         f.write(stamp)
     return OUT

@@ -34,7 +34,7 @@ def _parse_synthetic(model_path):
     opts = dict(kv.split('=', 1) for kv in query.split('&') if '=' in kv)
     arch = dict(synth_weights.YOLOV5X6 if name in ('yolov5x6', 'mdv5a', 'mdv5b') else synth_weights.TINY_P6)
     seed = int(opts.get('seed', 1 if name == 'mdv5b' else 0))
-    return arch, seed
+    return arch, seed, opts.get('profile', 'chaotic')
 
 
 class _Placeholder(torch.nn.Module):
@@ -143,8 +143,9 @@ def load_yolov5_checkpoint(path):
 def load_model(model_path):
     """(weights, arch) for a `.pt` path or a `synthetic://` spec."""
     if is_synthetic(model_path):
-        arch, seed = _parse_synthetic(model_path)
-        w = synth_weights.synth_yolov5_weights(arch['ch'], arch['n_backbone'], arch['n_head'], arch['nc'], seed=seed)
+        arch, seed, profile = _parse_synthetic(model_path)
+        w = synth_weights.synth_yolov5_weights(arch['ch'], arch['n_backbone'], arch['n_head'], arch['nc'], seed=seed,
+                                               profile=profile)
         arch['anchors_px'] = None
         return w, arch
     return load_yolov5_checkpoint(model_path)

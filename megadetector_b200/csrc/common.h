@@ -75,13 +75,15 @@ struct ConvDesc {
   int kw = 0;      // filter width when it differs from k (0: square)
   int pad_x = -1;  // column padding when it differs from pad (-1: same)
 };
+// opts the conv kernel of the CURRENT device into its full dynamic shared memory (call once per device, after cudaSetDevice)
+void conv_init_device();
 ConvOp* conv_build(const ConvDesc& d, int num_sms);
 void conv_launch(ConvOp* op, int n_img, cudaStream_t st);
 void conv_free(ConvOp* op);
 double conv_macs_per_image(const ConvOp* op);
 int conv_pick_bn(int cout_pad);
-// channels per filter tap in the packed weights: C_in itself when the kernel can take it as 64-channel chunks plus
-// a 16/32-channel tail, else rounded up to a multiple of 64 (zero weights; the TMA unit zero-fills the activations)
+// channels per filter tap in the packed weights: C_in rounded up to a multiple of 64 (zero weights; the TMA unit
+// zero-fills the activations)
 int conv_cin_pad(int cin);
 
 // weight re-layout helpers (host): PyTorch [co][ci][k][k] fp32 -> [co_pad][k][k][ci_pad] fp16
@@ -116,6 +118,7 @@ struct PreImage {  // one per image, lives in device memory
 void preprocess_launch(const PreImage* d_imgs, int n, int out_h, int out_w, __half* dst, float max_scale,
                        cudaStream_t st);
 void preprocess_init_constants();
+void preprocess_init_device();  // per device: constants + the kernel's dynamic shared-memory opt-in
 
 // ---------------------------------------------------------------------------------------------
 // K3/K4/K5 (aux.cu)

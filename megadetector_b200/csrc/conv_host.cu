@@ -7,18 +7,14 @@
 #include <vector>
 
 #include "conv_pair_tcgen05.cuh"
-#include "conv_tcgen05.cuh"
 
 namespace mdb {
 
 struct ConvOp {
   CUtensorMap tmA[4];
   CUtensorMap tmB;
-  ConvMaps maps;  // pair kernel
-  ConvParams p;
+  ConvMaps maps;
   PairParams pp;
-  bool pair = true;
-  int kc = 64;
   bool flat = false;
   int HW_out = 0;  // output pixels per image
   size_t smem = 0;
@@ -34,10 +30,11 @@ int conv_pick_bn(int cout_pad) {
 }
 
 int conv_cin_pad(int cin) {
-  // Whole 64-channel chunks: channels beyond the tensor's are zero-filled by the TMA unit and meet zero weights.  Narrow
-  // tail chunks (16 / 32-channel boxes with their own swizzle width) were implemented and measured in round 1: they
-  // cost as much shared-memory fill time as a zero-filled 64-channel chunk (the TMA unit is bound by rows, not bytes:
-  // profiles/r01_conv_tail_probe.txt), so they were removed again.
+  // Whole 64-channel chunks (128-byte swizzle rows): channels beyond the tensor's are zero-filled by the TMA unit (no memory
+  // traffic) and meet zero weights.  Short rows make the TMA unit request-bound (3x3 80->80 ran 15x off the MMA floor with
+  // 32-byte rows); narrow 16 / 32-channel tail chunks were implemented and measured in round 1 and cost as much
+  // shared-memory fill time as a zero-filled 64-channel chunk (the TMA unit is bound by rows, not bytes:
+  // profiles/r01_conv_tail_probe.txt, r01_conv_oob_probe.txt), so they were removed again.
   return ((cin + 63) / 64) * 64;
 }
 
@@ -61,33 +58,11 @@ static void pick_tile(int H, int W, int* tw, int* th) {
   *th = bh;
 }
 
-static bool use_pair_kernel() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("MDB_CONV_V1");
-    v = (e && e[0] == '1') ? 0 : 1;
-  }
-  return v == 1;
-}
-
-template <int KC>
-static void set_smem_attr_pair(size_t bytes) {
-  static size_t current = 0;
-  if (bytes > current) {
-    MDB_CUDA(cudaFuncSetAttribute(conv_pair_kernel<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  static_cast<int>(bytes)));
-    current = bytes;
-  }
-}
-
-template <int KC>
-static void set_smem_attr(size_t bytes) {
-  static size_t current = 0;
-  if (bytes > current) {
-    MDB_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  static_cast<int>(bytes)));
-    current = bytes;
-  }
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE attribute: every device an engine is created on opts the
+// kernel into the full 227 KB once (mdb_create -> conv_init_device), instead of a process-global "largest size seen" cache
+// that would leave a second GPU of the same process at the 48 KB default.
+void conv_init_device() {
+  MDB_CUDA(cudaFuncSetAttribute(conv_pair_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 8192));
 }
 
 ConvOp* conv_build(const ConvDesc& d, int num_sms) {
@@ -95,54 +70,21 @@ ConvOp* conv_build(const ConvDesc& d, int num_sms) {
   try {
     const View& in = d.in;
     const View& out = d.out;
+    constexpr int kc = 64;  // K chunk = one 128-byte swizzle row of channels (see conv_cin_pad)
     MDB_REQUIRE(in.C % 8 == 0, "conv input channels must be a multiple of 8");
-    MDB_REQUIRE(d.cin_pad >= in.C && d.cin_pad % 16 == 0, "bad cin_pad");
+    MDB_REQUIRE(d.cin_pad >= in.C && d.cin_pad % kc == 0, "C_in per tap must be padded to a multiple of 64");
     MDB_REQUIRE(d.cout_pad % 16 == 0 && d.cout_pad >= d.cout, "bad cout_pad");
     MDB_REQUIRE(d.s == 1 || d.s == 2, "stride must be 1 or 2");
     MDB_REQUIRE(out.C >= d.cout, "output view too narrow");
-    // K chunk = one swizzle row of channels.  Always 64 (128-byte rows) when the packed weights allow it: short
-    // rows (32/64 B) make the TMA unit request-bound (measured: 3x3 80->80 ran 15x off the MMA floor with 32-byte
-    // rows).  Channels beyond in.C inside the last chunk are zero-filled by the TMA unit (no memory traffic) and
-    // meet zero weights.
-    // The pair kernel always works on 64-channel chunks; a remainder of 16 or 32 channels per tap becomes a narrow
-    // "tail" chunk with its own swizzle width (32 / 64-byte rows) instead of a mostly zero-filled 64-channel one:
-    // shared-memory fill, not the tensor pipe, bounds these layers (profiles/r01_conv_oob_probe.txt).
-    const bool pair = use_pair_kernel();
-    const int kc = pair ? 64 : (d.cin_pad % 64 == 0 ? 64 : (d.cin_pad % 32 == 0 ? 32 : 16));
-    MDB_REQUIRE(!pair || d.cin_pad % 64 == 0, "pair kernel: C_in per tap must be padded to a multiple of 64");
-    op->kc = kc;
     op->num_sms = num_sms;
-    ConvParams& p = op->p;
     const int kw = d.kw > 0 ? d.kw : d.k;
     const int pad_x = d.pad_x >= 0 ? d.pad_x : d.pad;
     const int Ho = (in.H + 2 * d.pad - d.k) / d.s + 1;
     const int Wo = (in.W + 2 * pad_x - kw) / d.s + 1;
     MDB_REQUIRE(Ho == out.H && Wo == out.W && out.N == in.N, "conv output view has the wrong shape");
     op->HW_out = Ho * Wo;
-    p.H_out = Ho;
-    p.W_out = Wo;
     op->macs_per_image = static_cast<double>(Ho) * Wo * d.cout * in.C * d.k * kw;
     op->flat = (d.k == 1 && d.s == 1 && d.pad == 0);
-
-    p.BN = conv_pick_bn(d.cout_pad);
-    p.n_tiles = d.cout_pad / p.BN;
-    p.Cout = d.cout;
-    p.KH = d.k;
-    p.KW = kw;
-    p.stride = d.s;
-    p.pad = d.pad;
-    p.Cin = d.cin_pad;
-    p.chunks = (d.cin_pad + kc - 1) / kc;
-    p.bias = d.bias;
-    p.out = out.base;
-    p.out_pix_stride = out.Ctot;
-    p.out_c_off = out.c_off;
-    p.out_fp32 = out.fp32 ? 1 : 0;
-    p.res = d.res.base ? static_cast<const __half*>(d.res.base) : nullptr;
-    p.res_pix_stride = d.res.Ctot;
-    p.res_c_off = d.res.c_off;
-    p.act = d.act;
-    p.idesc = make_idesc_f16(kTileM, static_cast<uint32_t>(p.BN));
     if (d.res.base) {
       MDB_REQUIRE(d.res.H == Ho && d.res.W == Wo && d.res.N == in.N && !d.res.fp32, "residual view mismatch");
       MDB_REQUIRE(d.res.Ctot % 8 == 0 && d.res.c_off % 8 == 0, "residual view must be 16-byte aligned per pixel");
@@ -150,132 +92,119 @@ ConvOp* conv_build(const ConvDesc& d, int num_sms) {
     MDB_REQUIRE(out.fp32 ? (out.Ctot % 4 == 0 && out.c_off % 4 == 0) : (out.Ctot % 8 == 0 && out.c_off % 8 == 0),
                 "output view must be 16-byte aligned per pixel");
 
+    PairParams& q = op->pp;
+    q.H_out = Ho; q.W_out = Wo;
+    q.BN = conv_pick_bn(d.cout_pad);
+    q.n_tiles = d.cout_pad / q.BN;
+    q.Cout = d.cout;
+    q.taps = d.k * kw;
+    q.chunks = d.cin_pad / kc;
+    q.total_chunks = q.taps * q.chunks;
+    MDB_REQUIRE(q.taps <= 9, "at most 9 filter taps");
+    MDB_REQUIRE(d.cout_pad <= kPairMaxCout, "at most 1280 (padded) output channels");
     if (op->flat) {
-      p.tw = 128;
-      p.th = 1;
+      q.tw = 128;
+      q.th = 1;
       make_act_tmap_flat(&op->tmA[0], in, kc);
       op->tmA[1] = op->tmA[2] = op->tmA[3] = op->tmA[0];
     } else {
-      pick_tile(Ho, Wo, &p.tw, &p.th);
+      pick_tile(Ho, Wo, &q.tw, &q.th);
       if (d.s == 1) {
-        make_act_tmap(&op->tmA[0], in, kc, p.tw, p.th, -1, -1);
+        make_act_tmap(&op->tmA[0], in, kc, q.tw, q.th, -1, -1);
         op->tmA[1] = op->tmA[2] = op->tmA[3] = op->tmA[0];
       } else {
         for (int py = 0; py < 2; ++py)
-          for (int px = 0; px < 2; ++px) make_act_tmap(&op->tmA[py * 2 + px], in, kc, p.tw, p.th, py, px);
+          for (int px = 0; px < 2; ++px) make_act_tmap(&op->tmA[py * 2 + px], in, kc, q.tw, q.th, py, px);
       }
     }
-    op->pair = pair;
-    if (op->pair) {
-      // CTA pair: each CTA stages half of the B tile
-      make_wgt_tmap(&op->tmB, d.wgt, d.k * kw * d.cin_pad, d.cout_pad, kc, p.BN / 2);
-      PairParams& q = op->pp;
-      q.H_out = p.H_out; q.W_out = p.W_out; q.tw = p.tw; q.th = p.th;
-      q.n_tiles = p.n_tiles; q.BN = p.BN; q.Cout = p.Cout;
-      q.taps = d.k * kw;
-      q.chunks = p.chunks;
-      q.total_chunks = q.taps * p.chunks;
-      MDB_REQUIRE(q.taps <= 9, "pair kernel: at most 9 filter taps");
-      MDB_REQUIRE(d.cout_pad <= kPairMaxCout, "pair kernel: at most 1280 (padded) output channels");
-      for (int i = 0; i < 10; ++i) q.tap_word[i] = 0;
-      for (int kh = 0; kh < d.k; ++kh)
-        for (int kx = 0; kx < kw; ++kx) {
-          int dx, dy, par = 0;
-          if (d.s == 1) {
-            dx = kx - pad_x;
-            dy = kh - d.pad;
-          } else {  // the tap reads one of the four parity views of the input, at half resolution
-            const int ty = kh - d.pad, tx = kx - pad_x;
-            const int py = ty & 1, px = tx & 1;
-            dy = (ty - py) >> 1;
-            dx = (tx - px) >> 1;
-            par = py * 2 + px;
-          }
-          MDB_REQUIRE(dx >= -8 && dx < 120 && dy >= -8 && dy < 120, "filter tap offset out of range");
-          q.tap_word[kh * kw + kx] = static_cast<uint32_t>(dx + 8) | static_cast<uint32_t>(dy + 8) << 8 | static_cast<uint32_t>(par) << 16;
+    // CTA pair: each CTA stages half of the B tile
+    make_wgt_tmap(&op->tmB, d.wgt, d.k * kw * d.cin_pad, d.cout_pad, kc, q.BN / 2);
+    for (int i = 0; i < 10; ++i) q.tap_word[i] = 0;
+    for (int kh = 0; kh < d.k; ++kh)
+      for (int kx = 0; kx < kw; ++kx) {
+        int dx, dy, par = 0;
+        if (d.s == 1) {
+          dx = kx - pad_x;
+          dy = kh - d.pad;
+        } else {  // the tap reads one of the four parity views of the input, at half resolution
+          const int ty = kh - d.pad, tx = kx - pad_x;
+          const int py = ty & 1, px = tx & 1;
+          dy = (ty - py) >> 1;
+          dx = (tx - px) >> 1;
+          par = py * 2 + px;
         }
-      // chunks per pipeline stage: enough MMA time per mbarrier round trip (>= ~320 tensor cycles)
-      {
-        static const char* e = getenv("MDB_CONV_CPS");
-        q.cps = e ? atoi(e) : 2;  // measured sweep (profiles/r01_conv_cases_cps*.txt): 2 wins on every layer shape
-        if (q.cps < 1) q.cps = 1;
-        if (q.cps > 4) q.cps = 4;
+        MDB_REQUIRE(dx >= -8 && dx < 120 && dy >= -8 && dy < 120, "filter tap offset out of range");
+        q.tap_word[kh * kw + kx] = static_cast<uint32_t>(dx + 8) | static_cast<uint32_t>(dy + 8) << 8 | static_cast<uint32_t>(par) << 16;
       }
-      q.bias = p.bias; q.out = p.out; q.out_pix_stride = p.out_pix_stride; q.out_c_off = p.out_c_off;
-      q.out_fp32 = p.out_fp32; q.res = p.res; q.res_pix_stride = p.res_pix_stride; q.res_c_off = p.res_c_off;
-      q.act = p.act;
-      q.idesc = make_idesc_f16(256, static_cast<uint32_t>(p.BN));
-      q.dbg = nullptr;
-      q.halo = 0;
-      q.a_stages = 0;
-      {
-        static const char* ep = getenv("MDB_CONV_PROBE");  // honoured by -DMDB_CONV_PROBES builds only
-        q.probe = ep ? atoi(ep) : 0;
-      }
-      {
-        const int oa = out.fp32 ? 8 : 16;  // elements per 32 bytes
-        bool wide = (out.Ctot % oa == 0) && (out.c_off % oa == 0) && (reinterpret_cast<uintptr_t>(out.base) % 32 == 0);
-        if (d.res.base)
-          wide = wide && (d.res.Ctot % 16 == 0) && (d.res.c_off % 16 == 0) && (reinterpret_cast<uintptr_t>(d.res.base) % 32 == 0);
-        q.wide = wide ? 1 : 0;
-        q.fast = (wide && !out.fp32 && d.cout % 16 == 0 && d.cout_pad == d.cout) ? 1 : 0;
-      }
-      const size_t a_chunk = static_cast<size_t>(kTileM) * kc * 2;
-      const size_t b_chunk = (static_cast<size_t>(p.BN / 2) * kc * 2 + 1023) & ~static_cast<size_t>(1023);
-      // 3x3 / stride-1 layers whose output tiles well with 8 x 16 blocks use the row-halo main loop
-      {
-        static const char* eh = getenv("MDB_CONV_HALO");
-        const bool allow = !(eh && eh[0] == '0');
-        static const char* ehm = getenv("MDB_CONV_HALO_MIN");
-        const int halo_min_chunks = ehm ? atoi(ehm) : 2;
-        const double eff = static_cast<double>(Ho) * Wo / (static_cast<double>((Wo + 7) / 8 * 8) * ((Ho + 15) / 16 * 16));
-        if (allow && d.k == 3 && kw == 3 && d.s == 1 && d.pad == 1 && pad_x == 1 && eff >= 0.85 && p.chunks >= halo_min_chunks) {  // measured (one filter row per weight stage): -26% time at 80 ch, -16% at 160, -9% at 320
-          q.halo = 1;
-          q.a_stages = 2;
-          q.tw = kHaloTw;
-          q.th = kHaloTh;
-          make_act_tmap(&op->tmA[0], in, kc, kHaloTw, kHaloRows, -1, -1);
-          op->tmA[1] = op->tmA[2] = op->tmA[3] = op->tmA[0];
-          for (int i = 0; i < 4; ++i) op->maps.a[i] = op->tmA[0];
-          op->maps.b = op->tmB;
-          const size_t budget = 227 * 1024 - 8192 - 1024;  // static: barriers + the bias vector; alignment slack
-          const size_t a_bytes = static_cast<size_t>(q.a_stages) * 3 * kHaloBox;
-          int stages = static_cast<int>(std::min<size_t>(kPairMaxStages, (budget - a_bytes) / (3 * b_chunk)));  // a stage = one filter row
-          MDB_REQUIRE(stages >= 2, "not enough shared memory for the halo pipeline");
-          q.stages = stages;
-          q.cps = 1;
-          op->smem = a_bytes + 3 * b_chunk * stages + 1024;
-          set_smem_attr_pair<64>(op->smem);
-          return op;
-        }
-      }
-      const size_t stage = static_cast<size_t>(q.cps) * (a_chunk + b_chunk);
-      const size_t budget = 227 * 1024 - 8192;  // static: barriers + the bias vector; alignment slack
-      const int stage_iters = (q.total_chunks + q.cps - 1) / q.cps;
-      int stages = static_cast<int>(std::min<size_t>(kPairMaxStages, (budget - 1024) / stage));
-      stages = std::max(2, std::min(stages, std::max(2, stage_iters * 2)));
-      q.stages = stages;
-      op->smem = stage * stages + 1024;
-      for (int i = 0; i < 4; ++i) op->maps.a[i] = op->tmA[i];
-      op->maps.b = op->tmB;
-      set_smem_attr_pair<64>(op->smem);
-      return op;
+    // chunks per pipeline stage: enough MMA time per mbarrier round trip (>= ~320 tensor cycles)
+    {
+      static const char* e = getenv("MDB_CONV_CPS");
+      q.cps = e ? atoi(e) : 2;  // measured sweep (profiles/r01_conv_cases_cps*.txt): 2 wins on every layer shape
+      if (q.cps < 1) q.cps = 1;
+      if (q.cps > 4) q.cps = 4;
     }
-    MDB_REQUIRE(kw == d.k && pad_x == d.pad, "the single-CTA fallback kernel handles square filters only");
-    make_wgt_tmap(&op->tmB, d.wgt, d.k * d.k * d.cin_pad, d.cout_pad, kc, p.BN);
-
-    const size_t a_bytes = static_cast<size_t>(kTileM) * kc * 2;
-    const size_t b_bytes = (static_cast<size_t>(p.BN) * kc * 2 + 1023) & ~static_cast<size_t>(1023);
-    const size_t stage = a_bytes + b_bytes;
-    const size_t budget = 227 * 1024 - 2048;  // static barriers + alignment slack
-    int stages = static_cast<int>(std::min<size_t>(kConvMaxStages, (budget - 1024) / stage));
-    const int k_iters = d.k * d.k * p.chunks;
-    stages = std::max(2, std::min(stages, std::max(2, k_iters * 2)));
-    p.stages = stages;
+    q.bias = d.bias;
+    q.out = out.base;
+    q.out_pix_stride = out.Ctot;
+    q.out_c_off = out.c_off;
+    q.out_fp32 = out.fp32 ? 1 : 0;
+    q.res = d.res.base ? static_cast<const __half*>(d.res.base) : nullptr;
+    q.res_pix_stride = d.res.Ctot;
+    q.res_c_off = d.res.c_off;
+    q.act = d.act;
+    q.idesc = make_idesc_f16(256, static_cast<uint32_t>(q.BN));
+    q.dbg = nullptr;
+    q.halo = 0;
+    q.a_stages = 0;
+    {
+      static const char* ep = getenv("MDB_CONV_PROBE");  // honoured by -DMDB_CONV_PROBES builds only
+      q.probe = ep ? atoi(ep) : 0;
+    }
+    {
+      const int oa = out.fp32 ? 8 : 16;  // elements per 32 bytes
+      bool wide = (out.Ctot % oa == 0) && (out.c_off % oa == 0) && (reinterpret_cast<uintptr_t>(out.base) % 32 == 0);
+      if (d.res.base)
+        wide = wide && (d.res.Ctot % 16 == 0) && (d.res.c_off % 16 == 0) && (reinterpret_cast<uintptr_t>(d.res.base) % 32 == 0);
+      q.wide = wide ? 1 : 0;
+      q.fast = (wide && !out.fp32 && d.cout % 16 == 0 && d.cout_pad == d.cout) ? 1 : 0;
+    }
+    const size_t a_chunk = static_cast<size_t>(kTileM) * kc * 2;
+    const size_t b_chunk = (static_cast<size_t>(q.BN / 2) * kc * 2 + 1023) & ~static_cast<size_t>(1023);
+    // 3x3 / stride-1 layers whose output tiles well with 8 x 16 blocks use the row-halo main loop
+    {
+      static const char* eh = getenv("MDB_CONV_HALO");
+      const bool allow = !(eh && eh[0] == '0');
+      static const char* ehm = getenv("MDB_CONV_HALO_MIN");
+      const int halo_min_chunks = ehm ? atoi(ehm) : 2;
+      const double eff = static_cast<double>(Ho) * Wo / (static_cast<double>((Wo + 7) / 8 * 8) * ((Ho + 15) / 16 * 16));
+      // measured (one filter row per weight stage): -26% time at 80 ch, -16% at 160, -9% at 320
+      if (allow && d.k == 3 && kw == 3 && d.s == 1 && d.pad == 1 && pad_x == 1 && eff >= 0.85 && q.chunks >= halo_min_chunks) {
+        q.halo = 1;
+        q.a_stages = 2;
+        q.tw = kHaloTw;
+        q.th = kHaloTh;
+        make_act_tmap(&op->tmA[0], in, kc, kHaloTw, kHaloRows, -1, -1);
+        for (int i = 0; i < 4; ++i) op->maps.a[i] = op->tmA[0];
+        op->maps.b = op->tmB;
+        const size_t budget = 227 * 1024 - 8192 - 1024;  // static: barriers + the bias vector; alignment slack
+        const size_t a_bytes = static_cast<size_t>(q.a_stages) * 3 * kHaloBox;
+        int stages = static_cast<int>(std::min<size_t>(kPairMaxStages, (budget - a_bytes) / (3 * b_chunk)));  // a stage = one filter row
+        MDB_REQUIRE(stages >= 2, "not enough shared memory for the halo pipeline");
+        q.stages = stages;
+        q.cps = 1;
+        op->smem = a_bytes + 3 * b_chunk * stages + 1024;
+        return op;
+      }
+    }
+    const size_t stage = static_cast<size_t>(q.cps) * (a_chunk + b_chunk);
+    const size_t budget = 227 * 1024 - 8192;  // static: barriers + the bias vector; alignment slack
+    const int stage_iters = (q.total_chunks + q.cps - 1) / q.cps;
+    int stages = static_cast<int>(std::min<size_t>(kPairMaxStages, (budget - 1024) / stage));
+    stages = std::max(2, std::min(stages, std::max(2, stage_iters * 2)));
+    q.stages = stages;
     op->smem = stage * stages + 1024;
-    if (kc == 64) set_smem_attr<64>(op->smem);
-    else if (kc == 32) set_smem_attr<32>(op->smem);
-    else set_smem_attr<16>(op->smem);
+    for (int i = 0; i < 4; ++i) op->maps.a[i] = op->tmA[i];
+    op->maps.b = op->tmB;
   } catch (...) {
     delete op;
     throw;
@@ -345,36 +274,7 @@ static void conv_launch_pair(ConvOp* op, int n_img, cudaStream_t st) {
   }
 }
 
-void conv_launch(ConvOp* op, int n_img, cudaStream_t st) {
-  if (op->pair) {
-    conv_launch_pair(op, n_img, st);
-    return;
-  }
-  ConvParams p = op->p;
-  if (op->flat) {
-    const long long npix = static_cast<long long>(n_img) * op->HW_out;
-    p.n_img = 1;
-    p.H_out = 1;
-    p.W_out = static_cast<int>(npix);
-    p.tiles_x = static_cast<int>((npix + 127) / 128);
-    p.tiles_y = 1;
-  } else {
-    p.n_img = n_img;
-    p.tiles_x = (p.W_out + p.tw - 1) / p.tw;
-    p.tiles_y = (p.H_out + p.th - 1) / p.th;
-  }
-  p.m_tiles = p.n_img * p.tiles_x * p.tiles_y;
-  const long long total = static_cast<long long>(p.m_tiles) * p.n_tiles;
-  const int grid = static_cast<int>(std::min<long long>(total, op->num_sms));
-  if (grid <= 0) return;
-  if (op->kc == 64)
-    conv_igemm_kernel<64><<<grid, kConvThreads, op->smem, st>>>(op->tmA[0], op->tmA[1], op->tmA[2], op->tmA[3], op->tmB, p);
-  else if (op->kc == 32)
-    conv_igemm_kernel<32><<<grid, kConvThreads, op->smem, st>>>(op->tmA[0], op->tmA[1], op->tmA[2], op->tmA[3], op->tmB, p);
-  else
-    conv_igemm_kernel<16><<<grid, kConvThreads, op->smem, st>>>(op->tmA[0], op->tmA[1], op->tmA[2], op->tmA[3], op->tmB, p);
-  MDB_CUDA(cudaGetLastError());
-}
+void conv_launch(ConvOp* op, int n_img, cudaStream_t st) { conv_launch_pair(op, n_img, st); }
 
 void conv_free(ConvOp* op) { delete op; }
 double conv_macs_per_image(const ConvOp* op) { return op->macs_per_image; }

@@ -1,7 +1,19 @@
-// K2 (v2): implicit-GEMM convolution on CTA PAIRS -- tcgen05.mma.cta_group::2, 256 x BN pair tiles.
+// K2: implicit-GEMM convolution on tcgen05 tensor cores (sm_100a), CTA PAIRS -- tcgen05.mma.cta_group::2, 256 x BN pair tiles.
 //
-// Same GEMM view as conv_tcgen05.cuh (A = shifted NHWC boxes fetched by TMA with zero-fill, B = fused weights
-// [C_out][KH][KW][C_in], D in TMEM), re-organised after the first ncu captures (profiles/r01_*):
+// Replaces the cuDNN convolutions that the reference triggers through `self.model(batch_tensor)`
+// (megadetector/detection/pytorch_detector.py:1313; the module graph is the third-party YOLOv5x6 `DetectionModel`,
+// restated in SURVEY.md App. A).  One kernel covers every Conv(+bias)+SiLU of the network:
+//
+//   GEMM view   D[M = output pixels][N = C_out] = A[M][K = KH*KW*C_in] * W[N][K]^T
+//   A operand   never materialised: for each filter tap the TMA engine fetches a {64 channels, tw, th, 1 image} box of the
+//               NHWC fp16 activation tensor, shifted by the tap offset; out-of-image elements are zero-filled by the TMA
+//               unit (= conv padding).  Stride-2 convs use four parity views of the input (one tensor map per parity).
+//   B operand   fused weights stored [C_out][KH][KW][C_in] fp16 (K-major), 2-D TMA boxes {64, BN/2} per CTA.
+//   D           fp32 accumulators in TMEM (2 stages of up to 256 columns, 4 of up to 128).
+//   epilogue    tcgen05.ld -> +bias -> SiLU -> (+residual) -> fp16 (or fp32) NHWC store at a channel offset of the
+//               destination buffer (this is how Concat costs nothing).
+//
+// History (the first version was a single-CTA 128 x BN kernel; profiles/r01_*v1*):
 //   * the 128 x BN single-CTA kernel could not keep the tensor pipe fed: 36 KB of operands per 1.3 M MACs and
 //     <= 216 KB in flight per SM is not enough at the observed TMA latency (tensor pipe 40 % active on the
 //     3x3 320->320 layer, L2 at 37 %, DRAM at 7 %).  A CTA pair shares B: each CTA stages its own 128 A rows
@@ -13,17 +25,19 @@
 //     (four per TMEM lane quadrant, interleaved 16-column chunks), TMEM loads issued one chunk ahead, bias from
 //     shared memory, SiLU as ex2.approx + rcp.approx (2 MUFU ops per element).
 //
-// Warp roles per CTA (320 threads): warp 0 = TMA producer, warp 1 = TMEM owner (+ MMA issuer in the leader CTA),
+// Warp roles per CTA (576 threads): warp 0 = TMA producer, warp 1 = TMEM owner (+ MMA issuer in the leader CTA),
 // warps 2..17 = epilogue.  Barriers: full[s] lives in the LEADER (2 arrivals + bytes of both CTAs),
 // empty[s] / acc_full[a] are per CTA and signalled by multicast tcgen05.commit, acc_empty[a] lives in the leader
 // (one arrival per epilogue warp of both CTAs).
 #pragma once
 #include <cuda_fp16.h>
 
-#include "conv_tcgen05.cuh"
 #include "ptx.cuh"
 
 namespace mdb {
+
+constexpr int kTileM = 128;     // GEMM rows per CTA (TMEM lanes)
+constexpr int kTmemCols = 512;  // the whole TMEM of the SM
 
 // Cycle counters of the role threads (MDB_CONV_DEBUG=1) exist only in -DMDB_CONV_TIMERS builds: even predicated off,
 // the extra instructions in the single-thread loops cost 17% on 1x1 layers.
@@ -107,7 +121,9 @@ __device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
 // 256-bit global accesses (sm_100: LDG/STG.E.ENL2.256): one full 32-byte sector per lane and instruction -- half
 // the LSU wavefronts of two 128-bit accesses for the pixel-strided epilogue traffic
 __device__ __forceinline__ void ldg256(const void* p, uint4& a, uint4& b) {
-  asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+  // plain (coherent) load: for single-bottleneck C3 blocks the kernel writes its output in place over the residual
+  // (engine.cu Builder::c3), and the non-coherent path must not read memory the same kernel writes
+  asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
                : "l"(p));
 }
@@ -212,7 +228,7 @@ __device__ __forceinline__ void umma2_commit_mc_addr(uint32_t bar_addr) {
       : "memory");
 }
 // try_wait WITHOUT a suspend-time hint on purpose: with a hint (1 ms, as CUTLASS passes) the hardware parks the thread and
-// the wake-up latency cost 5-8% on the 1x1 layers (measured A/B, profiles/r01_conv_ab_suspend_hint.txt), although the
+// the wake-up latency cost 5-8% on the 1x1 layers (measured A/B, profiles/r01_conv_ab_experiments.txt par. 4), although the
 // polling loops are ~20% of all issued instructions there.
 __device__ __forceinline__ bool mbar_try_wait_addr(uint32_t addr, uint32_t parity) {
   uint32_t ok;
@@ -247,7 +263,7 @@ __device__ __forceinline__ void mbar_wait_addr_timed(uint32_t addr, uint32_t par
 // arithmetic (which ptxas then keeps on the uniform datapath, next to the TMA / MMA operands), and only the instructions
 // with side effects are issued by the elected lane.  The first version ran the whole loop inside `if (elect_one())`:
 // its ~110 dependent per-thread instructions per stage (R2UR round trips, re-loaded parameters) took 800-1100 cycles
-// per stage and bounded every layer with short stages (profiles/r01_conv_skeleton_probe.txt).
+// per stage and bounded every layer with short stages (skeleton probe, profiles/r01_conv_ab_experiments.txt par. 1-2).
 template <int KC>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1)
 conv_pair_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ PairParams p) {
@@ -590,8 +606,8 @@ conv_pair_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
         uint4 r0 = make_uint4(0, 0, 0, 0), r1 = make_uint4(0, 0, 0, 0);
         if (p.res != nullptr) {
           const __half* rp = p.res + pix * p.res_pix_stride + p.res_c_off + col0;
-          r0 = __ldg(reinterpret_cast<const uint4*>(rp));
-          r1 = __ldg(reinterpret_cast<const uint4*>(rp) + 1);
+          r0 = *reinterpret_cast<const uint4*>(rp);
+          r1 = *(reinterpret_cast<const uint4*>(rp) + 1);
         }
         float f[16];
         const float4* b4 = reinterpret_cast<const float4*>(bs + jj * 16);

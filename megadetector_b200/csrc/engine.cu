@@ -65,7 +65,18 @@ struct Plan {
   NmsScratch nms_scratch{};
   double macs_per_image = 0;
   std::map<int, cudaGraphExec_t> graphs;  // forward pass per batch size
+  // parity harness (mdb_debug_set_trace): dense copies of the traced steps' input / output / residual views
+  struct TraceRec {
+    size_t off[3] = {0, 0, 0};      // in, out, res
+    int shape[3][4] = {{0}};        // N, H, W, C
+    bool present[3] = {false, false, false};
+    bool out_fp32 = false;
+  };
+  std::map<std::string, TraceRec> trace;
+  void* trace_mem = nullptr;
+  size_t trace_cap = 0;
   ~Plan() {
+    if (trace_mem) cudaFree(trace_mem);
     for (auto& kv : graphs) cudaGraphExecDestroy(kv.second);
     for (auto& s : steps)
       if (s.op) conv_free(s.op);
@@ -143,7 +154,10 @@ struct mdb_engine {
   cudaEvent_t ev_t[4] = {nullptr, nullptr, nullptr, nullptr};
   std::map<std::string, ConvWeights> weights;
   bool weights_loaded = false;
+  // per-shape plans, bounded: least recently used plans are evicted (arena, pred, NMS scratch, graphs are freed)
   std::map<std::pair<int, int>, std::unique_ptr<Plan>> plans;
+  std::vector<std::pair<int, int>> plan_lru;  // most recent last
+  int max_plans = 6;
   std::map<TableKey, DevTable> tables;
   // staging (double-buffered across chunks)
   uint8_t* d_src[2] = {nullptr, nullptr};
@@ -171,6 +185,8 @@ struct mdb_engine {
   int64_t launches = 0;
   int pipeline_split = 4;
   bool use_graphs = true;
+  bool trace_all = false;
+  std::vector<std::string> trace_names;
   BatchState batch;
   std::string err;
 };
@@ -209,13 +225,13 @@ struct Builder {
     touch(in); touch(out); touch(res);
     P.steps.push_back(st);
   }
-  void upsample(VView in, VView out) {
-    Step st; st.kind = STEP_UPSAMPLE; st.name = "upsample"; st.in = in; st.out = out;
+  void upsample(VView in, VView out, int idx) {
+    Step st; st.kind = STEP_UPSAMPLE; st.name = "upsample." + std::to_string(idx); st.in = in; st.out = out;
     touch(in); touch(out);
     P.steps.push_back(st);
   }
   void sppf(VView cat) {
-    Step st; st.kind = STEP_SPPF; st.name = "sppf_pool"; st.in = cat; st.out = cat;
+    Step st; st.kind = STEP_SPPF; st.name = "sppf_pool.11"; st.in = cat; st.out = cat;
     touch(cat);
     P.steps.push_back(st);
   }
@@ -304,15 +320,15 @@ void build_graph(Plan& P, const mdb_arch& A, const std::map<std::string, ConvWei
   B.conv("model.11.cv2.conv", B.whole(sppf_cat), B.whole(x11), c[5], 1, 1, 0);
   // head
   B.conv("model.12.conv", B.whole(x11), B.slice(cat31, c[4], c[4]), c[4], 1, 1, 0);  // x12
-  B.upsample(B.slice(cat31, c[4], c[4]), B.slice(cat14, 0, c[4]));
+  B.upsample(B.slice(cat31, c[4], c[4]), B.slice(cat14, 0, c[4]), 13);
   const int x15 = B.newbuf(h32, w32, c[4]);
   B.c3(15, B.whole(cat14), B.whole(x15), c[4], nh, false);
   B.conv("model.16.conv", B.whole(x15), B.slice(cat28, c[3], c[3]), c[3], 1, 1, 0);  // x16
-  B.upsample(B.slice(cat28, c[3], c[3]), B.slice(cat18, 0, c[3]));
+  B.upsample(B.slice(cat28, c[3], c[3]), B.slice(cat18, 0, c[3]), 17);
   const int x19 = B.newbuf(h16, w16, c[3]);
   B.c3(19, B.whole(cat18), B.whole(x19), c[3], nh, false);
   B.conv("model.20.conv", B.whole(x19), B.slice(cat25, c[2], c[2]), c[2], 1, 1, 0);  // x20
-  B.upsample(B.slice(cat25, c[2], c[2]), B.slice(cat22, 0, c[2]));
+  B.upsample(B.slice(cat25, c[2], c[2]), B.slice(cat22, 0, c[2]), 21);
   const int x23 = B.newbuf(h8, w8, c[2]);
   B.c3(23, B.whole(cat22), B.whole(x23), c[2], nh, false);
   B.conv("model.24.conv", B.whole(x23), B.slice(cat25, 0, c[2]), c[2], 3, 2, 1);  // x24
@@ -380,12 +396,67 @@ void assign_offsets(Plan& P, bool reuse) {
   P.arena_bytes = total;
 }
 
+// A plan may be evicted only when nothing refers to it: not staged in a pipeline slot of the running batch, not the
+// target of the debug fetches.  The device is idle when this runs (callers synchronise first).
+bool plan_in_use(mdb_engine* e, const Plan* P) {
+  for (const Pending& pd : e->batch.inflight)
+    if (pd.plan == P) return true;
+  return false;
+}
+
+// frees least-recently-used plans until at most `keep` remain (plans in use are skipped); returns the number freed
+int evict_plans(mdb_engine* e, size_t keep) {
+  int freed = 0;
+  size_t i = 0;
+  while (e->plans.size() > keep && i < e->plan_lru.size()) {
+    const auto key = e->plan_lru[i];
+    auto it = e->plans.find(key);
+    if (it == e->plans.end()) { e->plan_lru.erase(e->plan_lru.begin() + i); continue; }
+    Plan* P = it->second.get();
+    if (plan_in_use(e, P)) { ++i; continue; }
+    cudaDeviceSynchronize();
+    for (int s = 0; s < 2; ++s)
+      if (e->slot_plan[s] == P) { e->slot_plan[s] = nullptr; e->slot_n[s] = 0; }
+    if (e->last_plan == P) e->last_plan = nullptr;
+    e->plans.erase(it);
+    e->plan_lru.erase(e->plan_lru.begin() + i);
+    ++freed;
+  }
+  return freed;
+}
+
+Plan* build_plan(mdb_engine* e, int H, int W);
+
+// Plans are cached per letterboxed shape.  The cache is bounded (mdb_config-independent: MDB_MAX_PLANS, default 6 -- the
+// classic letterbox produces few distinct shapes per camera, but a mixed-aspect data set can produce dozens, each with
+// an arena sized for max_batch): the least recently used plan is dropped first, and an allocation failure drops every
+// idle plan and retries once before the shape group is reported as an inference failure.
 Plan* get_plan(mdb_engine* e, int H, int W) {
   auto key = std::make_pair(H, W);
   auto it = e->plans.find(key);
-  if (it != e->plans.end()) return it->second.get();
+  if (it != e->plans.end()) {
+    auto pos = std::find(e->plan_lru.begin(), e->plan_lru.end(), key);
+    if (pos != e->plan_lru.end()) e->plan_lru.erase(pos);
+    e->plan_lru.push_back(key);
+    return it->second.get();
+  }
   MDB_REQUIRE(e->weights_loaded, "mdb_load_weights must be called before inference");
   MDB_REQUIRE(H % 64 == 0 && W % 64 == 0 && H >= 64 && W >= 64, "letterboxed shape must be a multiple of 64");
+  if (e->plans.size() >= static_cast<size_t>(e->max_plans)) evict_plans(e, static_cast<size_t>(e->max_plans) - 1);
+  Plan* P = nullptr;
+  try {
+    P = build_plan(e, H, W);
+  } catch (const CudaError&) {
+    cudaGetLastError();
+    if (evict_plans(e, 0) == 0) throw;
+    P = build_plan(e, H, W);  // second failure propagates
+  }
+  e->plan_lru.push_back(key);
+  return P;
+}
+
+Plan* build_plan(mdb_engine* e, int H, int W) {
+  auto key = std::make_pair(H, W);
   std::unique_ptr<Plan> P(new Plan());
   P->H = H; P->W = W; P->nb = e->cfg.max_batch;
   build_graph(*P, e->cfg.arch, &e->weights);
@@ -429,29 +500,92 @@ Plan* get_plan(mdb_engine* e, int H, int W) {
   return raw;
 }
 
+void launch_step(mdb_engine* e, Plan* P, Step& s, int n, cudaStream_t st);
 void run_network_eager(mdb_engine* e, Plan* P, int n, cudaStream_t st) {
-  for (auto& s : P->steps) {
-    switch (s.kind) {
-      case STEP_CONV: conv_launch(s.op, n, st); break;
-      case STEP_UPSAMPLE: upsample2x_launch(P->view(s.in), P->view(s.out), n, st); break;
-      case STEP_SPPF: {
-        const VBuf& b = P->bufs[s.in.buf];
-        const int hs = b.C / 4;
-        View cat = P->view(s.in);
-        View s1 = cat, p1 = cat, p2 = cat, p3 = cat;
-        s1.c_off = 0; p1.c_off = hs; p2.c_off = 2 * hs; p3.c_off = 3 * hs;
-        s1.C = p1.C = p2.C = p3.C = hs;
-        sppf_pool_launch(s1, p1, p2, p3, n, st);
-        break;
-      }
+  for (auto& s : P->steps) launch_step(e, P, s, n, st);
+}
+
+void launch_step(mdb_engine* e, Plan* P, Step& s, int n, cudaStream_t st) {
+  switch (s.kind) {
+    case STEP_CONV: conv_launch(s.op, n, st); break;
+    case STEP_UPSAMPLE: upsample2x_launch(P->view(s.in), P->view(s.out), n, st); break;
+    case STEP_SPPF: {
+      const VBuf& b = P->bufs[s.in.buf];
+      const int hs = b.C / 4;
+      View cat = P->view(s.in);
+      View s1 = cat, p1 = cat, p2 = cat, p3 = cat;
+      s1.c_off = 0; p1.c_off = hs; p2.c_off = 2 * hs; p3.c_off = 3 * hs;
+      s1.C = p1.C = p2.C = p3.C = hs;
+      sppf_pool_launch(s1, p1, p2, p3, n, st);
+      break;
     }
-    e->launches++;
+  }
+  e->launches++;
+}
+
+// Parity harness: eager pass that keeps dense copies of the selected steps' input, output and residual views (taken
+// right before / after the step runs, so in-place steps and arena reuse do not matter).
+void run_network_traced(mdb_engine* e, Plan* P, int n, cudaStream_t st) {
+  auto wanted = [&](const std::string& nm) {
+    if (e->trace_all) return true;
+    return std::find(e->trace_names.begin(), e->trace_names.end(), nm) != e->trace_names.end();
+  };
+  auto dense_bytes = [&](const VView& v, int C) {
+    const VBuf& b = P->bufs[v.buf];
+    return ((static_cast<size_t>(n) * b.H * b.W * C * (b.fp32 ? 4 : 2) + 255) / 256) * 256;
+  };
+  P->trace.clear();
+  size_t need = 0;
+  for (auto& s : P->steps) {
+    if (!wanted(s.name)) continue;
+    Plan::TraceRec r;
+    const VView vin = s.kind == STEP_SPPF ? VView{s.in.buf, 0, P->bufs[s.in.buf].C / 4} : s.in;
+    const VView views[3] = {vin, s.out, s.res};
+    for (int k = 0; k < 3; ++k) {
+      if (views[k].buf < 0) continue;
+      const VBuf& b = P->bufs[views[k].buf];
+      const int C = (k == 1 && s.kind == STEP_CONV) ? s.cout : views[k].C;
+      r.present[k] = true;
+      r.off[k] = need;
+      r.shape[k][0] = n; r.shape[k][1] = b.H; r.shape[k][2] = b.W; r.shape[k][3] = C;
+      if (k == 1) r.out_fp32 = b.fp32;
+      need += dense_bytes(views[k], C);
+    }
+    P->trace[s.name] = r;
+  }
+  if (need > P->trace_cap) {
+    if (P->trace_mem) MDB_CUDA(cudaFree(P->trace_mem));
+    P->trace_mem = nullptr; P->trace_cap = 0;
+    MDB_CUDA(cudaMalloc(&P->trace_mem, need));
+    P->trace_cap = need;
+  }
+  auto copy_view = [&](const VView& v, int C, size_t off) {
+    const VBuf& b = P->bufs[v.buf];
+    const size_t el = b.fp32 ? 4 : 2;
+    const char* src = static_cast<const char*>(P->arena) + b.offset + static_cast<size_t>(v.c_off) * el;
+    MDB_CUDA(cudaMemcpy2DAsync(static_cast<char*>(P->trace_mem) + off, C * el, src, static_cast<size_t>(b.C) * el, C * el,
+                               static_cast<size_t>(n) * b.H * b.W, cudaMemcpyDeviceToDevice, st));
+  };
+  for (auto& s : P->steps) {
+    auto it = P->trace.find(s.name);
+    if (it != P->trace.end()) {
+      const Plan::TraceRec& r = it->second;
+      const VView vin = s.kind == STEP_SPPF ? VView{s.in.buf, 0, P->bufs[s.in.buf].C / 4} : s.in;
+      copy_view(vin, r.shape[0][3], r.off[0]);
+      if (r.present[2]) copy_view(s.res, r.shape[2][3], r.off[2]);
+    }
+    launch_step(e, P, s, n, st);
+    if (it != P->trace.end()) copy_view(s.out, it->second.shape[1][3], it->second.off[1]);
   }
 }
 
 // The 167 launches of one forward pass are captured once per (plan, batch size) into a CUDA graph and replayed:
 // the host then spends ~10 us instead of ~2 ms per chunk on launches, and the kernels run back to back.
 void run_network(mdb_engine* e, Plan* P, int n, cudaStream_t st) {
+  if (e->trace_all || !e->trace_names.empty()) {
+    run_network_traced(e, P, n, st);
+    return;
+  }
   if (!e->use_graphs) {
     run_network_eager(e, P, n, st);
     return;
@@ -676,6 +810,11 @@ int batch_begin(mdb_engine* e, std::vector<ImgIn>& all, bool preprocessed, float
   const mdb_config& cfg = e->cfg;
   BatchState& B = e->batch;
   if (B.active) return fail(e, MDB_ERR_STATE, "a batch is already in progress");
+  if (e->tables.size() > 4096) {  // resize-coefficient tables are a few KB each; nothing is in flight here
+    cudaDeviceSynchronize();
+    for (auto& kv : e->tables) { cudaFree(kv.second.ofs); cudaFree(kv.second.coef); }
+    e->tables.clear();
+  }
   B = BatchState();
   B.active = true;
   B.thr = conf_thres;
@@ -863,7 +1002,9 @@ int mdb_create(mdb_engine** out, const mdb_config* cfg) {
       MDB_CUDA(cudaHostAlloc(&e->h_anchor[i], nd * sizeof(int32_t), cudaHostAllocDefault));
       for (int j = 0; j < 4; ++j) MDB_CUDA(cudaEventCreate(&e->ev_tt[i][j]));
     }
-    preprocess_init_constants();
+    preprocess_init_device();
+    conv_init_device();
+    if (const char* mp = getenv("MDB_MAX_PLANS")) e->max_plans = std::max(1, atoi(mp));
     const char* ng = getenv("MDB_NO_GRAPHS");
     e->use_graphs = !(ng && ng[0] == '1');
   } catch (const CudaError& ex) {
@@ -984,7 +1125,9 @@ int mdb_load_weights(mdb_engine* e, const mdb_tensor_desc* tensors, int32_t n) {
       }
     }
     e->plans.clear();  // plans hold weight pointers
+    e->plan_lru.clear();
     e->last_plan = nullptr;
+    for (int sl = 0; sl < 2; ++sl) { e->slot_plan[sl] = nullptr; e->slot_n[sl] = 0; }
     e->weights_loaded = true;
   } catch (const CudaError& ex) {
     return fail(e, MDB_ERR_CUDA, ex.msg);
@@ -1189,9 +1332,156 @@ int mdb_debug_fetch(mdb_engine* e, int32_t what, int32_t index, void* host_dst, 
   return MDB_OK;
 }
 
+
+int mdb_debug_set_trace(mdb_engine* e, const char* names) {
+  if (!e) return MDB_ERR_ARG;
+  e->trace_all = false;
+  e->trace_names.clear();
+  if (names == nullptr || names[0] == 0) return MDB_OK;
+  const std::string s(names);
+  if (s == "*") { e->trace_all = true; return MDB_OK; }
+  size_t b = 0;
+  while (b <= s.size()) {
+    const size_t c = s.find(',', b);
+    const std::string nm = s.substr(b, c == std::string::npos ? std::string::npos : c - b);
+    if (!nm.empty()) e->trace_names.push_back(nm);
+    if (c == std::string::npos) break;
+    b = c + 1;
+  }
+  return MDB_OK;
+}
+
+int mdb_debug_trace_names(mdb_engine* e, char* names_out, size_t cap, int32_t* n_steps) {
+  if (!e || !n_steps) return MDB_ERR_ARG;
+  if (!e->last_plan) return fail(e, MDB_ERR_STATE, "no batch has been run yet");
+  std::string all;
+  int n = 0;
+  for (auto& s : e->last_plan->steps) {
+    if (e->last_plan->trace.count(s.name) == 0) continue;
+    all += s.name;
+    all += '\n';
+    ++n;
+  }
+  *n_steps = n;
+  if (names_out && cap > 0) {
+    strncpy(names_out, all.c_str(), cap - 1);
+    names_out[cap - 1] = 0;
+  }
+  return MDB_OK;
+}
+
+int mdb_debug_fetch_trace(mdb_engine* e, const char* name, int32_t which, void* host_dst, size_t bytes, int64_t* shape5) {
+  if (!e || !name || which < 0 || which > 2) return MDB_ERR_ARG;
+  if (!e->last_plan) return fail(e, MDB_ERR_STATE, "no batch has been run yet");
+  try {
+    MDB_CUDA(cudaSetDevice(e->cfg.device));
+    Plan* P = e->last_plan;
+    auto it = P->trace.find(name);
+    if (it == P->trace.end()) return fail(e, MDB_ERR_ARG, std::string("step was not traced: ") + name);
+    const Plan::TraceRec& r = it->second;
+    const bool f32 = which == 1 && r.out_fp32;
+    int64_t shp[5] = {r.shape[which][0], r.shape[which][1], r.shape[which][2], r.shape[which][3], f32 ? 1 : 0};
+    if (!r.present[which]) shp[0] = shp[1] = shp[2] = shp[3] = 0;
+    if (shape5) memcpy(shape5, shp, sizeof(shp));
+    if (host_dst && r.present[which]) {
+      const size_t need = static_cast<size_t>(shp[0]) * shp[1] * shp[2] * shp[3] * (f32 ? 4 : 2);
+      if (bytes < need) return fail(e, MDB_ERR_ARG, "destination too small");
+      MDB_CUDA(cudaStreamSynchronize(e->st_compute));
+      MDB_CUDA(cudaMemcpy(host_dst, static_cast<char*>(P->trace_mem) + r.off[which], need, cudaMemcpyDeviceToHost));
+    }
+  } catch (const CudaError& ex) {
+    return fail(e, MDB_ERR_CUDA, ex.msg);
+  }
+  return MDB_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // single-kernel entry points (parity tests)
 // ---------------------------------------------------------------------------------------------
+int mdb_op_upsample2x(mdb_engine* e, const void* src_fp16, int32_t n, int32_t h, int32_t w, int32_t c, void* dst_fp16) {
+  if (!e || !src_fp16 || !dst_fp16 || n <= 0 || h <= 0 || w <= 0 || c <= 0 || c % 8 != 0) return fail(e, MDB_ERR_ARG, "bad argument");
+  void *d_s = nullptr, *d_d = nullptr;
+  int rc = MDB_OK;
+  try {
+    MDB_CUDA(cudaSetDevice(e->cfg.device));
+    const size_t sb = static_cast<size_t>(n) * h * w * c * 2, db = sb * 4;
+    MDB_CUDA(cudaMalloc(&d_s, sb));
+    MDB_CUDA(cudaMalloc(&d_d, db));
+    MDB_CUDA(cudaMemcpy(d_s, src_fp16, sb, cudaMemcpyHostToDevice));
+    MDB_CUDA(cudaMemset(d_d, 0xFF, db));
+    View s, d;
+    s.base = d_s; s.N = n; s.H = h; s.W = w; s.Ctot = c; s.C = c;
+    d.base = d_d; d.N = n; d.H = 2 * h; d.W = 2 * w; d.Ctot = c; d.C = c;
+    upsample2x_launch(s, d, n, e->st_compute);
+    e->launches++;
+    MDB_CUDA(cudaStreamSynchronize(e->st_compute));
+    MDB_CUDA(cudaMemcpy(dst_fp16, d_d, db, cudaMemcpyDeviceToHost));
+  } catch (const CudaError& ex) {
+    rc = fail(e, MDB_ERR_CUDA, ex.msg);
+  }
+  cudaFree(d_s); cudaFree(d_d);
+  return rc;
+}
+
+int mdb_op_sppf_pool(mdb_engine* e, const void* s1_fp16, int32_t n, int32_t h, int32_t w, int32_t c, void* cat_fp16) {
+  if (!e || !s1_fp16 || !cat_fp16 || n <= 0 || h <= 0 || w <= 0 || c <= 0 || c % 8 != 0) return fail(e, MDB_ERR_ARG, "bad argument");
+  void* d_cat = nullptr;
+  int rc = MDB_OK;
+  try {
+    MDB_CUDA(cudaSetDevice(e->cfg.device));
+    const size_t npix = static_cast<size_t>(n) * h * w;
+    MDB_CUDA(cudaMalloc(&d_cat, npix * 4 * c * 2));
+    MDB_CUDA(cudaMemset(d_cat, 0xFF, npix * 4 * c * 2));
+    MDB_CUDA(cudaMemcpy2D(d_cat, static_cast<size_t>(4) * c * 2, s1_fp16, static_cast<size_t>(c) * 2, static_cast<size_t>(c) * 2, npix,
+                          cudaMemcpyHostToDevice));
+    View v[4];
+    for (int i = 0; i < 4; ++i) { v[i].base = d_cat; v[i].N = n; v[i].H = h; v[i].W = w; v[i].Ctot = 4 * c; v[i].c_off = i * c; v[i].C = c; }
+    sppf_pool_launch(v[0], v[1], v[2], v[3], n, e->st_compute);
+    e->launches++;
+    MDB_CUDA(cudaStreamSynchronize(e->st_compute));
+    MDB_CUDA(cudaMemcpy(cat_fp16, d_cat, npix * 4 * c * 2, cudaMemcpyDeviceToHost));
+  } catch (const CudaError& ex) {
+    rc = fail(e, MDB_ERR_CUDA, ex.msg);
+  }
+  cudaFree(d_cat);
+  return rc;
+}
+
+int mdb_op_decode(mdb_engine* e, const float* const* raw4, const int32_t* ny4, const int32_t* nx4, int32_t n, float* pred) {
+  if (!e || !raw4 || !ny4 || !nx4 || !pred || n <= 0) return fail(e, MDB_ERR_ARG, "bad argument");
+  float* d_raw[4] = {nullptr, nullptr, nullptr, nullptr};
+  float* d_pred = nullptr;
+  int rc = MDB_OK;
+  try {
+    MDB_CUDA(cudaSetDevice(e->cfg.device));
+    const int no = e->cfg.arch.nc + 5;
+    const int craw = ((3 * no + 3) / 4) * 4;
+    const float strides[4] = {8.f, 16.f, 32.f, 64.f};
+    DecodeLevel lv[4];
+    int off = 0;
+    for (int l = 0; l < 4; ++l) {
+      const size_t b = static_cast<size_t>(n) * ny4[l] * nx4[l] * craw * 4;
+      MDB_REQUIRE(raw4[l] != nullptr && ny4[l] > 0 && nx4[l] > 0, "bad level");
+      MDB_CUDA(cudaMalloc(&d_raw[l], b));
+      MDB_CUDA(cudaMemcpy(d_raw[l], raw4[l], b, cudaMemcpyHostToDevice));
+      lv[l].raw = d_raw[l]; lv[l].ny = ny4[l]; lv[l].nx = nx4[l]; lv[l].c_stride = craw; lv[l].stride = strides[l]; lv[l].row_off = off;
+      for (int a = 0; a < 3; ++a) { lv[l].anchors[a][0] = e->cfg.arch.anchors_px[l][a][0]; lv[l].anchors[a][1] = e->cfg.arch.anchors_px[l][a][1]; }
+      off += 3 * ny4[l] * nx4[l];
+    }
+    const size_t pb = static_cast<size_t>(n) * off * no * 4;
+    MDB_CUDA(cudaMalloc(&d_pred, pb));
+    decode_launch(lv, n, no, off, d_pred, e->st_compute);
+    e->launches++;
+    MDB_CUDA(cudaStreamSynchronize(e->st_compute));
+    MDB_CUDA(cudaMemcpy(pred, d_pred, pb, cudaMemcpyDeviceToHost));
+  } catch (const CudaError& ex) {
+    rc = fail(e, MDB_ERR_CUDA, ex.msg);
+  }
+  for (int l = 0; l < 4; ++l) cudaFree(d_raw[l]);
+  cudaFree(d_pred);
+  return rc;
+}
+
 int mdb_op_letterbox(mdb_engine* e, const uint8_t* rgb_hwc, int32_t h, int32_t w, int64_t row_stride, void* dst_fp16,
                      int32_t* out_hw2) {
   if (!e || !rgb_hwc || !dst_fp16 || h <= 0 || w <= 0) return fail(e, MDB_ERR_ARG, "null argument");

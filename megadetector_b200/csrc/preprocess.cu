@@ -226,19 +226,19 @@ void preprocess_launch(const PreImage* d_imgs, int n, int out_h, int out_w, __ha
   const int row_bytes = ((src_cols * 3 + 15 + 15) / 16) * 16;
   const size_t tile_bytes = static_cast<size_t>(kTileH2) * kHaloW2 * 32;
   const size_t smem = tile_bytes + static_cast<size_t>(row_bytes) * src_rows;
-  static size_t attr = 0;
-  if (smem <= 200 * 1024) {
-    if (smem > 48 * 1024 && smem > attr) {
-      MDB_CUDA(cudaFuncSetAttribute(letterbox_s2d_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    static_cast<int>(smem)));
-      attr = smem;
-    }
+  if (smem <= 200 * 1024) {  // opted in per device by preprocess_init_device()
     letterbox_s2d_kernel<true><<<grid, kPreThreads, smem, st>>>(d_imgs, out_h, out_w, dst, row_bytes, src_rows);
   } else {
     // extreme down-scales (source window larger than shared memory): read through L1 instead
     letterbox_s2d_kernel<false><<<grid, kPreThreads, tile_bytes, st>>>(d_imgs, out_h, out_w, dst, 0, 0);
   }
   MDB_CUDA(cudaGetLastError());
+}
+
+// per-device setup (mdb_create, after cudaSetDevice): cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute
+void preprocess_init_device() {
+  preprocess_init_constants();
+  MDB_CUDA(cudaFuncSetAttribute(letterbox_s2d_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
 }
 
 }  // namespace mdb

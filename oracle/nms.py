@@ -139,3 +139,37 @@ def nms_torch(prediction, conf_thres=0.25, iou_thres=0.45, max_det=300):
         d = d[d[:, 4].argsort(descending=True)][:max_det]
         out.append(d)
     return out
+
+
+def nms_torch_indexed(pred, conf_thres=0.25, iou_thres=0.45, max_det=300):
+    """
+    `nms_torch` for ONE image that also returns the kept anchor indices: (det [N,6] float32 numpy, anchor_idx [N] int64).
+    Same ATen ops + torchvision.ops.nms C++ kernel the reference calls (pytorch_detector.py:529-606); used by the parity
+    tests where every anchor is a candidate (61 200 per image) and the numpy loop above would take minutes.  Checked
+    against `nms_one_image` in tests/test_oracle_nms.py.  Ties among equal confidences: torch's final argsort is
+    unstable, so callers compare tie groups as sets (tests/helpers.py).
+    """
+    import torch
+    import torchvision
+    x = torch.as_tensor(pred, dtype=torch.float32)
+    idx = torch.nonzero(x[:, 4] > conf_thres).flatten()
+    x = x[idx]
+    if x.shape[0] == 0:
+        return np.zeros((0, 6), np.float32), np.zeros((0,), np.int64)
+    half = x[:, 2:4] / 2.0
+    box = torch.cat((x[:, 0:2] - half, x[:, 0:2] + half), 1)
+    conf, cls = (x[:, 5:] * x[:, 4:5]).max(1)
+    m = conf > conf_thres
+    box, conf, cls, idx = box[m], conf[m], cls[m], idx[m]
+    parts, anchors = [], []
+    for c in cls.unique():
+        cm = cls == c
+        keep = torchvision.ops.nms(box[cm], conf[cm], iou_thres)
+        parts.append(torch.cat((box[cm][keep], conf[cm][keep, None], torch.full((len(keep), 1), float(c))), 1))
+        anchors.append(idx[cm][keep])
+    if not parts:
+        return np.zeros((0, 6), np.float32), np.zeros((0,), np.int64)
+    d = torch.cat(parts, 0)
+    a = torch.cat(anchors, 0)
+    order = torch.argsort(d[:, 4].double(), descending=True, stable=True)[:max_det]
+    return d[order].numpy(), a[order].numpy()

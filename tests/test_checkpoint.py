@@ -132,8 +132,8 @@ def synth_weights_default_anchors():
 
 def test_synthetic_specs():
     assert checkpoint.is_synthetic('synthetic://yolov5x6?seed=3')
-    arch, seed = checkpoint._parse_synthetic('synthetic://yolov5x6?seed=3')
+    arch, seed, _ = checkpoint._parse_synthetic('synthetic://yolov5x6?seed=3')
     assert seed == 3 and tuple(arch['ch']) == (80, 160, 320, 640, 960, 1280)
-    arch, seed = checkpoint._parse_synthetic('synthetic://mdv5b')
+    arch, seed, _ = checkpoint._parse_synthetic('synthetic://mdv5b')
     assert seed == 1
     assert len(synth_weights._specs(**{k: arch[k] for k in ('ch', 'n_backbone', 'n_head', 'nc')})) == 163

@@ -63,3 +63,16 @@ def test_torchvision_backed_variant_agrees():
         res = onms.nms_torch(torch.from_numpy(pred.copy()), conf_thres=thr, iou_thres=iou)
         for b, det in enumerate(res):
             assert_dets_equal_modulo_ties(z['{}/det{}'.format(name, b)], det.numpy(), '{}[{}]'.format(name, b))
+
+
+def test_indexed_torch_variant_agrees_with_goldens_and_numpy_anchors():
+    from helpers import assert_anchors_equal_modulo_ties
+    z, names = _cases()
+    for name in names:
+        pred = z[name + '/pred']
+        thr, iou = z[name + '/thr']
+        for b in range(pred.shape[0]):
+            det, anc = onms.nms_torch_indexed(pred[b], float(thr), float(iou))
+            assert_dets_equal_modulo_ties(z['{}/det{}'.format(name, b)], det, '{}[{}]'.format(name, b))
+            ndet, nanc = onms.nms_one_image(pred[b], thr, iou)
+            assert_anchors_equal_modulo_ties(ndet[:, 4], nanc, det[:, 4], anc, '{}[{}]'.format(name, b))
