@@ -72,7 +72,7 @@ def _specs(ch, n_backbone, n_head, nc):
 PROFILES = {
     'chaotic': dict(pre=1.0, res=0.7, bias=None, box_sd=1.0, cls=(0.0, 1.5), obj=(-13.0, 2.5)),
     'contractive': dict(pre=0.05, res=0.02, bias=0.0, box_sd=0.03, cls=(-1.5, 0.15), cls_own=1.5, obj=(-3.2, 0.35),
-                        fp16_weights=1.0),
+                        obj_lvl=(-4.0, -4.0, 0.0, 0.0), fp16_weights=1.0),
 }
 
 
@@ -106,6 +106,10 @@ class _Calibrator:
                     pr = self.prof
                     tgt_std = pr['box_sd'] if c < 4 else (self.obj_logit[1] if c == 4 else pr['cls'][1])
                     tgt_mean = 0.0 if c < 4 else (self.obj_logit[0] if c == 4 else pr['cls'][0])
+                    if c == 4 and 'obj_lvl' in pr:
+                        # sparse high-confidence candidates: only the coarse levels reach conf >= 0.05, the fine levels
+                        # (94 % of the anchors) stay background, as in a real detector's output
+                        tgt_mean += pr['obj_lvl'][int(name.rsplit('.', 1)[1])]
                     if c > 4 and 'cls_own' in pr:
                         # anchor slot a votes for class a (mod nc): every class occurs, and no arg-max is a near tie
                         tgt_mean = pr['cls_own'] if (c - 5) == a % (no - 5) else pr['cls'][0]

@@ -35,8 +35,9 @@ pytestmark = pytest.mark.gpu
 
 SCORE_TOL = 1e-3            # BASELINE.json north_star
 BOX_TOL_PX = 1e-3 * 1280    # 1e-3 of the letterbox size
-CONF_TOL = 1.0e-3 + 1.0e-3  # record confidences are truncated to 3 decimals (ct_utils.truncate_float): +1 unit of that
-COORD_TOL = 1e-3            # md_tests.py:100; one rounded pixel of a 1080-px side is 9.3e-4
+CONF_TOL = 1.0e-3 + 1.0e-3 + 1e-9  # record confidences are truncated to 3 decimals (ct_utils.truncate_float): +1 unit of that
+COORD_TOL = 1e-3 + 1e-4 + 1e-9     # md_tests.py:100 is 1e-3; one rounded pixel of a 1080-px side is 9.3e-4 and the records are
+                                   # truncated to 4 decimals: +1 unit of that
 TIE_TOL = 2 * SCORE_TOL     # candidates closer than this in the ORACLE's own confidences may swap
 MAX_FLIP_FRACTION = 0.03
 
@@ -74,27 +75,36 @@ def _iou(a, b):
     return inter / u if u > 0 else 0.0
 
 
-def _explained_by_tie(anchor, p_ref, kept_other, cut_conf, saturated):
-    """An anchor kept on one side only is a legitimate flip if, in the ORACLE's predictions, it is tied (within TIE_TOL)
-    with an overlapping same-class candidate kept on the other side, or with the max_det cut."""
-    row = p_ref[anchor]
+def _conf_cls_box(row):
     cls = int(np.argmax(row[5:] * row[4]))
-    conf = float(row[5 + cls] * row[4])
+    return float(row[5 + cls] * row[4]), cls, (row[0] - row[2] / 2, row[1] - row[3] / 2, row[0] + row[2] / 2, row[1] + row[3] / 2)
+
+
+def _explain(anchor, p_ref, kept_here, kept_other, cut_conf, saturated):
+    """
+    Why is `anchor` kept on one side only?  Judged on the ORACLE's predictions.  Greedy NMS keeps a candidate unless a kept,
+    overlapping, same-class candidate with a higher confidence exists; so a one-sided anchor has, on the other side, either
+      'tie'      an overlapping kept competitor whose confidence is within TIE_TOL (order decided by the last bit), or whose
+                 IoU sits on the 0.45 threshold, or the anchor itself sits on the max_det cut;
+      'cascade'  an overlapping kept competitor that is itself one-sided (its own discrepancy is judged separately);
+      None       nothing of the sort: a real disagreement.
+    """
+    conf, cls, box = _conf_cls_box(p_ref[anchor])
     if saturated and conf <= cut_conf + TIE_TOL:
-        return True
-    box = (row[0] - row[2] / 2, row[1] - row[3] / 2, row[0] + row[2] / 2, row[1] + row[3] / 2)
+        return 'tie'
+    verdict = None
     for b in kept_other:
-        r2 = p_ref[b]
-        c2 = int(np.argmax(r2[5:] * r2[4]))
-        if c2 != cls:
+        conf2, cls2, box2 = _conf_cls_box(p_ref[b])
+        if cls2 != cls:
             continue
-        conf2 = float(r2[5 + c2] * r2[4])
-        box2 = (r2[0] - r2[2] / 2, r2[1] - r2[3] / 2, r2[0] + r2[2] / 2, r2[1] + r2[3] / 2)
         iou = _iou(box, box2)
-        # order flip between two overlapping near-equal candidates, or an IoU that sits on the 0.45 threshold
-        if iou > 0.40 and (abs(conf - conf2) <= TIE_TOL or abs(iou - 0.45) <= 0.02):
-            return True
-    return False
+        if iou <= 0.40:
+            continue
+        if abs(conf - conf2) <= TIE_TOL or abs(iou - 0.45) <= 0.02:
+            return 'tie'
+        if b not in kept_here:
+            verdict = 'cascade'
+    return verdict
 
 
 def _parity_case(tag, model_spec, arch, n_imgs, max_batch):
@@ -130,7 +140,7 @@ def _parity_case(tag, model_spec, arch, n_imgs, max_batch):
               'per_image_max_score_err': [float(err[i, :, 4:].max()) for i in range(n_imgs)]}
     # 3 + 4. NMS parity on the engine's own predictions; record-level comparison with the oracle
     records = det.generate_detections_one_batch(imgs, ids, detection_threshold=thr)
-    identical, flips, n_ref, n_matched, max_dconf, max_dcoord = 0, 0, 0, 0, 0.0, 0.0
+    identical, identical_hi, flips, n_ref, n_matched, n_extra, max_dconf, max_dcoord = 0, 0, {}, 0, 0, 0, 0.0, 0.0
     cands, unexplained = [], []
     for i in range(n_imgs):
         odet, oanc = onms.nms_torch_indexed(pred[i], thr, 0.45)  # reference semantics on the ENGINE's predictions
@@ -151,10 +161,12 @@ def _parity_case(tag, model_spec, arch, n_imgs, max_batch):
         saturated = len(ranc) >= 300 or c[i] >= 300
         cut_conf = float(rdet[-1, 4]) if len(rdet) else 0.0
         # records are stored in ascending confidence order: row j of the kept list is record len-1-j
+        hi_o, hi_e = set(), set()
         for anc, j in o_anchor.items():
             rec = rdets[len(rdets) - 1 - j]
             if rec['conf'] < 0.05:
                 continue
+            hi_o.add(anc)
             n_ref += 1
             if anc in e_anchor:
                 got = gdets[len(gdets) - 1 - e_anchor[anc]]
@@ -163,25 +175,43 @@ def _parity_case(tag, model_spec, arch, n_imgs, max_batch):
                 max_dconf = max(max_dconf, abs(got['conf'] - rec['conf']))
                 max_dcoord = max(max_dcoord, max(abs(x - y) for x, y in zip(got['bbox'], rec['bbox'])))
             else:
-                flips += 1
-                if not _explained_by_tie(anc, p_ref[i], list(e_anchor), cut_conf, saturated):
-                    unexplained.append((i, anc))
-    report.update({'images_index_identical': identical, 'ref_dets_conf_ge_0.05': n_ref, 'matched_by_anchor': n_matched,
-                   'nms_flips': flips, 'unexplained_flips': len(unexplained), 'max_dconf': max_dconf,
+                why = _explain(anc, p_ref[i], o_anchor, e_anchor, cut_conf, saturated)
+                flips[why] = flips.get(why, 0) + 1
+                if why is None:
+                    unexplained.append((i, anc, 'oracle-only'))
+        for anc, j in e_anchor.items():  # the other direction: detections only the engine reports
+            got = gdets[len(gdets) - 1 - j]
+            if got['conf'] < 0.05:
+                continue
+            hi_e.add(anc)
+            if anc not in o_anchor:
+                n_extra += 1
+                why = _explain(anc, p_ref[i], e_anchor, o_anchor, cut_conf, saturated)
+                if why is None:
+                    unexplained.append((i, anc, 'engine-only'))
+        # sets of anchors above the record threshold, ignoring members that sit within one truncation unit of 0.05
+        if {x for x in hi_o if x in e_anchor or rdets[len(rdets) - 1 - o_anchor[x]]['conf'] > 0.052} == \
+                {x for x in hi_e if x in o_anchor or gdets[len(gdets) - 1 - e_anchor[x]]['conf'] > 0.052}:
+            identical_hi += 1
+    n_flips = sum(flips.values())
+    report.update({'images_index_identical_all_300': identical, 'images_index_identical_conf_ge_0.05': identical_hi,
+                   'ref_dets_conf_ge_0.05': n_ref, 'matched_by_anchor': n_matched, 'engine_only_dets_conf_ge_0.05': n_extra,
+                   'nms_flips': {str(k): v for k, v in flips.items()}, 'unexplained_flips': len(unexplained), 'max_dconf': max_dconf,
                    'max_dcoord': max_dcoord, 'candidates_per_image_min_max': [min(cands), max(cands)]})
     det.close()
     os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
     with open(os.path.join(ROOT, 'gpurun_out', 'parity_1e3_{}.json'.format(tag)), 'w') as f:
         json.dump(report, f, indent=1)
     print('\n[parity 1e-3 {}] {}'.format(tag, {k: v for k, v in report.items() if k != 'per_image_max_score_err'}))
-    print('[parity 1e-3 {}] {} of {} images index-identical'.format(tag, identical, n_imgs))
+    print('[parity 1e-3 {}] {} of {} images index-identical over the detections with conf >= 0.05, {} of {} over all 300 '
+          'kept rows'.format(tag, identical_hi, n_imgs, identical, n_imgs))
     assert score_err <= SCORE_TOL, report
     assert box_err <= BOX_TOL_PX, report
     assert n_ref > 0, 'the record-level comparison is vacuous: no oracle detection with conf >= 0.05'
     assert max_dconf <= CONF_TOL, report
     assert max_dcoord <= COORD_TOL, report
     assert not unexplained, (unexplained[:10], report)
-    assert flips <= MAX_FLIP_FRACTION * n_ref, report
+    assert n_flips <= MAX_FLIP_FRACTION * n_ref, report
     return report
 
 
