@@ -36,8 +36,8 @@ pytestmark = pytest.mark.gpu
 SCORE_TOL = 1e-3            # BASELINE.json north_star
 BOX_TOL_PX = 1e-3 * 1280    # 1e-3 of the letterbox size
 CONF_TOL = 1.0e-3 + 1.0e-3 + 1e-9  # record confidences are truncated to 3 decimals (ct_utils.truncate_float): +1 unit of that
-COORD_TOL = 1e-3 + 1e-4 + 1e-9     # md_tests.py:100 is 1e-3; one rounded pixel of a 1080-px side is 9.3e-4 and the records are
-                                   # truncated to 4 decimals: +1 unit of that
+COORD_TOL = 2e-3                   # md_tests.py:100 is 1e-3; boxes are ROUNDED to whole pixels before they are normalised (:1379), one
+                                   # pixel of a 1080-px side is 9.3e-4, and a width / height can move by two (both edges flip)
 TIE_TOL = 2 * SCORE_TOL     # candidates closer than this in the ORACLE's own confidences may swap
 MAX_FLIP_FRACTION = 0.03
 
