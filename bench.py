@@ -107,7 +107,7 @@ def run_reference(args, rank, world):
     from oracle import yolov5 as oy
     from oracle.detector import OracleDetector
     cores = _best_cpu_threads()
-    weights, _ = checkpoint.load_model(MODEL)
+    weights, _ = checkpoint.load_model(args.model)
     ora = OracleDetector(weights, oy.Arch(), fast_nms=True)
     per_step = max(1, args.ref_images)
     imgs = [synth_image(i, SRC_H, SRC_W) for i in range(per_step)]
@@ -148,6 +148,8 @@ def main():
     ap.add_argument('--ref-images', type=int, default=4, help='images per step of the CPU reference arm')
     ap.add_argument('--cpu-baseline-images', type=int, default=6)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-incumbent', action='store_true', help='skip the stock PyTorch/cuDNN timing on the same GPU')
+    ap.add_argument('--model', default=MODEL, help='model spec (config 4: synthetic://mdv5b) or a .pt file')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
@@ -175,7 +177,7 @@ def main():
 
     B = args.batch
     W = max(3, args.warmup)
-    det = B200Detector(MODEL, {'max_batch': B, 'device': 'cuda:%d' % local_rank})
+    det = B200Detector(args.model, {'max_batch': B, 'device': 'cuda:%d' % local_rank})
     eng = det.engine
     if os.environ.get('MDB_SPLIT'):
         eng.set_pipeline_split(int(os.environ['MDB_SPLIT']))
@@ -248,7 +250,7 @@ def main():
             'data': 'synthetic',
             'config': {'workload': 'MDv5a-shape YOLOv5x6 (calibrated random init, no checkpoint offline), bs={} per GPU, '
                                    '1920x1080 RGB u8 -> letterbox 768x1280, conf_thres 1e-5, image-sharded'.format(B),
-                       'pool_images_per_rank': POOL, 'l2': 'inputs per step ({:.0f} MB u8 + activations) exceed the 126 MB L2'.format(h2d / 1e6),
+                       'model': args.model, 'pool_images_per_rank': POOL, 'l2': 'inputs per step ({:.0f} MB u8 + activations) exceed the 126 MB L2'.format(h2d / 1e6),
                        'detections_last_batch': n_dets},
             'e2e': {'value': e2e_v, 'unit': 'images/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                     'ms_per_step': e2e_ms / args.steps, 'api': 'B200Detector.generate_detections_one_batch (pinned host images in, records out)',
@@ -266,9 +268,16 @@ def main():
             'clocks': sampler.summary(),
         }
         if not args.no_cpu_baseline and world == 1:
-            line['cpu_baseline'] = cpu_baseline(args.cpu_baseline_images)
-        print(json.dumps(line), flush=True)
+            line['cpu_baseline'] = cpu_baseline(args.cpu_baseline_images, args.model)
     det.close()
+    if rank == 0:
+        if not args.no_incumbent and world == 1:
+            # outside every timed region, after the engine has been destroyed: the incumbent on the same box
+            try:
+                line['incumbent'] = incumbent(args.model, B)
+            except Exception as e:  # it is a reported side figure: never lose the bench line over it
+                line['incumbent'] = {'error': str(e)[:200]}
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -296,7 +305,48 @@ def _best_cpu_threads():
     return best
 
 
-def cpu_baseline(n_images):
+def incumbent(model, batch, iters=3):
+    """
+    BASELINE.md par. 4/6: what the reference's GPU path costs on THIS box -- the same module graph (oracle.yolov5.forward)
+    through stock PyTorch/cuDNN on cuda:0, with torch's default TF32 convolutions (the reference's setting) and with
+    `.half()` weights/activations.  Forward pass only (no letterbox, no NMS), inputs resident, CUDA events.  A reported
+    side figure, timed after (and outside) every region of the engine's own numbers.
+    """
+    import torch
+    from megadetector_b200 import checkpoint
+    from oracle import yolov5 as oy
+    weights, arch = checkpoint.load_model(model)
+    a = oy.Arch(ch=list(arch['ch']), n_backbone=list(arch['n_backbone']), n_head=arch['n_head'], nc=arch['nc'])
+    dev = torch.device('cuda')
+    out = {'what': 'oracle.yolov5.forward (the reference\'s module graph) via stock PyTorch/cuDNN, forward only, '
+                   'bs={} x 3x768x1280, {} timed iterations after 2 warm-ups'.format(batch, iters), 'torch': torch.__version__}
+    for tag, dtype, tf32 in (('tf32', torch.float32, True), ('fp16', torch.float16, False)):
+        torch.backends.cudnn.allow_tf32 = tf32
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+        torch.backends.cudnn.benchmark = True
+        wd = {k: v.to(dev, dtype) for k, v in weights.items()}
+        x = torch.rand(batch, 3, LB_H, LB_W, device=dev, dtype=dtype)
+        with torch.no_grad():
+            for _ in range(2):
+                oy.forward(x, wd, a)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(iters):
+                oy.forward(x, wd, a)
+            e1.record()
+            torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / iters
+        out[tag] = {'ms_per_batch': ms, 'images_per_s': batch / (ms / 1000.0),
+                    'conv_tflops': batch * GFLOP_PER_IMAGE / 1000.0 / (ms / 1000.0)}
+        del wd, x
+        torch.cuda.empty_cache()
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    return out
+
+
+def cpu_baseline(n_images, model=MODEL):
     """The CPU oracle of the same path on the box's host cores, bounded sample (reported baseline, not a target)."""
     import torch
     from megadetector_b200 import checkpoint
@@ -304,7 +354,7 @@ def cpu_baseline(n_images):
     from oracle import yolov5 as oy
     from oracle.detector import OracleDetector
     cores = _best_cpu_threads()
-    weights, _ = checkpoint.load_model(MODEL)
+    weights, _ = checkpoint.load_model(model)
     ora = OracleDetector(weights, oy.Arch(), fast_nms=True)
     imgs = [synth_image(i, SRC_H, SRC_W) for i in range(n_images + 1)]
     ora.generate_detections_one_batch(imgs[:1], ['w'], CONF_THRES)

@@ -1,4 +1,5 @@
-"""Import-time stand-in for `jsonpickle` (absent offline); only what the reference touches at import."""
+"""Minimal stand-in for the `jsonpickle` package (absent offline; the reference imports it at module load time in
+utils/ct_utils.py and uses it only for pretty-printing objects).  Test infrastructure."""
 import json
 
 
