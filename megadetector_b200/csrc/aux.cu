@@ -4,6 +4,7 @@
 #include <cfloat>
 
 #include "common.h"
+#include "nms_cand.cuh"
 
 namespace mdb {
 
@@ -113,40 +114,62 @@ struct DecodeArgs {
 
 __device__ __forceinline__ float sigmoid_acc(float x) { return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x))); }
 
+// With `keys != nullptr` the kernel also runs K6 on the row it just produced (confidence threshold, best class,
+// candidate key append; see nms.cu): the prediction tensor is thresholded at HBM rate by the thread that wrote it.
 __global__ void decode_kernel(const DecodeArgs args, int no, int rows_per_img, float* __restrict__ pred,
-                              long long total_rows) {
+                              long long total_rows, float thr, unsigned long long* __restrict__ keys,
+                              int32_t* __restrict__ counts, int cap) {
   const long long r = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (r >= total_rows) return;
-  const int n = static_cast<int>(r / rows_per_img);
-  const int row = static_cast<int>(r - static_cast<long long>(n) * rows_per_img);
-  int l = 0;
+  const bool in = r < total_rows;
+  int n = -1, row = 0;
+  bool ok = false;
+  float conf = 0.0f;
+  if (in) {
+    n = static_cast<int>(r / rows_per_img);
+    row = static_cast<int>(r - static_cast<long long>(n) * rows_per_img);
+    int l = 0;
 #pragma unroll
-  for (int i = 1; i < 4; ++i)
-    if (row >= args.lv[i].row_off) l = i;
-  const DecodeLevel& L = args.lv[l];
-  const int local = row - L.row_off;
-  const int ix = local % L.nx;
-  const int iy = (local / L.nx) % L.ny;
-  const int a = local / (L.nx * L.ny);
-  const float* src = L.raw + ((static_cast<long long>(n) * L.ny + iy) * L.nx + ix) * L.c_stride + a * no;
-  float* dst = pred + r * no;
-  const float s0 = sigmoid_acc(src[0]), s1 = sigmoid_acc(src[1]), s2 = sigmoid_acc(src[2]), s3 = sigmoid_acc(src[3]);
-  dst[0] = __fmul_rn(__fadd_rn(__fmul_rn(s0, 2.0f), static_cast<float>(ix) - 0.5f), L.stride);
-  dst[1] = __fmul_rn(__fadd_rn(__fmul_rn(s1, 2.0f), static_cast<float>(iy) - 0.5f), L.stride);
-  const float w2 = __fmul_rn(s2, 2.0f), h2 = __fmul_rn(s3, 2.0f);
-  dst[2] = __fmul_rn(__fmul_rn(w2, w2), L.anchors[a][0]);
-  dst[3] = __fmul_rn(__fmul_rn(h2, h2), L.anchors[a][1]);
-  for (int c = 4; c < no; ++c) dst[c] = sigmoid_acc(src[c]);
+    for (int i = 1; i < 4; ++i)
+      if (row >= args.lv[i].row_off) l = i;
+    const DecodeLevel& L = args.lv[l];
+    const int local = row - L.row_off;
+    const int ix = local % L.nx;
+    const int iy = (local / L.nx) % L.ny;
+    const int a = local / (L.nx * L.ny);
+    const float* src = L.raw + ((static_cast<long long>(n) * L.ny + iy) * L.nx + ix) * L.c_stride + a * no;
+    float* dst = pred + r * no;
+    const float s0 = sigmoid_acc(src[0]), s1 = sigmoid_acc(src[1]), s2 = sigmoid_acc(src[2]), s3 = sigmoid_acc(src[3]);
+    dst[0] = __fmul_rn(__fadd_rn(__fmul_rn(s0, 2.0f), static_cast<float>(ix) - 0.5f), L.stride);
+    dst[1] = __fmul_rn(__fadd_rn(__fmul_rn(s1, 2.0f), static_cast<float>(iy) - 0.5f), L.stride);
+    const float w2 = __fmul_rn(s2, 2.0f), h2 = __fmul_rn(s3, 2.0f);
+    dst[2] = __fmul_rn(__fmul_rn(w2, w2), L.anchors[a][0]);
+    dst[3] = __fmul_rn(__fmul_rn(h2, h2), L.anchors[a][1]);
+    const float obj = sigmoid_acc(src[4]);
+    dst[4] = obj;
+    float best = -INFINITY;
+    for (int c = 5; c < no; ++c) {
+      const float p = sigmoid_acc(src[c]);
+      dst[c] = p;
+      // reference nms(): x[:, 5:] *= x[:, 4:5]; conf = max over classes (first maximum), pytorch_detector.py:560-575
+      const float cc = __fmul_rn(p, obj);
+      if (cc > best) best = cc;
+    }
+    ok = keys != nullptr && obj > thr && best > thr;
+    conf = best;
+  }
+  if (keys != nullptr) cand_append(ok, n, row, conf, keys, counts, cap);
 }
 
-void decode_launch(const DecodeLevel* lv4, int n_img, int no, int rows_per_img, float* pred, cudaStream_t st) {
+void decode_launch(const DecodeLevel* lv4, int n_img, int no, int rows_per_img, float* pred, cudaStream_t st, float thr,
+                   unsigned long long* cand_keys, int32_t* cand_counts, int cand_cap) {
   DecodeArgs args;
   for (int i = 0; i < 4; ++i) args.lv[i] = lv4[i];
   const long long total = static_cast<long long>(n_img) * rows_per_img;
   if (total == 0) return;
+  if (cand_keys != nullptr) MDB_CUDA(cudaMemsetAsync(cand_counts, 0, sizeof(int32_t) * n_img, st));
   const int threads = 256;
-  decode_kernel<<<static_cast<unsigned>((total + threads - 1) / threads), threads, 0, st>>>(args, no, rows_per_img,
-                                                                                          pred, total);
+  decode_kernel<<<static_cast<unsigned>((total + threads - 1) / threads), threads, 0, st>>>(
+      args, no, rows_per_img, pred, total, thr, cand_keys, cand_counts, cand_cap);
   MDB_CUDA(cudaGetLastError());
 }
 

@@ -132,7 +132,9 @@ struct DecodeLevel {
   float anchors[3][2];
   int row_off;
 };
-void decode_launch(const DecodeLevel* lv4, int n_img, int no, int rows_per_img, float* pred, cudaStream_t st);
+// thr / cand_*: when cand_keys != nullptr the kernel also runs the candidate pass (K6, nms.cu) on the rows it writes
+void decode_launch(const DecodeLevel* lv4, int n_img, int no, int rows_per_img, float* pred, cudaStream_t st,
+                   float thr = 0.0f, unsigned long long* cand_keys = nullptr, int32_t* cand_counts = nullptr, int cand_cap = 0);
 
 // ---------------------------------------------------------------------------------------------
 // K6-K8 (nms.cu)
@@ -141,13 +143,19 @@ struct NmsImageParams {  // scale_coords inputs, one per image (device array); g
   float gain, pad_x, pad_y, max_x, max_y;
 };
 struct NmsScratch {
-  // per image: candidate arrays of `cap` entries, double-buffered for the radix passes
-  uint32_t* key[2];
-  int32_t* idx[2];
+  // per image: `cap` 64-bit candidate keys (~bits(conf) << 32 | anchor), double-buffered for the radix passes of long
+  // lists, and the candidate count
+  unsigned long long* key[2];
+  int32_t* count;
   int cap;
 };
 size_t nms_scratch_bytes(int n_img, int anchors);
 void nms_bind_scratch(NmsScratch* s, void* mem, int n_img, int anchors);
+void nms_init_device();  // per device: dynamic shared-memory opt-in of the per-image kernel
+// K6 over a given prediction tensor (the engine runs K6 inside the decode kernel instead): fills scratch.key[0] / count
+void nms_candidates_launch(const float* pred, int n_img, int anchors, int no, float conf_thres, const NmsScratch& scratch,
+                           cudaStream_t st);
+// K7 + K8 on the candidate lists in `scratch`
 void nms_launch(const float* pred, int n_img, int anchors, int no, float conf_thres, float iou_thres_floor,
                 int max_det, const NmsImageParams* d_params, const NmsScratch& scratch, float* det_out,
                 int32_t* det_count, int32_t* kept_anchor, cudaStream_t st);

@@ -673,11 +673,12 @@ void stage_compute(mdb_engine* e, Plan* P, int n, int slot, float conf_thres, in
     cudaStream_t sp = e->st_post;
     MDB_CUDA(cudaEventRecord(e->ev_net_done[slot], st));
     MDB_CUDA(cudaStreamWaitEvent(sp, e->ev_net_done[slot], 0));
-    decode_launch(P->lv, n, no, P->anchors, P->pred, sp);
+    decode_launch(P->lv, n, no, P->anchors, P->pred, sp, conf_thres, P->nms_scratch.key[0], P->nms_scratch.count,
+                  P->nms_scratch.cap);
     MDB_CUDA(cudaEventRecord(e->ev_decode_done, sp));
     nms_launch(P->pred, n, P->anchors, no, conf_thres, float_floor_of_double(static_cast<double>(e->cfg.iou_thres)),
                max_det, e->d_nmsp[slot], P->nms_scratch, e->d_det[slot], e->d_cnt[slot], e->d_anchor[slot], sp);
-    e->launches += 2;
+    e->launches += 2;  // decode + candidate pass (one kernel), per-image sort + suppression
     MDB_CUDA(cudaMemcpyAsync(e->h_det[slot], e->d_det[slot], sizeof(float) * n * max_det * 6, cudaMemcpyDeviceToHost, sp));
     MDB_CUDA(cudaMemcpyAsync(e->h_cnt[slot], e->d_cnt[slot], sizeof(int32_t) * n, cudaMemcpyDeviceToHost, sp));
     MDB_CUDA(cudaMemcpyAsync(e->h_anchor[slot], e->d_anchor[slot], sizeof(int32_t) * n * max_det, cudaMemcpyDeviceToHost, sp));
@@ -1004,6 +1005,7 @@ int mdb_create(mdb_engine** out, const mdb_config* cfg) {
     }
     preprocess_init_device();
     conv_init_device();
+    nms_init_device();
     if (const char* mp = getenv("MDB_MAX_PLANS")) e->max_plans = std::max(1, atoi(mp));
     const char* ng = getenv("MDB_NO_GRAPHS");
     e->use_graphs = !(ng && ng[0] == '1');
@@ -1612,6 +1614,8 @@ int mdb_op_nms(mdb_engine* e, const float* pred, int32_t n, int32_t anchors, int
     MDB_CUDA(cudaMemset(d_anc, 0xFF, static_cast<size_t>(n) * max_det * 4));
     NmsScratch sc;
     nms_bind_scratch(&sc, d_scr, n, anchors);
+    nms_candidates_launch(d_pred, n, anchors, no, conf_thres, sc, st);
+    e->launches++;
     nms_launch(d_pred, n, anchors, no, conf_thres, float_floor_of_double(iou_thres), max_det, nullptr, sc, d_det, d_cnt,
                d_anc, st);
     e->launches++;

@@ -2,16 +2,27 @@
 //
 // Replaces the reference's `nms()` (megadetector/detection/pytorch_detector.py:502-610, a loop of ATen
 // kernels, torchvision.ops.nms and >= 3 host syncs per image) and `scale_coords(...).round()`
-// (pytorch_detector.py:1379).  One CTA of 1024 threads owns one image and never talks to the host:
+// (pytorch_detector.py:1379).  Nothing here talks to the host.
 //
-//   K6  ordered compaction   anchors in index order: obj > thr, conf = p_c*obj, first-max class, conf > thr
-//                            (warp ballot + block scan; candidates stay in anchor order)
-//   K7a stable LSD radix sort of the candidates by descending confidence (4 x 8 bits over the float bits;
-//       warp match + per-warp digit counters); stability == torchvision's "equal score: lower index first"
-//   K7b greedy suppression over the globally sorted list with class-aware IoU tests.  Because a box can only
-//       be suppressed by a higher-ranked box of its own class, walking the merged list and stopping after
-//       max_det survivors yields exactly the reference's "per-class NMS, concat, sort by conf, keep 300".
+//   K6  candidate pass, GRID-WIDE (HBM rate): one thread per anchor of every image: obj > thr, conf = p_c*obj,
+//       first-max class, conf > thr  ->  64-bit key  (~bits(conf) << 32 | anchor)  appended to the image's candidate
+//       list (warp-aggregated atomics; the order of the list is irrelevant because the anchor is part of the key).
+//       In the engine this pass is the tail of the Detect decode kernel (aux.cu), i.e. the prediction tensor is
+//       thresholded by the thread that produced the row; `cand_from_pred_kernel` is the same pass over a given tensor.
+//   K7a one CTA per image: LSD radix sort of the keys, ascending == confidence descending, equal confidence: lower
+//       anchor first (torchvision's stable order).  Lists of up to 8192 candidates are sorted in shared memory, longer
+//       ones in global scratch; passes whose digit is constant (upper anchor bytes, exponent byte) are skipped.
+//   K7b greedy class-aware suppression over the sorted list in windows of 512 candidates: (1) every candidate of the
+//       window is tested against the boxes kept so far by two threads (half of the kept list each), (2) the survivors
+//       are compacted, (3) their pairwise suppression bit-matrix is computed by all threads, (4) ONE warp resolves the
+//       window serially on the bit-matrix (a register OR per survivor, no block barrier).  Because a box can only be
+//       suppressed by a higher-ranked box of its own class, walking the merged list and stopping after max_det
+//       survivors yields exactly the reference's "per-class NMS, concat, sort by conf, keep 300".
 //   K8  scale_coords + clip + round-half-even on the survivors, written with their anchor indices.
+//
+// Round 1 did all of this in one 1024-thread CTA per image (ordered compaction: 60 barrier rounds; one barrier round
+// per survivor): 0.41 ms per launch regardless of the image count, 1.6 % of the HBM rate on the prediction tensor
+// (profiles/r01_ncu_nms_details.txt).
 //
 // Bit-exactness: every float op that torch/torchvision perform is issued with an explicit round-to-nearest
 // intrinsic, so nvcc cannot contract a*b+c into an FMA; thresholds are compared in the reference's types
@@ -20,11 +31,17 @@
 #include <cstring>
 
 #include "common.h"
+#include "nms_cand.cuh"
 
 namespace mdb {
 
 constexpr int kNmsThreads = 1024;
 constexpr int kNmsWarps = kNmsThreads / 32;
+constexpr int kWin = 512;                  // candidates per suppression window
+constexpr int kWinWords = kWin / 32;       // words per row of the window's suppression bit-matrix
+constexpr int kSortSmemKeys = 8192;        // lists up to this length are sorted in shared memory
+// dynamic shared memory: two key buffers (sort ping-pong); after the sort the spare one holds the window state
+constexpr size_t kNmsDynSmem = 2 * static_cast<size_t>(kSortSmemKeys) * sizeof(unsigned long long);
 
 float float_floor_of_double(double t) {
   float f = static_cast<float>(t);
@@ -32,15 +49,16 @@ float float_floor_of_double(double t) {
   return f;
 }
 
-size_t nms_scratch_bytes(int n_img, int anchors) { return static_cast<size_t>(n_img) * anchors * 16; }
+size_t nms_scratch_bytes(int n_img, int anchors) {
+  return static_cast<size_t>(n_img) * anchors * 16 + static_cast<size_t>(n_img) * sizeof(int32_t) + 256;
+}
 
 void nms_bind_scratch(NmsScratch* s, void* mem, int n_img, int anchors) {
   char* p = static_cast<char*>(mem);
-  const size_t one = static_cast<size_t>(n_img) * anchors * 4;
-  s->key[0] = reinterpret_cast<uint32_t*>(p);
-  s->key[1] = reinterpret_cast<uint32_t*>(p + one);
-  s->idx[0] = reinterpret_cast<int32_t*>(p + 2 * one);
-  s->idx[1] = reinterpret_cast<int32_t*>(p + 3 * one);
+  const size_t one = static_cast<size_t>(n_img) * anchors * 8;
+  s->key[0] = reinterpret_cast<unsigned long long*>(p);
+  s->key[1] = reinterpret_cast<unsigned long long*>(p + one);
+  s->count = reinterpret_cast<int32_t*>(p + 2 * one);
   s->cap = anchors;
 }
 
@@ -48,6 +66,7 @@ struct Cand {
   float x1, y1, x2, y2, area, conf;
   int cls;
 };
+static_assert(sizeof(Cand) == 28, "Cand is copied as 7 words");
 
 // reference: box = xc -/+ w/2 (float32), class_conf = p*obj, first maximum
 __device__ __forceinline__ bool eval_anchor(const float* __restrict__ row, int no, float thr, Cand& c) {
@@ -98,64 +117,57 @@ __device__ __forceinline__ bool iou_exceeds(const Cand& a, const Cand& b, float 
   return ovr > thr_floor;
 }
 
-__global__ void __launch_bounds__(kNmsThreads, 1)
-nms_image_kernel(const float* __restrict__ pred, int anchors, int no, float thr, float iou_floor, int max_det,
-                 const NmsImageParams* __restrict__ params, NmsScratch sc, float* __restrict__ det_out,
-                 int32_t* __restrict__ det_count, int32_t* __restrict__ kept_anchor) {
-  __shared__ uint32_t s_warp_cnt[kNmsWarps];
-  __shared__ uint32_t s_digit_off[256];
-  __shared__ uint16_t s_warp_digit[kNmsWarps][256];
-  __shared__ int s_n, s_kept, s_first;
-  __shared__ Cand s_keep[kMaxDetCap];
-  __shared__ int s_keep_anchor[kMaxDetCap];
-  __shared__ int s_warp_first[kNmsWarps];
-
-  const int img = blockIdx.x;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const float* P = pred + static_cast<size_t>(img) * anchors * no;
-  uint32_t* key0 = sc.key[0] + static_cast<size_t>(img) * sc.cap;
-  uint32_t* key1 = sc.key[1] + static_cast<size_t>(img) * sc.cap;
-  int32_t* idx0 = sc.idx[0] + static_cast<size_t>(img) * sc.cap;
-  int32_t* idx1 = sc.idx[1] + static_cast<size_t>(img) * sc.cap;
-
-  // ------------------------------- K6: ordered compaction -------------------------------
-  if (tid == 0) s_n = 0;
-  __syncthreads();
-  for (int base = 0; base < anchors; base += kNmsThreads) {
-    const int a = base + tid;
-    Cand c;
-    const bool ok = (a < anchors) && eval_anchor(P + static_cast<size_t>(a) * no, no, thr, c);
-    const uint32_t bal = __ballot_sync(0xffffffffu, ok);
-    if (lane == 0) s_warp_cnt[warp] = __popc(bal);
-    __syncthreads();
-    uint32_t before = 0, total = 0;
-    for (int w2 = 0; w2 < kNmsWarps; ++w2) {
-      const uint32_t cnt = s_warp_cnt[w2];
-      if (w2 < warp) before += cnt;
-      total += cnt;
+// ------------------------------- K6 over a given prediction tensor -------------------------------
+__global__ void cand_from_pred_kernel(const float* __restrict__ pred, int anchors, int no, float thr,
+                                      unsigned long long* __restrict__ keys, int32_t* __restrict__ counts, int cap,
+                                      long long total_rows) {
+  const long long r = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const bool in = r < total_rows;
+  const int n = in ? static_cast<int>(r / anchors) : -1;
+  const int row = in ? static_cast<int>(r - static_cast<long long>(n) * anchors) : 0;
+  float conf = 0.f;
+  bool ok = false;
+  if (in) {
+    const float* p = pred + r * no;
+    const float obj = __ldg(p + 4);
+    if (obj > thr) {
+      float best = -INFINITY;
+      for (int k = 0; k < no - 5; ++k) {
+        const float cc = __fmul_rn(__ldg(p + 5 + k), obj);
+        if (cc > best) best = cc;
+      }
+      ok = best > thr;
+      conf = best;
     }
-    const int n0 = s_n;
-    if (ok) {
-      const int pos = n0 + before + __popc(bal & ((1u << lane) - 1u));
-      key0[pos] = ~__float_as_uint(c.conf);  // conf > 0: bit pattern is monotonic; inverted for descending order
-      idx0[pos] = a;
-    }
-    __syncthreads();
-    if (tid == 0) s_n = n0 + total;
-    __syncthreads();
   }
-  const int n = s_n;
+  cand_append(ok, n, row, conf, keys, counts, cap);
+}
 
-  // ------------------------------- K7a: stable LSD radix sort -------------------------------
-  uint32_t* kin = key0; uint32_t* kout = key1;
-  int32_t* iin = idx0; int32_t* iout = idx1;
-  for (int pass = 0; pass < 4 && n > 1; ++pass) {
+// ------------------------------- radix sort of 64-bit keys (one CTA) -------------------------------
+// Stable LSD passes over 8 digits of 8 bits; a pass whose digit is the same for all keys moves nothing and is skipped.
+// kin/kout may live in shared or in global memory.  Returns the buffer that holds the sorted keys.
+__device__ unsigned long long* radix_sort_keys(unsigned long long* kin, unsigned long long* kout, int n,
+                                               uint32_t* s_digit_off, uint16_t (*s_warp_digit)[256], int* s_flag) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int pass = 0; pass < 8 && n > 1; ++pass) {
     const int shift = pass * 8;
     if (tid < 256) s_digit_off[tid] = 0;
+    if (tid == 0) *s_flag = 0;
     __syncthreads();
-    for (int i = tid; i < n; i += kNmsThreads) atomicAdd(&s_digit_off[(kin[i] >> shift) & 255u], 1u);
+    for (int base = 0; base < n; base += kNmsThreads) {
+      const int i = base + tid;
+      const bool valid = i < n;
+      const uint32_t d = valid ? static_cast<uint32_t>(kin[i] >> shift) & 255u : 256u;
+      const uint32_t peers = __match_any_sync(0xffffffffu, d);
+      if (valid && (peers & ((1u << lane) - 1u)) == 0) atomicAdd(&s_digit_off[d], static_cast<uint32_t>(__popc(peers)));
+    }
     __syncthreads();
-    // exclusive scan over 256 digit counts (warp 0, 8 per lane)
+    if (tid < 256 && s_digit_off[tid] == static_cast<uint32_t>(n)) *s_flag = 1;  // constant digit
+    __syncthreads();
+    const int skip = *s_flag;
+    __syncthreads();  // everyone has read the flag before the next pass resets it
+    if (skip) continue;
+    // exclusive scan over the 256 digit counts (warp 0, 8 per lane)
     if (warp == 0) {
       uint32_t loc[8], sum = 0;
 #pragma unroll
@@ -174,12 +186,12 @@ nms_image_kernel(const float* __restrict__ pred, int anchors, int no, float thr,
     for (int base = 0; base < n; base += kNmsThreads) {
       const int i = base + tid;
       const bool valid = i < n;
-      uint32_t k = 0; int32_t v = 0; uint32_t d = 0;
-      if (valid) { k = kin[i]; v = iin[i]; d = (k >> shift) & 255u; }
+      unsigned long long k = 0;
+      uint32_t d = 256u;
+      if (valid) { k = kin[i]; d = static_cast<uint32_t>(k >> shift) & 255u; }
       for (int j = lane; j < 256; j += 32) s_warp_digit[warp][j] = 0;
       __syncwarp();
-      // peers in this warp with the same digit (invalid lanes use digit 256 -> never match a valid one)
-      const uint32_t peers = __match_any_sync(0xffffffffu, valid ? d : 256u);
+      const uint32_t peers = __match_any_sync(0xffffffffu, d);
       const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
       if (valid && rank == 0) s_warp_digit[warp][d] = static_cast<uint16_t>(__popc(peers));
       __syncthreads();
@@ -195,58 +207,153 @@ nms_image_kernel(const float* __restrict__ pred, int anchors, int no, float thr,
         for (int w2 = 0; w2 < kNmsWarps; ++w2) tot += s_warp_digit[w2][tid];
         s_digit_off[tid] += tot;
       }
-      if (valid) { kout[pos] = k; iout[pos] = v; }
+      if (valid) kout[pos] = k;
       __syncthreads();
     }
-    uint32_t* tk = kin; kin = kout; kout = tk;
-    int32_t* ti = iin; iin = iout; iout = ti;
+    unsigned long long* t = kin; kin = kout; kout = t;
   }
   __threadfence_block();
   __syncthreads();
+  return kin;
+}
+
+// ------------------------------- K7 + K8 -------------------------------
+__global__ void __launch_bounds__(kNmsThreads, 1)
+nms_image_kernel(const float* __restrict__ pred, int anchors, int no, float thr, float iou_floor, int max_det,
+                 const NmsImageParams* __restrict__ params, NmsScratch sc, float* __restrict__ det_out,
+                 int32_t* __restrict__ det_count, int32_t* __restrict__ kept_anchor) {
+  extern __shared__ __align__(16) unsigned char s_dyn[];
+  __shared__ uint32_t s_digit_off[256];
+  __shared__ uint16_t s_warp_digit[kNmsWarps][256];
+  __shared__ uint32_t s_warp_cnt[kNmsWarps];
+  __shared__ int s_flag, s_kept, s_A;
+  __shared__ Cand s_keep[kMaxDetCap];
+  __shared__ int s_keep_anchor[kMaxDetCap];
+
+  const int img = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* P = pred + static_cast<size_t>(img) * anchors * no;
+  const int n = min(sc.count[img], sc.cap);
+  unsigned long long* g0 = sc.key[0] + static_cast<size_t>(img) * sc.cap;
+  unsigned long long* g1 = sc.key[1] + static_cast<size_t>(img) * sc.cap;
+  unsigned long long* sm0 = reinterpret_cast<unsigned long long*>(s_dyn);
+  unsigned long long* sm1 = sm0 + kSortSmemKeys;
+
+  // ------------------------------- K7a: sort -------------------------------
+  const unsigned long long* sorted;
+  unsigned char* spare;  // >= 64 KB of shared memory not holding the sorted keys
+  if (n <= kSortSmemKeys) {
+    for (int i = tid; i < n; i += kNmsThreads) sm0[i] = g0[i];
+    __syncthreads();
+    unsigned long long* res = radix_sort_keys(sm0, sm1, n, s_digit_off, s_warp_digit, &s_flag);
+    sorted = res;
+    spare = reinterpret_cast<unsigned char*>(res == sm0 ? sm1 : sm0);
+  } else {
+    sorted = radix_sort_keys(g0, g1, n, s_digit_off, s_warp_digit, &s_flag);
+    spare = s_dyn;
+  }
+  // window state in the spare buffer: candidates of the window, compacted survivor list, suppression bit-matrix
+  Cand* s_win = reinterpret_cast<Cand*>(spare);                                          // 512 x 28 B = 14336
+  int* s_win_anchor = reinterpret_cast<int*>(spare + 14336);                              // 2048
+  uint8_t* s_dead1 = reinterpret_cast<uint8_t*>(spare + 14336 + 2048);                     // 512
+  uint16_t* s_alist = reinterpret_cast<uint16_t*>(spare + 14336 + 2048 + 512);            // 1024
+  uint32_t* s_sup = reinterpret_cast<uint32_t*>(spare + 14336 + 2048 + 512 + 1024);       // 512 x 16 x 4 = 32768
 
   // ------------------------------- K7b: greedy class-aware suppression -------------------------------
   if (tid == 0) s_kept = 0;
   __syncthreads();
-  bool done = false;
-  for (int base = 0; base < n && !done; base += kNmsThreads) {
-    const int i = base + tid;
-    Cand me;
-    int my_anchor = -1;
-    bool alive = false;
-    if (i < n) {
-      my_anchor = iin[i];
-      alive = eval_anchor(P + static_cast<size_t>(my_anchor) * no, no, thr, me);  // always true
-      const int kc = s_kept;
-      for (int k = 0; k < kc && alive; ++k)
-        if (s_keep[k].cls == me.cls && iou_exceeds(s_keep[k], me, iou_floor)) alive = false;
-    }
-    // resolve the survivors of this chunk in rank order
-    while (true) {
-      const uint32_t bal = __ballot_sync(0xffffffffu, alive);
-      if (lane == 0) s_warp_first[warp] = bal ? (warp * 32 + __ffs(bal) - 1) : kNmsThreads;
-      __syncthreads();
-      if (warp == 0) {
-        int f = s_warp_first[lane];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) f = min(f, __shfl_xor_sync(0xffffffffu, f, o));
-        if (lane == 0) s_first = f;
+  const int t = tid & (kWin - 1), half = tid >> 9;
+  for (int base = 0; base < n; base += kWin) {
+    const int i = base + t;
+    const bool valid = i < n;
+    if (half == 0) {
+      Cand c;
+      c.cls = -1;
+      int anc = -1;
+      if (valid) {
+        anc = static_cast<int>(static_cast<uint32_t>(sorted[i]));
+        eval_anchor(P + static_cast<size_t>(anc) * no, no, thr, c);  // always a candidate
       }
-      __syncthreads();
-      const int first = s_first;
-      if (first >= kNmsThreads) break;
-      const int slot = s_kept;
-      if (tid == first) {
-        s_keep[slot] = me;
-        s_keep_anchor[slot] = my_anchor;
-        alive = false;
-      }
-      __syncthreads();
-      if (tid == 0) s_kept = slot + 1;
-      if (slot + 1 >= max_det) { done = true; break; }
-      if (alive && tid > first && s_keep[slot].cls == me.cls && iou_exceeds(s_keep[slot], me, iou_floor)) alive = false;
-      __syncthreads();
+      s_win[t] = c;
+      s_win_anchor[t] = anc;
     }
     __syncthreads();
+    const Cand me = s_win[t];
+    const int kc = s_kept;
+    // (1) against the boxes kept so far: each half of the block scans half of the list
+    bool dead = !valid;
+    {
+      const int k0 = half ? (kc >> 1) : 0, k1 = half ? kc : (kc >> 1);
+      for (int k = k0; k < k1 && !dead; ++k)
+        if (s_keep[k].cls == me.cls && iou_exceeds(s_keep[k], me, iou_floor)) dead = true;
+    }
+    if (half == 1) s_dead1[t] = dead ? 1 : 0;
+    __syncthreads();
+    // (2) compact the survivors of the window, in rank order
+    bool alive = false;
+    if (half == 0) {
+      alive = !dead && !s_dead1[t];
+      const uint32_t bal = __ballot_sync(0xffffffffu, alive);
+      if (lane == 0) s_warp_cnt[warp] = __popc(bal);
+    }
+    __syncthreads();
+    if (half == 0) {
+      uint32_t before = 0, total = 0;
+      for (int w2 = 0; w2 < kWin / 32; ++w2) {
+        const uint32_t cnt = s_warp_cnt[w2];
+        if (w2 < warp) before += cnt;
+        total += cnt;
+      }
+      const uint32_t bal = __ballot_sync(0xffffffffu, alive);
+      if (alive) s_alist[before + __popc(bal & ((1u << lane) - 1u))] = static_cast<uint16_t>(t);
+      if (tid == 0) s_A = static_cast<int>(total);
+    }
+    __syncthreads();
+    const int A = s_A;
+    if (A > 0) {
+      // (3) sup[i][w]: bit b set <=> survivor j = 32*w + b ranks after i, has i's class and overlaps i beyond the threshold
+      const int wpr = (A + 31) >> 5;
+      for (int idx = tid; idx < A * wpr; idx += kNmsThreads) {
+        const int ri = idx / wpr, w = idx - ri * wpr;
+        uint32_t bits = 0;
+        if (w * 32 + 31 > ri) {
+          const Cand ci = s_win[s_alist[ri]];
+          const int j0 = w * 32;
+#pragma unroll 4
+          for (int b = 0; b < 32; ++b) {
+            const int j = j0 + b;
+            if (j > ri && j < A) {
+              const Cand cj = s_win[s_alist[j]];
+              if (cj.cls == ci.cls && iou_exceeds(ci, cj, iou_floor)) bits |= 1u << b;
+            }
+          }
+        }
+        s_sup[ri * kWinWords + w] = bits;
+      }
+      __syncthreads();
+      // (4) one warp resolves the window: lane l owns word l of the "removed" bit-vector
+      if (warp == 0) {
+        uint32_t removed = 0;
+        int kept = kc;
+        uint32_t row = lane < wpr ? s_sup[lane] : 0u;
+        for (int ri = 0; ri < A; ++ri) {
+          const uint32_t next = (ri + 1 < A && lane < wpr) ? s_sup[(ri + 1) * kWinWords + lane] : 0u;  // independent of the decision
+          const uint32_t r = __shfl_sync(0xffffffffu, removed, ri >> 5);
+          if (!((r >> (ri & 31)) & 1u)) {
+            const int src = s_alist[ri];
+            if (lane < 7) reinterpret_cast<uint32_t*>(&s_keep[kept])[lane] = reinterpret_cast<const uint32_t*>(&s_win[src])[lane];
+            if (lane == 7) s_keep_anchor[kept] = s_win_anchor[src];
+            ++kept;
+            if (kept >= max_det) break;
+            removed |= row;
+          }
+          row = next;
+        }
+        if (lane == 0) s_kept = kept;
+      }
+    }
+    __syncthreads();
+    if (s_kept >= max_det) break;
   }
   __syncthreads();
 
@@ -276,14 +383,30 @@ nms_image_kernel(const float* __restrict__ pred, int anchors, int no, float thr,
   if (tid == 0) det_count[img] = kept;
 }
 
+void nms_init_device() {
+  MDB_CUDA(cudaFuncSetAttribute(nms_image_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kNmsDynSmem)));
+}
+
+void nms_candidates_launch(const float* pred, int n_img, int anchors, int no, float conf_thres, const NmsScratch& scratch,
+                           cudaStream_t st) {
+  if (n_img <= 0) return;
+  MDB_REQUIRE(scratch.cap >= anchors, "NMS scratch too small");
+  MDB_CUDA(cudaMemsetAsync(scratch.count, 0, sizeof(int32_t) * n_img, st));
+  const long long total = static_cast<long long>(n_img) * anchors;
+  const int threads = 256;
+  cand_from_pred_kernel<<<static_cast<unsigned>((total + threads - 1) / threads), threads, 0, st>>>(
+      pred, anchors, no, conf_thres, scratch.key[0], scratch.count, scratch.cap, total);
+  MDB_CUDA(cudaGetLastError());
+}
+
 void nms_launch(const float* pred, int n_img, int anchors, int no, float conf_thres, float iou_thres_floor,
                 int max_det, const NmsImageParams* d_params, const NmsScratch& scratch, float* det_out,
                 int32_t* det_count, int32_t* kept_anchor, cudaStream_t st) {
   if (n_img <= 0) return;
   MDB_REQUIRE(max_det >= 1 && max_det <= kMaxDetCap, "max_det out of range");
   MDB_REQUIRE(scratch.cap >= anchors, "NMS scratch too small");
-  nms_image_kernel<<<n_img, kNmsThreads, 0, st>>>(pred, anchors, no, conf_thres, iou_thres_floor, max_det, d_params,
-                                                  scratch, det_out, det_count, kept_anchor);
+  nms_image_kernel<<<n_img, kNmsThreads, kNmsDynSmem, st>>>(pred, anchors, no, conf_thres, iou_thres_floor, max_det,
+                                                            d_params, scratch, det_out, det_count, kept_anchor);
   MDB_CUDA(cudaGetLastError());
 }
 

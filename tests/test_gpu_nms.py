@@ -64,3 +64,29 @@ def test_nms_empty_and_all_below_threshold(engine):
     pred = np.zeros((2, 256, 8), np.float32)
     det, cnt, anc = engine.op_nms(pred, 1e-5, 0.45)
     assert cnt.tolist() == [0, 0]
+
+
+@pytest.mark.parametrize('n_cand', [1, 31, 511, 512, 513, 1025, 8191, 8192, 8193, 30000])
+def test_nms_candidate_count_boundaries(engine, n_cand):
+    """Window (512) and shared-memory sort (8192) boundaries of the kernel, with many exactly equal confidences (ties must
+    resolve to the lower anchor index, torchvision's stable order) and a batch whose images have different list lengths."""
+    from oracle import nms as onms
+    rng = np.random.default_rng(n_cand)
+    anchors = 40000
+    preds = []
+    for b, nc_b in enumerate((n_cand, max(1, n_cand // 3), 0)):
+        p = _random_pred(rng, anchors, 60)
+        obj = np.full(anchors, 1e-7, np.float32)
+        sel = rng.permutation(anchors)[:nc_b]
+        # quantised confidences: large tie groups
+        obj[sel] = (rng.integers(1, 40, size=nc_b) / 40.0).astype(np.float32)
+        p[:, 4] = obj
+        p[:, 5:] = np.float32(0.5) * (1 + np.eye(3, dtype=np.float32)[rng.integers(0, 3, size=anchors)])
+        preds.append(p)
+    pred = np.stack(preds)
+    det, cnt, anc = engine.op_nms(pred, 1e-5, 0.45)
+    for b in range(pred.shape[0]):
+        odet, oanc = onms.nms_torch_indexed(pred[b], 1e-5, 0.45)
+        assert cnt[b] == odet.shape[0], (b, cnt[b], odet.shape[0])
+        assert_dets_equal_modulo_ties(odet, det[b, :cnt[b]], 'img{}'.format(b))
+        assert_anchors_equal_modulo_ties(odet[:, 4], oanc, det[b, :cnt[b], 4], anc[b, :cnt[b]], 'img{}'.format(b))
