@@ -115,6 +115,19 @@ MDB_API int mdb_infer_preprocessed(mdb_engine* e, const uint8_t* const* lb_hwc, 
                            const int32_t* src_h, const int32_t* src_w, int32_t n, float conf_thres, float* det_out,
                            int32_t* det_count, int32_t* kept_anchor, int32_t* status);
 
+/* JPEG files decoded ON THE GPU (nvJPEG: hardware JPEG engine or GPU-hybrid backend), straight into the buffers K1 reads:
+ * replaces visualization_utils.load_image (megadetector/visualization/visualization_utils.py:103-176,306-323: PIL open ->
+ * RGB -> EXIF orientation 3/6/8), which run_detector_batch calls per image on the host (run_detector_batch.py:724).
+ * jpeg[i] / nbytes[i]: the file's bytes (host memory).  Unreadable streams and 4-component (CMYK) files get
+ * MDB_IMG_BAD_INPUT, as PIL-unreadable files do in the reference.  src_hw (may be NULL): [n][2] decoded height, width
+ * (after the orientation has been applied) -- the `scaling_shape` the records are normalised by.
+ * Decoded pixels differ from libjpeg-turbo's by a few LSB at chroma edges (different IDCT / up-sampling arithmetic). */
+MDB_API int mdb_infer_jpeg_batch(mdb_engine* e, const uint8_t* const* jpeg, const size_t* nbytes, int32_t n, float conf_thres,
+                                 float* det_out, int32_t* det_count, int32_t* kept_anchor, int32_t* status, int32_t* src_hw);
+/* parity hook: decode one JPEG and return the RGB pixels ([h][w][3] u8), hw2 = {h, w}, backend = 1 hardware / 2 GPU hybrid */
+MDB_API int mdb_op_decode_jpeg(mdb_engine* e, const uint8_t* jpeg, size_t nbytes, uint8_t* rgb_out, size_t cap, int32_t* hw2,
+                               int32_t* backend);
+
 /* `image_size` argument of generate_detections_one_batch (pytorch_detector.py:1011-1024): long-side target of
  * the letterbox for subsequent calls (default cfg.img_size). */
 MDB_API int mdb_set_image_size(mdb_engine* e, int32_t img_size);

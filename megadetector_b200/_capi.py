@@ -21,6 +21,7 @@ EXPORTS = [
     'mdb_create', 'mdb_load_weights', 'mdb_destroy', 'mdb_last_error', 'mdb_infer_batch', 'mdb_batch_begin', 'mdb_batch_next', 'mdb_infer_preprocessed',
     'mdb_letterbox_geometry', 'mdb_set_image_size', 'mdb_debug_fetch', 'mdb_last_timing', 'mdb_bench_resident', 'mdb_profile_steps', 'mdb_set_pipeline_split', 'mdb_launch_count', 'mdb_op_letterbox',
     'mdb_op_conv2d', 'mdb_op_nms', 'mdb_alloc_pinned', 'mdb_free_pinned', 'mdb_version',
+    'mdb_infer_jpeg_batch', 'mdb_op_decode_jpeg',
     'mdb_debug_set_trace', 'mdb_debug_trace_names', 'mdb_debug_fetch_trace', 'mdb_op_upsample2x', 'mdb_op_sppf_pool', 'mdb_op_decode',
 ]
 
@@ -107,6 +108,10 @@ def load_library():
     lib.mdb_op_conv2d.restype = C.c_int
     lib.mdb_op_nms.argtypes = [vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_double, C.c_int32, vp, vp, vp]
     lib.mdb_op_nms.restype = C.c_int
+    lib.mdb_infer_jpeg_batch.argtypes = [vp, P(vp), P(C.c_size_t), C.c_int32, C.c_float, vp, vp, vp, vp, vp]
+    lib.mdb_infer_jpeg_batch.restype = C.c_int
+    lib.mdb_op_decode_jpeg.argtypes = [vp, vp, C.c_size_t, vp, C.c_size_t, P(C.c_int32), P(C.c_int32)]
+    lib.mdb_op_decode_jpeg.restype = C.c_int
     lib.mdb_debug_set_trace.argtypes = [vp, C.c_char_p]
     lib.mdb_debug_set_trace.restype = C.c_int
     lib.mdb_debug_trace_names.argtypes = [vp, vp, C.c_size_t, P(C.c_int32)]
@@ -338,6 +343,33 @@ class Engine:
                                              status.ctypes.data)
         self._check(rc, 'mdb_infer_preprocessed')
         return det, cnt, anc, status
+
+    def infer_jpeg_batch(self, blobs, conf_thres, want_anchors=False):
+        """blobs: list of `bytes` (JPEG files).  Returns (det, count, anchors, status, src_hw [n,2])."""
+        n = len(blobs)
+        bufs = [np.frombuffer(b, np.uint8) if b is not None and len(b) else None for b in blobs]
+        ptrs = (C.c_void_p * n)(*[(a.ctypes.data if a is not None else None) for a in bufs])
+        lens = (C.c_size_t * n)(*[(a.size if a is not None else 0) for a in bufs])
+        det = np.zeros((n, self.max_det, 6), np.float32)
+        cnt = np.zeros((n,), np.int32)
+        anc = np.full((n, self.max_det), -1, np.int32) if want_anchors else None
+        status = np.zeros((n,), np.int32)
+        hw = np.zeros((n, 2), np.int32)
+        rc = self.lib.mdb_infer_jpeg_batch(self.h, ptrs, lens, n, float(conf_thres), det.ctypes.data, cnt.ctypes.data,
+                                           anc.ctypes.data if anc is not None else None, status.ctypes.data, hw.ctypes.data)
+        self._check(rc, 'mdb_infer_jpeg_batch')
+        return det, cnt, anc, status, hw
+
+    def op_decode_jpeg(self, blob):
+        """-> (rgb [h,w,3] u8, backend) for one JPEG file's bytes."""
+        a = np.frombuffer(blob, np.uint8)
+        hw = (C.c_int32 * 2)()
+        be = C.c_int32(0)
+        self._check(self.lib.mdb_op_decode_jpeg(self.h, a.ctypes.data, a.size, None, 0, hw, C.byref(be)), 'mdb_op_decode_jpeg')
+        out = np.empty((hw[0], hw[1], 3), np.uint8)
+        self._check(self.lib.mdb_op_decode_jpeg(self.h, a.ctypes.data, a.size, out.ctypes.data, out.nbytes, hw, C.byref(be)),
+                    'mdb_op_decode_jpeg')
+        return out, int(be.value)
 
     def set_image_size(self, img_size):
         self._check(self.lib.mdb_set_image_size(self.h, int(img_size)), 'mdb_set_image_size')

@@ -17,7 +17,7 @@ CSRC = os.path.join(HERE, 'csrc')
 VARIANT = os.environ.get('MDB_LIB_VARIANT', '')
 OUT = os.path.join(HERE, 'libmdb200{}.so'.format('_' + VARIANT if VARIANT else ''))
 OBJ_DIR = os.path.join(HERE, 'csrc', 'build' + ('_' + VARIANT if VARIANT else ''))
-SOURCES = ['tmap.cu', 'conv_host.cu', 'preprocess.cu', 'aux.cu', 'nms.cu', 'engine.cu']
+SOURCES = ['tmap.cu', 'conv_host.cu', 'preprocess.cu', 'aux.cu', 'nms.cu', 'jpeg.cu', 'engine.cu']
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 ARCH_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a']
 CFLAGS = ['-O3', '-std=c++17', '-lineinfo', '-Xcompiler', '-fPIC', '-Xcompiler', '-fvisibility=hidden',

@@ -121,6 +121,19 @@ void preprocess_init_constants();
 void preprocess_init_device();  // per device: constants + the kernel's dynamic shared-memory opt-in
 
 // ---------------------------------------------------------------------------------------------
+// JPEG decode on the GPU (jpeg.cu): nvJPEG, loaded with dlopen at first use
+// ---------------------------------------------------------------------------------------------
+struct JpegDecoder;
+struct JpegImage {  // decoded, orientation-corrected interleaved RGB image in device memory (dense rows); ptr == nullptr: unreadable
+  const uint8_t* ptr;
+  int h, w;
+};
+JpegDecoder* jpeg_create();
+void jpeg_destroy(JpegDecoder* d);
+int jpeg_decode_batch(JpegDecoder* d, const uint8_t* const* jpeg, const size_t* nbytes, int n, JpegImage* out, cudaStream_t st);
+int jpeg_exif_orientation(const uint8_t* p, size_t n);
+
+// ---------------------------------------------------------------------------------------------
 // K3/K4/K5 (aux.cu)
 // ---------------------------------------------------------------------------------------------
 void upsample2x_launch(const View& src, const View& dst, int n_img, cudaStream_t st);

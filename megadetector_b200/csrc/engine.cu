@@ -110,6 +110,7 @@ struct ImgIn {
   long long stride;
   int src_h, src_w;  // original size for scale_coords
   int index;         // position in the caller's arrays
+  bool on_device = false;  // ptr is device memory (JPEG path): K1 reads it in place, nothing is uploaded
 };
 
 struct Pending {
@@ -188,6 +189,8 @@ struct mdb_engine {
   bool trace_all = false;
   std::vector<std::string> trace_names;
   BatchState batch;
+  JpegDecoder* jpeg = nullptr;
+  int last_jpeg_backend = 0;
   std::string err;
 };
 
@@ -710,7 +713,9 @@ void enqueue_chunk(mdb_engine* e, Plan* P, const std::vector<ImgIn>& imgs, const
     const ImgIn& im = imgs[i];
     uint8_t* d = e->d_src[slot] + offs[i];
     const size_t row = static_cast<size_t>(im.w) * 3;
-    if (im.stride == static_cast<long long>(row)) {
+    if (im.on_device) {
+      d = const_cast<uint8_t*>(im.ptr);  // decoded by nvJPEG on the copy stream, ordered before ev_copy_done below
+    } else if (im.stride == static_cast<long long>(row)) {
       MDB_CUDA(cudaMemcpyAsync(d, im.ptr, row * im.h, cudaMemcpyHostToDevice, e->st_copy));
     } else {
       MDB_CUDA(cudaMemcpy2DAsync(d, row, im.ptr, static_cast<size_t>(im.stride), row, im.h, cudaMemcpyHostToDevice,
@@ -1042,6 +1047,7 @@ void mdb_destroy(mdb_engine* e) {
     if (e->h_anchor[i]) cudaFreeHost(e->h_anchor[i]);
     for (int j = 0; j < 4; ++j) if (e->ev_tt[i][j]) cudaEventDestroy(e->ev_tt[i][j]);
   }
+  if (e->jpeg) jpeg_destroy(e->jpeg);
   if (e->st_compute) cudaStreamDestroy(e->st_compute);
   if (e->st_copy) cudaStreamDestroy(e->st_copy);
   if (e->st_post) cudaStreamDestroy(e->st_post);
@@ -1166,6 +1172,50 @@ int mdb_infer_preprocessed(mdb_engine* e, const uint8_t* const* lb_hwc, const in
   } catch (const CudaError& ex) {
     return fail(e, MDB_ERR_CUDA, ex.msg);
   }
+}
+
+int mdb_infer_jpeg_batch(mdb_engine* e, const uint8_t* const* jpeg, const size_t* nbytes, int32_t n, float conf_thres,
+                         float* det_out, int32_t* det_count, int32_t* kept_anchor, int32_t* status, int32_t* src_hw) {
+  if (!e || !jpeg || !nbytes || !det_out || !det_count || !status || n < 0) return fail(e, MDB_ERR_ARG, "null argument");
+  try {
+    MDB_CUDA(cudaSetDevice(e->cfg.device));
+    if (!e->jpeg) e->jpeg = jpeg_create();
+    std::vector<JpegImage> dec(n);
+    e->last_jpeg_backend = jpeg_decode_batch(e->jpeg, jpeg, nbytes, n, dec.data(), e->st_copy);
+    std::vector<ImgIn> all(n);
+    for (int i = 0; i < n; ++i) {
+      ImgIn im{dec[i].ptr, dec[i].h, dec[i].w, static_cast<long long>(dec[i].w) * 3, dec[i].h, dec[i].w, i};
+      im.on_device = true;
+      all[i] = im;
+      if (src_hw) { src_hw[2 * i] = dec[i].h; src_hw[2 * i + 1] = dec[i].w; }
+    }
+    return infer_common(e, all, false, conf_thres, det_out, det_count, kept_anchor, status, n);
+  } catch (const CudaError& ex) {
+    return fail(e, MDB_ERR_CUDA, ex.msg);
+  }
+}
+
+int mdb_op_decode_jpeg(mdb_engine* e, const uint8_t* jpeg, size_t nbytes, uint8_t* rgb_out, size_t cap, int32_t* hw2,
+                       int32_t* backend) {
+  if (!e || !jpeg || !hw2) return fail(e, MDB_ERR_ARG, "null argument");
+  try {
+    MDB_CUDA(cudaSetDevice(e->cfg.device));
+    if (!e->jpeg) e->jpeg = jpeg_create();
+    JpegImage im;
+    const int be = jpeg_decode_batch(e->jpeg, &jpeg, &nbytes, 1, &im, e->st_copy);
+    if (backend) *backend = be;
+    hw2[0] = im.h; hw2[1] = im.w;
+    if (!im.ptr) return fail(e, MDB_ERR_ARG, "not a decodable 1- or 3-component JPEG");
+    if (rgb_out) {
+      const size_t need = static_cast<size_t>(im.h) * im.w * 3;
+      if (cap < need) return fail(e, MDB_ERR_ARG, "destination too small");
+      MDB_CUDA(cudaStreamSynchronize(e->st_copy));
+      MDB_CUDA(cudaMemcpy(rgb_out, im.ptr, need, cudaMemcpyDeviceToHost));
+    }
+  } catch (const CudaError& ex) {
+    return fail(e, MDB_ERR_CUDA, ex.msg);
+  }
+  return MDB_OK;
 }
 
 int mdb_set_image_size(mdb_engine* e, int32_t img_size) {

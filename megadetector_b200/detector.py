@@ -326,6 +326,49 @@ class B200Detector:
                         results[i] = {'file': ids[i], 'detections': None, 'failure': FAILURE_INFER}
         return results
 
+    def generate_detections_from_jpeg_files(self, files, detection_threshold=0.00001, verbose=False):
+        """
+        JPEG files decoded on the GPU (nvJPEG) and detected in one call: the counterpart of `vis_utils.load_image` +
+        `generate_detections_one_batch` (run_detector_batch.py:724,756) for `.jpg` files.  `files`: list of paths or of
+        (image_id, bytes) pairs.  Same records; unreadable files get FAILURE_IMAGE_OPEN.  Decoded pixels differ from PIL's by
+        a few LSB (different JPEG arithmetic), so confidences may differ in the third decimal.
+        """
+        if self.engine is None:
+            raise RuntimeError('this B200Detector was created with preprocess_only; it cannot run inference')
+        ids, blobs = [], []
+        for f in files:
+            if isinstance(f, (tuple, list)):
+                ids.append(f[0])
+                blobs.append(bytes(f[1]))
+            else:
+                ids.append(f)
+                try:
+                    with open(f, 'rb') as fh:
+                        blobs.append(fh.read())
+                except Exception:
+                    blobs.append(None)
+        if self._current_image_size != self.default_image_size:
+            self.engine.set_image_size(self.default_image_size)
+            self._current_image_size = self.default_image_size
+        gc_was_enabled = gc.isenabled()
+        gc.disable()
+        try:
+            det, cnt, _, status, hw = self.engine.infer_jpeg_batch(blobs, detection_threshold)
+            results = []
+            for i, iid in enumerate(ids):
+                if status[i] == _capi.MDB_IMG_BAD_INPUT:
+                    results.append({'file': iid, 'detections': None, 'failure': FAILURE_IMAGE_OPEN})
+                elif status[i] != _capi.MDB_IMG_OK:
+                    results.append({'file': iid, 'detections': None, 'failure': FAILURE_INFER})
+                else:
+                    dets, max_conf = format_detections(det[i], cnt[i], int(hw[i, 0]), int(hw[i, 1]),
+                                                       self.use_model_native_classes)
+                    results.append({'file': iid, 'detections': dets, 'max_detection_conf': max_conf})
+        finally:
+            if gc_was_enabled:
+                gc.enable()
+        return results
+
     def generate_detections_one_image(self, img_original, image_id='unknown', detection_threshold=0.00001,
                                       image_size=None, augment=False, verbose=False):
         """pytorch_detector.py:1428-1478: wrapper around the batch function."""

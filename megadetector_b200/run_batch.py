@@ -1,0 +1,218 @@
+"""
+In-process multi-GPU batch driver: `python -m megadetector_b200.run_batch MODEL IMAGE_DIR OUT.json --gpus N`.
+
+The reference scales out by hand: the notebook splits the file list into N contiguous chunks, writes N shell scripts with
+CUDA_VISIBLE_DEVICES=i, runs N copies of the CLI and merges the N JSON files
+(/root/reference/notebooks/manage_local_batch.py:496-547,933-975; the author's TODO for an in-process `--gpus N`:
+/root/reference/TODO.md:203-205).  This module does the same inside one command: the file list is split with the
+reference's own chunking rule (sharding.split_list_into_n_chunks == ct_utils.split_list_into_n_chunks 'greedy'), one worker
+process per GPU owns one `B200Detector` (one `mdb_engine`, images independent end to end, NO collective on the data path),
+decodes its images with a thread pool, runs them in batches and returns its records; the parent merges them with the
+notebook's uniqueness check and writes one results file in the reference's format (run_detector_batch.py:1546-1700,
+format_version 1.4 fields: info / detection_categories / images).
+
+The result file is diff-equal to what N runs of `run_detector_batch` behind the INTEGRATION.md hook produce, because every
+record comes from the same `B200Detector.generate_detections_one_batch` call and images never interact.
+"""
+import argparse
+import json
+import os
+import sys
+import time
+from concurrent.futures import ThreadPoolExecutor
+
+from . import sharding
+
+IMAGE_EXTENSIONS = ('.jpg', '.jpeg', '.gif', '.png', '.tif', '.tiff', '.bmp')  # path_utils.IMG_EXTENSIONS
+DEFAULT_OUTPUT_CONFIDENCE_THRESHOLD = 0.005  # run_detector.py DEFAULT_OUTPUT_CONFIDENCE_THRESHOLD
+
+
+def find_images(folder, recursive=True):
+    """path_utils.find_images semantics: case-insensitive extension match, sorted."""
+    out = []
+    if recursive:
+        for root, _, files in os.walk(folder):
+            out.extend(os.path.join(root, f) for f in files if f.lower().endswith(IMAGE_EXTENSIONS))
+    else:
+        out = [os.path.join(folder, f) for f in os.listdir(folder) if f.lower().endswith(IMAGE_EXTENSIONS)]
+    return sorted(out)
+
+
+def load_image(path):
+    """visualization_utils.load_image (visualization_utils.py:103-176,306-323): PIL, RGB, EXIF orientation applied."""
+    from PIL import Image
+    image = Image.open(path)
+    if image.mode not in ('RGBA', 'RGB', 'L', 'I;16'):
+        raise AttributeError('Image {} uses unsupported mode {}'.format(path, image.mode))
+    if image.mode in ('RGBA', 'L'):
+        image = image.convert(mode='RGB')
+    try:
+        exif = image._getexif()
+        orientation = exif.get(274, None)
+        rotations = {3: 180, 6: 270, 8: 90}
+        if orientation is not None and orientation != 1 and orientation in rotations:
+            image = image.rotate(rotations[orientation], expand=True)
+    except Exception:
+        pass
+    image.load()
+    return image
+
+
+def process_files(detector, files, batch_size, confidence_threshold, loader_threads=8, quiet=True, gpu_decode=False):
+    """One worker's loop: decode with a thread pool one batch ahead, detect, apply the output threshold
+    (run_detector_batch.py:724-767).  gpu_decode: `.jpg` / `.jpeg` files are read as bytes and decoded by nvJPEG on the GPU
+    (B200Detector.generate_detections_from_jpeg_files); other formats keep the PIL path."""
+    results = []
+    if gpu_decode and hasattr(detector, 'generate_detections_from_jpeg_files'):
+        jpegs = [f for f in files if f.lower().endswith(('.jpg', '.jpeg'))]
+        files = [f for f in files if not f.lower().endswith(('.jpg', '.jpeg'))]
+
+        def read(f):
+            try:
+                with open(f, 'rb') as fh:
+                    return (f, fh.read())
+            except Exception:
+                return (f, b'')
+
+        jb = [jpegs[i:i + batch_size] for i in range(0, len(jpegs), batch_size)]
+        with ThreadPoolExecutor(max_workers=loader_threads) as pool:
+            pending = list(pool.map(read, jb[0])) if jb else None
+            for bi in range(len(jb)):
+                blobs = pending
+                nxt = pool.map(read, jb[bi + 1]) if bi + 1 < len(jb) else None
+                for r in detector.generate_detections_from_jpeg_files(blobs):
+                    if r.get('detections') is None:
+                        results.append({'file': r['file'], 'failure': r['failure']})
+                    else:
+                        r['detections'] = [d for d in r['detections'] if d['conf'] >= confidence_threshold]
+                        results.append(r)
+                pending = list(nxt) if nxt is not None else None
+
+    def load(f):
+        try:
+            return load_image(f)
+        except Exception as e:
+            if not quiet:
+                print('Image {} cannot be loaded: {}'.format(f, e))
+            return None
+
+    batches = [files[i:i + batch_size] for i in range(0, len(files), batch_size)]
+    with ThreadPoolExecutor(max_workers=loader_threads) as pool:
+        pending = pool.map(load, batches[0]) if batches else None
+        for bi, batch in enumerate(batches):
+            images = list(pending)
+            pending = pool.map(load, batches[bi + 1]) if bi + 1 < len(batches) else None
+            ok = [(f, im) for f, im in zip(batch, images) if im is not None]
+            for f, im in zip(batch, images):
+                if im is None:
+                    results.append({'file': f, 'failure': 'image access failure'})
+            if ok:
+                recs = detector.generate_detections_one_batch([im for _, im in ok], [f for f, _ in ok])
+                for r in recs:
+                    if 'failure' in r and r.get('detections') is None:
+                        results.append({'file': r['file'], 'failure': r['failure']})
+                        continue
+                    r['detections'] = [d for d in r['detections'] if d['conf'] >= confidence_threshold]
+                    results.append(r)
+    return results
+
+
+def _worker(rank, world, model_file, files, batch_size, confidence_threshold, detector_options, factory, out_queue,
+            gpu_decode=False):
+    try:
+        opts = dict(detector_options or {})
+        opts.setdefault('max_batch', batch_size)
+        opts['device'] = 'cuda:{}'.format(rank)
+        if factory is not None:
+            mod, name = factory.rsplit(':', 1)
+            import importlib
+            detector = getattr(importlib.import_module(mod), name)(model_file, opts)
+        else:
+            from .detector import B200Detector
+            detector = B200Detector(model_file, opts)
+        mine = sharding.shard_for_rank(files, rank, world)
+        t0 = time.time()
+        res = process_files(detector, mine, batch_size, confidence_threshold, gpu_decode=gpu_decode)
+        out_queue.put((rank, res, time.time() - t0, None))
+        if hasattr(detector, 'close'):
+            detector.close()
+    except Exception as e:  # never leave the parent waiting
+        import traceback
+        out_queue.put((rank, None, 0.0, '{}\n{}'.format(e, traceback.format_exc())))
+
+
+def run_sharded(model_file, files, n_gpus, batch_size=64, confidence_threshold=DEFAULT_OUTPUT_CONFIDENCE_THRESHOLD,
+                detector_options=None, detector_factory=None, gpu_decode=False):
+    """
+    Runs `files` on `n_gpus` GPUs of this box, one process per GPU.  Returns the merged records sorted by file.
+    detector_factory: optional 'module:callable' (model_file, options) -> detector, for tests of the plumbing.
+    """
+    import multiprocessing as mp
+    files = list(files)
+    n_gpus = max(1, min(int(n_gpus), max(1, len(files))))
+    ctx = mp.get_context('spawn')  # CUDA contexts do not survive fork
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, n_gpus, model_file, files, batch_size, confidence_threshold,
+                                               detector_options, detector_factory, q, gpu_decode)) for r in range(n_gpus)]
+    for p in procs:
+        p.start()
+    parts, times = [None] * n_gpus, [0.0] * n_gpus
+    for _ in range(n_gpus):
+        rank, res, dt, err = q.get()
+        if err is not None:
+            for p in procs:
+                p.terminate()
+            raise RuntimeError('worker {} failed: {}'.format(rank, err))
+        parts[rank], times[rank] = res, dt
+    for p in procs:
+        p.join()
+    merged = [r for part in parts for r in part]
+    names = [r['file'] for r in merged]
+    if len(set(names)) != len(names):  # manage_local_batch.py:947-958
+        raise ValueError('duplicate images in the merged results')
+    return sorted(merged, key=lambda r: r['file']), times
+
+
+def write_results(results, output_file, relative_path_base=None, detector_file=None):
+    """The subset of run_detector_batch.write_results_to_file (:1546-1700) this driver needs; same JSON layout."""
+    images = []
+    for r in results:
+        r = dict(r)
+        if relative_path_base is not None:
+            r['file'] = os.path.relpath(r['file'], relative_path_base).replace('\\', '/')
+        r.pop('max_detection_conf', None)  # include_max_conf=False is the reference's default
+        images.append(r)
+    images.sort(key=lambda r: r['file'])
+    info = {'detection_completion_time': time.strftime('%Y-%m-%d %H:%M:%S', time.gmtime()), 'format_version': '1.4'}
+    if detector_file is not None:
+        info['detector'] = os.path.basename(detector_file)
+    out = {'images': images, 'detection_categories': {'1': 'animal', '2': 'person', '3': 'vehicle'}, 'info': info}
+    with open(output_file, 'w') as f:
+        json.dump(out, f, indent=1)
+    return output_file
+
+
+def main(argv=None):
+    ap = argparse.ArgumentParser(description=__doc__.split('\n\n')[0])
+    ap.add_argument('detector_file')
+    ap.add_argument('image_dir')
+    ap.add_argument('output_file')
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--batch_size', type=int, default=64)
+    ap.add_argument('--threshold', type=float, default=DEFAULT_OUTPUT_CONFIDENCE_THRESHOLD)
+    ap.add_argument('--recursive', action='store_true')
+    ap.add_argument('--output_relative_filenames', action='store_true')
+    ap.add_argument('--gpu_decode', action='store_true', help='decode .jpg files with nvJPEG on the GPU instead of PIL')
+    args = ap.parse_args(argv)
+    files = find_images(args.image_dir, args.recursive)
+    t0 = time.time()
+    results, times = run_sharded(args.detector_file, files, args.gpus, args.batch_size, args.threshold,
+                                 gpu_decode=args.gpu_decode)
+    write_results(results, args.output_file, args.image_dir if args.output_relative_filenames else None, args.detector_file)
+    print('Processed {} images on {} GPUs in {:.1f} s (per-GPU detector time: {})'.format(
+        len(files), args.gpus, time.time() - t0, ', '.join('{:.1f}'.format(t) for t in times)))
+    return 0
+
+
+if __name__ == '__main__':
+    sys.exit(main())
