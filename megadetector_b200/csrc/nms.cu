@@ -39,9 +39,12 @@ constexpr int kNmsThreads = 1024;
 constexpr int kNmsWarps = kNmsThreads / 32;
 constexpr int kWin = 512;                  // candidates per suppression window
 constexpr int kWinWords = kWin / 32;       // words per row of the window's suppression bit-matrix
-constexpr int kSortSmemKeys = 8192;        // lists up to this length are sorted in shared memory
-// dynamic shared memory: two key buffers (sort ping-pong); after the sort the spare one holds the window state
-constexpr size_t kNmsDynSmem = 2 * static_cast<size_t>(kSortSmemKeys) * sizeof(unsigned long long);
+constexpr int kSortSmemKeys = 8192;        // keys sorted per round in shared memory
+constexpr int kBins = 8192;                // confidence bins (2^15 float bit patterns each) used to cut long lists into rounds
+constexpr int kBinShift = 15;
+// dynamic shared memory: two key buffers (sort ping-pong; after the sort the spare one holds the window state) and the
+// cumulative confidence histogram of long lists
+constexpr size_t kNmsDynSmem = 2 * static_cast<size_t>(kSortSmemKeys) * sizeof(unsigned long long) + kBins * sizeof(uint32_t);
 
 float float_floor_of_double(double t) {
   float f = static_cast<float>(t);
@@ -147,7 +150,7 @@ __global__ void cand_from_pred_kernel(const float* __restrict__ pred, int anchor
 // Stable LSD passes over 8 digits of 8 bits; a pass whose digit is the same for all keys moves nothing and is skipped.
 // kin/kout may live in shared or in global memory.  Returns the buffer that holds the sorted keys.
 __device__ unsigned long long* radix_sort_keys(unsigned long long* kin, unsigned long long* kout, int n,
-                                               uint32_t* s_digit_off, uint16_t (*s_warp_digit)[256], int* s_flag) {
+                                               uint32_t* s_digit_off, uint32_t (*s_warp_digit)[256], int* s_flag) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int pass = 0; pass < 8 && n > 1; ++pass) {
     const int shift = pass * 8;
@@ -193,21 +196,20 @@ __device__ unsigned long long* radix_sort_keys(unsigned long long* kin, unsigned
       __syncwarp();
       const uint32_t peers = __match_any_sync(0xffffffffu, d);
       const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
-      if (valid && rank == 0) s_warp_digit[warp][d] = static_cast<uint16_t>(__popc(peers));
+      if (valid && rank == 0) s_warp_digit[warp][d] = static_cast<uint32_t>(__popc(peers));
       __syncthreads();
-      uint32_t pos = 0;
-      if (valid) {
-        uint32_t before = 0;
-        for (int w2 = 0; w2 < warp; ++w2) before += s_warp_digit[w2][d];
-        pos = s_digit_off[d] + before + rank;
-      }
-      __syncthreads();
+      // per digit: exclusive scan of the warps' counts on top of the running digit offset (one thread per digit)
       if (tid < 256) {
-        uint32_t tot = 0;
-        for (int w2 = 0; w2 < kNmsWarps; ++w2) tot += s_warp_digit[w2][tid];
-        s_digit_off[tid] += tot;
+        uint32_t run = s_digit_off[tid];
+        for (int w2 = 0; w2 < kNmsWarps; ++w2) {
+          const uint32_t c = s_warp_digit[w2][tid];
+          s_warp_digit[w2][tid] = run;
+          run += c;
+        }
+        s_digit_off[tid] = run;
       }
-      if (valid) kout[pos] = k;
+      __syncthreads();
+      if (valid) kout[s_warp_digit[warp][d] + rank] = k;
       __syncthreads();
     }
     unsigned long long* t = kin; kin = kout; kout = t;
@@ -224,7 +226,7 @@ nms_image_kernel(const float* __restrict__ pred, int anchors, int no, float thr,
                  int32_t* __restrict__ det_count, int32_t* __restrict__ kept_anchor) {
   extern __shared__ __align__(16) unsigned char s_dyn[];
   __shared__ uint32_t s_digit_off[256];
-  __shared__ uint16_t s_warp_digit[kNmsWarps][256];
+  __shared__ uint32_t s_warp_digit[kNmsWarps][256];
   __shared__ uint32_t s_warp_cnt[kNmsWarps];
   __shared__ int s_flag, s_kept, s_A;
   __shared__ Cand s_keep[kMaxDetCap];
@@ -239,121 +241,199 @@ nms_image_kernel(const float* __restrict__ pred, int anchors, int no, float thr,
   unsigned long long* sm0 = reinterpret_cast<unsigned long long*>(s_dyn);
   unsigned long long* sm1 = sm0 + kSortSmemKeys;
 
-  // ------------------------------- K7a: sort -------------------------------
-  const unsigned long long* sorted;
-  unsigned char* spare;  // >= 64 KB of shared memory not holding the sorted keys
+  uint32_t* s_cum = reinterpret_cast<uint32_t*>(s_dyn + 2 * static_cast<size_t>(kSortSmemKeys) * sizeof(unsigned long long));
+  if (tid == 0) s_kept = 0;
+  __syncthreads();
+
+  // K7b on `m` sorted keys (window state lives in `spare`, >= 51 KB of shared memory that does not hold the keys);
+  // continues from the boxes kept so far, returns when the keys are exhausted or max_det boxes are kept
+  auto suppress_sorted = [&](const unsigned long long* sorted, int m, unsigned char* spare) {
+    Cand* s_win = reinterpret_cast<Cand*>(spare);                                          // 512 x 28 B = 14336
+    int* s_win_anchor = reinterpret_cast<int*>(spare + 14336);                              // 2048
+    uint8_t* s_dead1 = reinterpret_cast<uint8_t*>(spare + 14336 + 2048);                     // 512
+    uint16_t* s_alist = reinterpret_cast<uint16_t*>(spare + 14336 + 2048 + 512);            // 1024
+    uint32_t* s_sup = reinterpret_cast<uint32_t*>(spare + 14336 + 2048 + 512 + 1024);       // 512 x 16 x 4 = 32768
+    const int t = tid & (kWin - 1), half = tid >> 9;
+    for (int base = 0; base < m; base += kWin) {
+      const int i = base + t;
+      const bool valid = i < m;
+      if (half == 0) {
+        Cand c;
+        c.cls = -1;
+        int anc = -1;
+        if (valid) {
+          anc = static_cast<int>(static_cast<uint32_t>(sorted[i]));
+          eval_anchor(P + static_cast<size_t>(anc) * no, no, thr, c);  // always a candidate
+        }
+        s_win[t] = c;
+        s_win_anchor[t] = anc;
+      }
+      __syncthreads();
+      const Cand me = s_win[t];
+      const int kc = s_kept;
+      // (1) against the boxes kept so far: each half of the block scans half of the list
+      bool dead = !valid;
+      {
+        const int k0 = half ? (kc >> 1) : 0, k1 = half ? kc : (kc >> 1);
+        for (int k = k0; k < k1 && !dead; ++k)
+          if (s_keep[k].cls == me.cls && iou_exceeds(s_keep[k], me, iou_floor)) dead = true;
+      }
+      if (half == 1) s_dead1[t] = dead ? 1 : 0;
+      __syncthreads();
+      // (2) compact the survivors of the window, in rank order
+      bool alive = false;
+      if (half == 0) {
+        alive = !dead && !s_dead1[t];
+        const uint32_t bal = __ballot_sync(0xffffffffu, alive);
+        if (lane == 0) s_warp_cnt[warp] = __popc(bal);
+      }
+      __syncthreads();
+      if (half == 0) {
+        uint32_t before = 0, total = 0;
+        for (int w2 = 0; w2 < kWin / 32; ++w2) {
+          const uint32_t cnt = s_warp_cnt[w2];
+          if (w2 < warp) before += cnt;
+          total += cnt;
+        }
+        const uint32_t bal = __ballot_sync(0xffffffffu, alive);
+        if (alive) s_alist[before + __popc(bal & ((1u << lane) - 1u))] = static_cast<uint16_t>(t);
+        if (tid == 0) s_A = static_cast<int>(total);
+      }
+      __syncthreads();
+      const int A = s_A;
+      if (A > 0) {
+        // (3) sup[i][w]: bit b set <=> survivor j = 32*w + b ranks after i, has i's class and overlaps i beyond the threshold
+        const int wpr = (A + 31) >> 5;
+        for (int idx = tid; idx < A * wpr; idx += kNmsThreads) {
+          const int ri = idx / wpr, w = idx - ri * wpr;
+          uint32_t bits = 0;
+          if (w * 32 + 31 > ri) {
+            const Cand ci = s_win[s_alist[ri]];
+            const int j0 = w * 32;
+#pragma unroll 4
+            for (int b = 0; b < 32; ++b) {
+              const int j = j0 + b;
+              if (j > ri && j < A) {
+                const Cand cj = s_win[s_alist[j]];
+                if (cj.cls == ci.cls && iou_exceeds(ci, cj, iou_floor)) bits |= 1u << b;
+              }
+            }
+          }
+          s_sup[ri * kWinWords + w] = bits;
+        }
+        __syncthreads();
+        // (4) one warp resolves the window: lane l owns word l of the "removed" bit-vector
+        if (warp == 0) {
+          uint32_t removed = 0;
+          int kept = kc;
+          uint32_t row = lane < wpr ? s_sup[lane] : 0u;
+          for (int ri = 0; ri < A; ++ri) {
+            const uint32_t next = (ri + 1 < A && lane < wpr) ? s_sup[(ri + 1) * kWinWords + lane] : 0u;  // independent of the decision
+            const uint32_t r = __shfl_sync(0xffffffffu, removed, ri >> 5);
+            if (!((r >> (ri & 31)) & 1u)) {
+              const int src = s_alist[ri];
+              if (lane < 7) reinterpret_cast<uint32_t*>(&s_keep[kept])[lane] = reinterpret_cast<const uint32_t*>(&s_win[src])[lane];
+              if (lane == 7) s_keep_anchor[kept] = s_win_anchor[src];
+              ++kept;
+              if (kept >= max_det) break;
+              removed |= row;
+            }
+            row = next;
+          }
+          if (lane == 0) s_kept = kept;
+        }
+      }
+      __syncthreads();
+      if (s_kept >= max_det) break;
+    }
+    __syncthreads();
+  };
+
   if (n <= kSortSmemKeys) {
+    // ------------------------------- short list: one round, everything in shared memory -------------------------------
     for (int i = tid; i < n; i += kNmsThreads) sm0[i] = g0[i];
     __syncthreads();
     unsigned long long* res = radix_sort_keys(sm0, sm1, n, s_digit_off, s_warp_digit, &s_flag);
-    sorted = res;
-    spare = reinterpret_cast<unsigned char*>(res == sm0 ? sm1 : sm0);
+    suppress_sorted(res, n, reinterpret_cast<unsigned char*>(res == sm0 ? sm1 : sm0));
   } else {
-    sorted = radix_sort_keys(g0, g1, n, s_digit_off, s_warp_digit, &s_flag);
-    spare = s_dyn;
-  }
-  // window state in the spare buffer: candidates of the window, compacted survivor list, suppression bit-matrix
-  Cand* s_win = reinterpret_cast<Cand*>(spare);                                          // 512 x 28 B = 14336
-  int* s_win_anchor = reinterpret_cast<int*>(spare + 14336);                              // 2048
-  uint8_t* s_dead1 = reinterpret_cast<uint8_t*>(spare + 14336 + 2048);                     // 512
-  uint16_t* s_alist = reinterpret_cast<uint16_t*>(spare + 14336 + 2048 + 512);            // 1024
-  uint32_t* s_sup = reinterpret_cast<uint32_t*>(spare + 14336 + 2048 + 512 + 1024);       // 512 x 16 x 4 = 32768
-
-  // ------------------------------- K7b: greedy class-aware suppression -------------------------------
-  if (tid == 0) s_kept = 0;
-  __syncthreads();
-  const int t = tid & (kWin - 1), half = tid >> 9;
-  for (int base = 0; base < n; base += kWin) {
-    const int i = base + t;
-    const bool valid = i < n;
-    if (half == 0) {
-      Cand c;
-      c.cls = -1;
-      int anc = -1;
-      if (valid) {
-        anc = static_cast<int>(static_cast<uint32_t>(sorted[i]));
-        eval_anchor(P + static_cast<size_t>(anc) * no, no, thr, c);  // always a candidate
+    // ------------------------------- long list: rounds of <= 8192 keys, highest confidences first -------------------------------
+    // cumulative histogram over confidence bins (ascending key == descending confidence)
+    constexpr uint32_t kBase = 0xC07FFFFFu;  // ~bits(1.0f): the smallest key high word
+    auto bin_of = [&](unsigned long long k) -> uint32_t {
+      const uint32_t hi = static_cast<uint32_t>(k >> 32);
+      const uint32_t b = (hi > kBase ? hi - kBase : 0u) >> kBinShift;
+      return b < static_cast<uint32_t>(kBins - 1) ? b : static_cast<uint32_t>(kBins - 1);
+    };
+    for (int i = tid; i < kBins; i += kNmsThreads) s_cum[i] = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += kNmsThreads) atomicAdd(&s_cum[bin_of(g0[i])], 1u);
+    __syncthreads();
+    {  // inclusive scan of 8192 counters: 8 per thread, warp scan, block scan through s_warp_cnt
+      uint32_t loc[8], sum = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { loc[j] = s_cum[tid * 8 + j]; sum += loc[j]; }
+      uint32_t incl = sum;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
       }
-      s_win[t] = c;
-      s_win_anchor[t] = anc;
-    }
-    __syncthreads();
-    const Cand me = s_win[t];
-    const int kc = s_kept;
-    // (1) against the boxes kept so far: each half of the block scans half of the list
-    bool dead = !valid;
-    {
-      const int k0 = half ? (kc >> 1) : 0, k1 = half ? kc : (kc >> 1);
-      for (int k = k0; k < k1 && !dead; ++k)
-        if (s_keep[k].cls == me.cls && iou_exceeds(s_keep[k], me, iou_floor)) dead = true;
-    }
-    if (half == 1) s_dead1[t] = dead ? 1 : 0;
-    __syncthreads();
-    // (2) compact the survivors of the window, in rank order
-    bool alive = false;
-    if (half == 0) {
-      alive = !dead && !s_dead1[t];
-      const uint32_t bal = __ballot_sync(0xffffffffu, alive);
-      if (lane == 0) s_warp_cnt[warp] = __popc(bal);
-    }
-    __syncthreads();
-    if (half == 0) {
-      uint32_t before = 0, total = 0;
-      for (int w2 = 0; w2 < kWin / 32; ++w2) {
-        const uint32_t cnt = s_warp_cnt[w2];
-        if (w2 < warp) before += cnt;
-        total += cnt;
-      }
-      const uint32_t bal = __ballot_sync(0xffffffffu, alive);
-      if (alive) s_alist[before + __popc(bal & ((1u << lane) - 1u))] = static_cast<uint16_t>(t);
-      if (tid == 0) s_A = static_cast<int>(total);
-    }
-    __syncthreads();
-    const int A = s_A;
-    if (A > 0) {
-      // (3) sup[i][w]: bit b set <=> survivor j = 32*w + b ranks after i, has i's class and overlaps i beyond the threshold
-      const int wpr = (A + 31) >> 5;
-      for (int idx = tid; idx < A * wpr; idx += kNmsThreads) {
-        const int ri = idx / wpr, w = idx - ri * wpr;
-        uint32_t bits = 0;
-        if (w * 32 + 31 > ri) {
-          const Cand ci = s_win[s_alist[ri]];
-          const int j0 = w * 32;
-#pragma unroll 4
-          for (int b = 0; b < 32; ++b) {
-            const int j = j0 + b;
-            if (j > ri && j < A) {
-              const Cand cj = s_win[s_alist[j]];
-              if (cj.cls == ci.cls && iou_exceeds(ci, cj, iou_floor)) bits |= 1u << b;
-            }
-          }
-        }
-        s_sup[ri * kWinWords + w] = bits;
-      }
+      if (lane == 31) s_warp_cnt[warp] = incl;
       __syncthreads();
-      // (4) one warp resolves the window: lane l owns word l of the "removed" bit-vector
-      if (warp == 0) {
-        uint32_t removed = 0;
-        int kept = kc;
-        uint32_t row = lane < wpr ? s_sup[lane] : 0u;
-        for (int ri = 0; ri < A; ++ri) {
-          const uint32_t next = (ri + 1 < A && lane < wpr) ? s_sup[(ri + 1) * kWinWords + lane] : 0u;  // independent of the decision
-          const uint32_t r = __shfl_sync(0xffffffffu, removed, ri >> 5);
-          if (!((r >> (ri & 31)) & 1u)) {
-            const int src = s_alist[ri];
-            if (lane < 7) reinterpret_cast<uint32_t*>(&s_keep[kept])[lane] = reinterpret_cast<const uint32_t*>(&s_win[src])[lane];
-            if (lane == 7) s_keep_anchor[kept] = s_win_anchor[src];
-            ++kept;
-            if (kept >= max_det) break;
-            removed |= row;
-          }
-          row = next;
-        }
-        if (lane == 0) s_kept = kept;
-      }
+      uint32_t before = 0;
+      for (int w2 = 0; w2 < warp; ++w2) before += s_warp_cnt[w2];
+      uint32_t run = before + incl - sum;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { run += loc[j]; s_cum[tid * 8 + j] = run; }
+      __syncthreads();
     }
-    __syncthreads();
-    if (s_kept >= max_det) break;
+    int lo = -1;  // bins <= lo have been processed
+    bool fallback = false;
+    while (lo < kBins - 1 && s_kept < max_det) {
+      const uint32_t done = lo >= 0 ? s_cum[lo] : 0u;
+      if (done >= static_cast<uint32_t>(n)) break;
+      // largest hi with cum[hi] - done <= kSortSmemKeys (binary search; every thread computes the same value)
+      int a = lo + 1, b = kBins - 1;
+      if (s_cum[a] - done > static_cast<uint32_t>(kSortSmemKeys)) { fallback = true; break; }  // one bin alone is too long
+      while (a < b) {
+        const int mid = (a + b + 1) >> 1;
+        if (s_cum[mid] - done <= static_cast<uint32_t>(kSortSmemKeys)) a = mid; else b = mid - 1;
+      }
+      const int hi = a;
+      const int m = static_cast<int>(s_cum[hi] - done);
+      if (m > 0) {
+        if (tid == 0) s_A = 0;
+        __syncthreads();
+        for (int base = 0; base < n; base += kNmsThreads) {
+          const int i = base + tid;
+          unsigned long long k = 0;
+          bool take = false;
+          if (i < n) {
+            k = g0[i];
+            const int bb = static_cast<int>(bin_of(k));
+            take = bb > lo && bb <= hi;
+          }
+          const uint32_t bal = __ballot_sync(0xffffffffu, take);
+          int wbase = 0;
+          if (lane == 0 && bal) wbase = atomicAdd(&s_A, __popc(bal));
+          wbase = __shfl_sync(0xffffffffu, wbase, 0);
+          if (take) sm0[wbase + __popc(bal & ((1u << lane) - 1u))] = k;
+        }
+        __syncthreads();
+        unsigned long long* res = radix_sort_keys(sm0, sm1, m, s_digit_off, s_warp_digit, &s_flag);
+        suppress_sorted(res, m, reinterpret_cast<unsigned char*>(res == sm0 ? sm1 : sm0));
+      }
+      lo = hi;
+      __syncthreads();
+    }
+    if (fallback) {
+      // a single confidence bin holds more than 8192 candidates (mass ties): sort the whole list in global memory and
+      // continue after the keys already processed (the rounds above consumed exactly the first cum[lo] sorted keys)
+      const uint32_t done = lo >= 0 ? s_cum[lo] : 0u;
+      __syncthreads();
+      const unsigned long long* sorted = radix_sort_keys(g0, g1, n, s_digit_off, s_warp_digit, &s_flag);
+      suppress_sorted(sorted + done, n - static_cast<int>(done), s_dyn);
+    }
   }
   __syncthreads();
 

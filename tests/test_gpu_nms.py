@@ -66,12 +66,14 @@ def test_nms_empty_and_all_below_threshold(engine):
     assert cnt.tolist() == [0, 0]
 
 
-@pytest.mark.parametrize('n_cand', [1, 31, 511, 512, 513, 1025, 8191, 8192, 8193, 30000])
-def test_nms_candidate_count_boundaries(engine, n_cand):
-    """Window (512) and shared-memory sort (8192) boundaries of the kernel, with many exactly equal confidences (ties must
-    resolve to the lower anchor index, torchvision's stable order) and a batch whose images have different list lengths."""
+@pytest.mark.parametrize('n_cand,levels', [(1, 40), (31, 40), (511, 40), (512, 40), (513, 40), (1025, 40), (8191, 40),
+                                           (8192, 40), (8193, 40), (30000, 40), (30000, 4000), (20000, 2), (9000, 1)])
+def test_nms_candidate_count_boundaries(engine, n_cand, levels):
+    """Window (512) and shared-memory round (8192) boundaries of the kernel, with many exactly equal confidences (ties must
+    resolve to the lower anchor index, torchvision's stable order), a batch whose images have different list lengths, long
+    lists cut into confidence rounds, and tie groups longer than a round (global-memory fallback sort)."""
     from oracle import nms as onms
-    rng = np.random.default_rng(n_cand)
+    rng = np.random.default_rng(n_cand + levels)
     anchors = 40000
     preds = []
     for b, nc_b in enumerate((n_cand, max(1, n_cand // 3), 0)):
@@ -79,7 +81,7 @@ def test_nms_candidate_count_boundaries(engine, n_cand):
         obj = np.full(anchors, 1e-7, np.float32)
         sel = rng.permutation(anchors)[:nc_b]
         # quantised confidences: large tie groups
-        obj[sel] = (rng.integers(1, 40, size=nc_b) / 40.0).astype(np.float32)
+        obj[sel] = (rng.integers(1, levels + 1, size=nc_b) / float(levels + 1)).astype(np.float32)
         p[:, 4] = obj
         p[:, 5:] = np.float32(0.5) * (1 + np.eye(3, dtype=np.float32)[rng.integers(0, 3, size=anchors)])
         preds.append(p)
