@@ -154,6 +154,13 @@ ConvOp* conv_build(const ConvDesc& d, int num_sms) {
     q.act = d.act;
     q.idesc = make_idesc_f16(256, static_cast<uint32_t>(q.BN));
     q.dbg = nullptr;
+    {
+      // Epilogue-bound layers (MMA time per tile = K/64 x 16 x BN/... < epilogue time ~ 14 x BN cycles, i.e. total K <~ 1024):
+      // the blocked producer / MMA threads back off instead of spinning (MDB_CONV_BACKOFF=<ns>, 0 = spin)
+      static const char* eb = getenv("MDB_CONV_BACKOFF");
+      const int ns = eb ? atoi(eb) : 0;
+      q.backoff_ns = (q.total_chunks * kc <= 1024) ? ns : 0;
+    }
     q.halo = 0;
     q.a_stages = 0;
     {

@@ -93,6 +93,10 @@ struct PairParams {
   int a_stages;    // halo mode: number of A (3-box) buffers
   uint32_t idesc;  // M = 256
   long long* dbg;  // per-CTA cycle counters (MDB_CONV_DEBUG=1 in a -DMDB_CONV_TIMERS build), null otherwise
+  int backoff_ns;  // > 0: the producer / MMA role threads sleep this long between polls of the barriers they are BLOCKED on when
+                   // the epilogue bounds the layer (ring full), instead of spinning: the two spinning role warps were a third of
+                   // all issued instructions of a 1x1 layer and share their SM sub-partitions with eight epilogue warps
+                   // (profiles/r02_ncu_c1x1_160_*)
   int probe;       // timing probes only (results are garbage), bit mask: 1 = skip TMA loads, 2 = skip MMAs, 4 = epilogue releases
                    // the accumulator without reading it, 8 = no global stores/residual loads, 16 = no SiLU
 };
@@ -252,6 +256,18 @@ __device__ __forceinline__ void mbar_wait_addr(uint32_t addr, uint32_t parity) {
     if ((++polls & 63u) == 0 && clock64() - t0 > 4000000000LL) { asm volatile("trap;"); }  // ~2 s of SM clocks
   }
 }
+// wait that yields the issue slots while blocked: used where being late by `ns` costs nothing (the waiter is ahead of the
+// epilogue by a whole accumulator / pipeline ring)
+__device__ __forceinline__ void mbar_wait_addr_backoff(uint32_t addr, uint32_t parity, uint32_t ns) {
+  if (mbar_try_wait_addr(addr, parity)) return;
+  if (ns == 0) { mbar_wait_addr(addr, parity); return; }
+  const long long t0 = clock64();
+  uint32_t polls = 0;
+  while (!mbar_try_wait_addr(addr, parity)) {
+    __nanosleep(ns);
+    if ((++polls & 63u) == 0 && clock64() - t0 > 4000000000LL) { asm volatile("trap;"); }
+  }
+}
 __device__ __forceinline__ void mbar_wait_addr_timed(uint32_t addr, uint32_t parity, long long& acc) {
   if (!kTimers) { mbar_wait_addr(addr, parity); return; }
   const long long t0 = clock64();
@@ -355,6 +371,7 @@ conv_pair_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
     const uint32_t full0_remote = mapa_rank(full0, 0);
     const uint32_t a_full0_remote = mapa_rank(a_full0, 0);
     const bool loads = !(kProbes && (p.probe & 1));
+    const uint32_t bo = static_cast<uint32_t>(p.backoff_ns);
     if (p.halo) {
       // ---- 3x3 / stride 1: per 64-channel chunk, three {64 ch, 8 px, 18 rows} boxes (one per kw shift) are
       // fetched once and serve all three kh taps (the kh shift is a 1024-byte offset in shared memory);
@@ -369,7 +386,8 @@ conv_pair_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
         const int ox0 = txi * kHaloTw - 1, oy0 = tyi * kHaloTh - 1;
         const int nb0 = n_tile * p.BN + static_cast<int>(rank * half_n);
         for (int c = 0; c < p.chunks; ++c) {
-          mbar_wait_addr_timed(a_empty0 + 8u * as, aph ^ 1u, w_empty);
+          if (kTimers) mbar_wait_addr_timed(a_empty0 + 8u * as, aph ^ 1u, w_empty);
+          else mbar_wait_addr_backoff(a_empty0 + 8u * as, aph ^ 1u, bo);
           if (el) {
             if (leader) mbar_arrive_expect_tx_addr(a_full0 + 8u * as, loads ? 2u * a_stage_bytes : 0u);
             else mbar_arrive_cluster_addr(a_full0_remote + 8u * as);
@@ -387,7 +405,8 @@ conv_pair_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
           int kcol = c * KC;
           const int tap_cols = p.chunks * KC;
           for (int kh = 0; kh < 3; ++kh, kcol += 3 * tap_cols) {
-            mbar_wait_addr_timed(empty0 + 8u * s, ph ^ 1u, w_empty);
+            if (kTimers) mbar_wait_addr_timed(empty0 + 8u * s, ph ^ 1u, w_empty);
+            else mbar_wait_addr_backoff(empty0 + 8u * s, ph ^ 1u, bo);
             if (el) {
               if (leader) mbar_arrive_expect_tx_addr(full0 + 8u * s, loads ? 6u * b_bytes : 0u);
               else mbar_arrive_cluster_addr(full0_remote + 8u * s);
@@ -414,7 +433,8 @@ conv_pair_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
         uint32_t w = p.tap_word[0];
         for (int q0 = 0; q0 < p.total_chunks; q0 += p.cps) {
           const int nch = min(p.cps, p.total_chunks - q0);
-          mbar_wait_addr_timed(empty0 + 8u * s, ph ^ 1u, w_empty);
+          if (kTimers) mbar_wait_addr_timed(empty0 + 8u * s, ph ^ 1u, w_empty);
+          else mbar_wait_addr_backoff(empty0 + 8u * s, ph ^ 1u, bo);
           if (el) {
             if (leader) mbar_arrive_expect_tx_addr(full0 + 8u * s, loads ? static_cast<uint32_t>(nch) * tx_stage : 0u);
             else mbar_arrive_cluster_addr(full0_remote + 8u * s);
@@ -458,7 +478,8 @@ conv_pair_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
       for (int tile = cluster_id; tile < total_tiles; tile += num_clusters, ++tcount) {
         const uint32_t acc = tcount & acc_mask;
         const uint32_t acc_ph = (tcount >> acc_shift) & 1u;
-        mbar_wait_addr_timed(acc_empty0 + 8u * acc, acc_ph ^ 1u, w_acc);
+        if (kTimers) mbar_wait_addr_timed(acc_empty0 + 8u * acc, acc_ph ^ 1u, w_acc);
+        else mbar_wait_addr_backoff(acc_empty0 + 8u * acc, acc_ph ^ 1u, static_cast<uint32_t>(p.backoff_ns));
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * acc_stride;
         if (p.halo) {
