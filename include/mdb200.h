@@ -65,6 +65,11 @@ typedef struct mdb_config {
   int32_t letterbox_scaleup; /* 1 in "classic" mode */
   float iou_thres;     /* 0.45 classic / 0.6 otherwise, pytorch_detector.py:1318-1321 */
   int32_t max_det;     /* 300 */
+  /* 0: "classic" (letterbox resize + auto pad), 1: "modern" (pytorch_detector.py:1036-1101: long side resized to img_size with
+   * cv2.INTER_AREA when shrinking / INTER_LINEAR when growing, then padded to ceil(side / stride + 0.5) * stride, boxes
+   * mapped back with ratio_pad).  letterbox_auto / letterbox_scaleup are ignored in mode 1. */
+  int32_t compat_mode;
+  int32_t use_ceil_for_resize; /* "use_ceil_for_resize" in compatibility_mode, pytorch_detector.py:1038,1052-1057 */
   mdb_arch arch;
 } mdb_config;
 
@@ -127,6 +132,13 @@ MDB_API int mdb_infer_jpeg_batch(mdb_engine* e, const uint8_t* const* jpeg, cons
 /* parity hook: decode one JPEG and return the RGB pixels ([h][w][3] u8), hw2 = {h, w}, backend = 1 hardware / 2 GPU hybrid */
 MDB_API int mdb_op_decode_jpeg(mdb_engine* e, const uint8_t* jpeg, size_t nbytes, uint8_t* rgb_out, size_t cap, int32_t* hw2,
                                int32_t* backend);
+
+/* mdb_infer_preprocessed with explicit scale_coords parameters per image: gain_pad[i] = {gain, pad_x, pad_y}, the
+ * ratio_pad the "modern" mode passes to scale_coords (pytorch_detector.py:1372-1381: gain = resized_h / original_h,
+ * pad = letterbox_pad); NULL = derive them from the shapes ("classic"). */
+MDB_API int mdb_infer_preprocessed_rp(mdb_engine* e, const uint8_t* const* lb_hwc, const int32_t* lh, const int32_t* lw,
+                              const int32_t* src_h, const int32_t* src_w, const float* gain_pad, int32_t n, float conf_thres,
+                              float* det_out, int32_t* det_count, int32_t* kept_anchor, int32_t* status);
 
 /* `image_size` argument of generate_detections_one_batch (pytorch_detector.py:1011-1024): long-side target of
  * the letterbox for subsequent calls (default cfg.img_size). */

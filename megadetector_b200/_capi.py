@@ -21,7 +21,7 @@ EXPORTS = [
     'mdb_create', 'mdb_load_weights', 'mdb_destroy', 'mdb_last_error', 'mdb_infer_batch', 'mdb_batch_begin', 'mdb_batch_next', 'mdb_infer_preprocessed',
     'mdb_letterbox_geometry', 'mdb_set_image_size', 'mdb_debug_fetch', 'mdb_last_timing', 'mdb_bench_resident', 'mdb_profile_steps', 'mdb_set_pipeline_split', 'mdb_launch_count', 'mdb_op_letterbox',
     'mdb_op_conv2d', 'mdb_op_nms', 'mdb_alloc_pinned', 'mdb_free_pinned', 'mdb_version',
-    'mdb_infer_jpeg_batch', 'mdb_op_decode_jpeg',
+    'mdb_infer_jpeg_batch', 'mdb_op_decode_jpeg', 'mdb_infer_preprocessed_rp',
     'mdb_debug_set_trace', 'mdb_debug_trace_names', 'mdb_debug_fetch_trace', 'mdb_op_upsample2x', 'mdb_op_sppf_pool', 'mdb_op_decode',
 ]
 
@@ -34,7 +34,8 @@ class MdbArch(C.Structure):
 class MdbConfig(C.Structure):
     _fields_ = [('struct_size', C.c_int32), ('device', C.c_int32), ('max_batch', C.c_int32), ('img_size', C.c_int32),
                 ('stride', C.c_int32), ('letterbox_auto', C.c_int32), ('letterbox_scaleup', C.c_int32),
-                ('iou_thres', C.c_float), ('max_det', C.c_int32), ('arch', MdbArch)]
+                ('iou_thres', C.c_float), ('max_det', C.c_int32), ('compat_mode', C.c_int32),
+                ('use_ceil_for_resize', C.c_int32), ('arch', MdbArch)]
 
 
 class MdbTensorDesc(C.Structure):
@@ -108,6 +109,9 @@ def load_library():
     lib.mdb_op_conv2d.restype = C.c_int
     lib.mdb_op_nms.argtypes = [vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_double, C.c_int32, vp, vp, vp]
     lib.mdb_op_nms.restype = C.c_int
+    lib.mdb_infer_preprocessed_rp.argtypes = [vp, P(vp), P(C.c_int32), P(C.c_int32), P(C.c_int32), P(C.c_int32), vp,
+                                              C.c_int32, C.c_float, vp, vp, vp, vp]
+    lib.mdb_infer_preprocessed_rp.restype = C.c_int
     lib.mdb_infer_jpeg_batch.argtypes = [vp, P(vp), P(C.c_size_t), C.c_int32, C.c_float, vp, vp, vp, vp, vp]
     lib.mdb_infer_jpeg_batch.restype = C.c_int
     lib.mdb_op_decode_jpeg.argtypes = [vp, vp, C.c_size_t, vp, C.c_size_t, P(C.c_int32), P(C.c_int32)]
@@ -144,7 +148,7 @@ DEFAULT_ANCHORS_PX = [
 
 def make_config(device=0, max_batch=8, img_size=1280, stride=64, letterbox_auto=True, letterbox_scaleup=True,
                 iou_thres=0.45, max_det=300, ch=(80, 160, 320, 640, 960, 1280), n_backbone=(4, 8, 12, 4, 4), n_head=4,
-                nc=3, anchors_px=None):
+                nc=3, anchors_px=None, compat_mode=0, use_ceil_for_resize=False):
     cfg = MdbConfig()
     cfg.struct_size = C.sizeof(MdbConfig)
     cfg.device = device
@@ -155,6 +159,8 @@ def make_config(device=0, max_batch=8, img_size=1280, stride=64, letterbox_auto=
     cfg.letterbox_scaleup = int(bool(letterbox_scaleup))
     cfg.iou_thres = iou_thres
     cfg.max_det = max_det
+    cfg.compat_mode = int(compat_mode)
+    cfg.use_ceil_for_resize = int(bool(use_ceil_for_resize))
     for i in range(6):
         cfg.arch.ch[i] = int(ch[i])
     for i in range(5):
@@ -320,7 +326,8 @@ class Engine:
                 if self.lib.mdb_batch_next(self.h, done, max(1, n), C.byref(nd)) != MDB_OK or nd.value == 0:
                     finished = True
 
-    def infer_preprocessed(self, images, src_shapes, conf_thres, want_anchors=True):
+    def infer_preprocessed(self, images, src_shapes, conf_thres, want_anchors=True, gain_pad=None):
+        """gain_pad: optional [n][3] (gain, pad_x, pad_y) = the ratio_pad of scale_coords ("modern" mode)."""
         n = len(images)
         ptrs = (C.c_void_p * n)()
         lh = (C.c_int32 * n)()
@@ -338,10 +345,11 @@ class Engine:
         cnt = np.zeros((n,), np.int32)
         anc = np.full((n, self.max_det), -1, np.int32) if want_anchors else None
         status = np.zeros((n,), np.int32)
-        rc = self.lib.mdb_infer_preprocessed(self.h, ptrs, lh, lw, sh, sw, n, float(conf_thres), det.ctypes.data,
-                                             cnt.ctypes.data, anc.ctypes.data if anc is not None else None,
-                                             status.ctypes.data)
-        self._check(rc, 'mdb_infer_preprocessed')
+        gp = None if gain_pad is None else np.ascontiguousarray(gain_pad, np.float32).reshape(n, 3)
+        rc = self.lib.mdb_infer_preprocessed_rp(self.h, ptrs, lh, lw, sh, sw, gp.ctypes.data if gp is not None else None, n,
+                                                float(conf_thres), det.ctypes.data, cnt.ctypes.data,
+                                                anc.ctypes.data if anc is not None else None, status.ctypes.data)
+        self._check(rc, 'mdb_infer_preprocessed_rp')
         return det, cnt, anc, status
 
     def infer_jpeg_batch(self, blobs, conf_thres, want_anchors=False):

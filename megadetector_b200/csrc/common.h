@@ -96,12 +96,20 @@ void pack_weights_stem_s2d(const float* w, int co, int co_pad, int ci_pad, std::
 // ---------------------------------------------------------------------------------------------
 struct LetterboxGeom {
   int src_h, src_w;
-  int new_w, new_h;  // new_unpad
+  int new_w, new_h;  // new_unpad ("classic") / size after the pre-resize ("modern")
   int top, bottom, left, right;
   int out_h, out_w;
   double ratio, dw, dh;
+  int interp = 0;    // 0: cv2.INTER_LINEAR (or no resize), 1: cv2.INTER_AREA ("modern" down-scaling)
+  // scale_coords inputs (yolov5 utils.general): classic -> gain/pad derived from the shapes; modern -> ratio_pad given
+  double sc_gain = 0, sc_pad_x = 0, sc_pad_y = 0;
 };
 LetterboxGeom letterbox_geometry(int h, int w, int img_size, int stride, bool autopad, bool scaleup);
+// "modern" compatibility mode (pytorch_detector.py:1036-1101): long side resized to img_size (INTER_AREA when shrinking,
+// INTER_LINEAR when growing, int() or ceil() of the scaled sides), then padded to ceil(side / stride + 0.5) * stride
+LetterboxGeom letterbox_geometry_modern(int h, int w, int img_size, int stride, bool use_ceil);
+// coefficient tables of cv::resize(INTER_AREA) for u8 (cv::computeResizeAreaTab): CSR over destination indices
+void area_tables(int ssize, int dsize, std::vector<int32_t>& first, std::vector<int32_t>& si, std::vector<float>& alpha);
 // coefficient tables of cv::resize(INTER_LINEAR) for u8: ofs[d], coef[2*d], coef[2*d+1]
 void linear_tables(int ssize, int dsize, bool vertical, std::vector<int32_t>& ofs, std::vector<int16_t>& coef);
 
@@ -114,6 +122,15 @@ struct PreImage {  // one per image, lives in device memory
   const int16_t* xcoef;
   const int32_t* yofs;
   const int16_t* ycoef;
+  // INTER_AREA ("modern" mode, mode != 0): taps of destination column / row d are [first[d], first[d+1])
+  int mode = 0;        // 0 linear, 1 area (generic, float taps), 2 area with integer scales (cv::ResizeAreaFast)
+  int iscale_x = 0, iscale_y = 0;
+  const int32_t* xa_first = nullptr;
+  const int32_t* xa_si = nullptr;
+  const float* xa_alpha = nullptr;
+  const int32_t* ya_first = nullptr;
+  const int32_t* ya_si = nullptr;
+  const float* ya_alpha = nullptr;
 };
 void preprocess_launch(const PreImage* d_imgs, int n, int out_h, int out_w, __half* dst, float max_scale,
                        cudaStream_t st);

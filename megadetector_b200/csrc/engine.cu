@@ -100,8 +100,10 @@ struct TableKey {
   }
 };
 struct DevTable {
-  int32_t* ofs = nullptr;
-  int16_t* coef = nullptr;
+  int32_t* ofs = nullptr;   // linear: source offsets; area: CSR `first`
+  int16_t* coef = nullptr;  // linear only
+  int32_t* si = nullptr;    // area: source index per tap
+  float* alpha = nullptr;   // area: weight per tap
 };
 
 struct ImgIn {
@@ -111,6 +113,7 @@ struct ImgIn {
   int src_h, src_w;  // original size for scale_coords
   int index;         // position in the caller's arrays
   bool on_device = false;  // ptr is device memory (JPEG path): K1 reads it in place, nothing is uploaded
+  double rp_gain = 0, rp_pad_x = 0, rp_pad_y = 0;  // dict inputs: explicit scale_coords ratio_pad ("modern"); 0 = from the shapes
 };
 
 struct Pending {
@@ -640,6 +643,57 @@ const DevTable& get_table(mdb_engine* e, int ssize, int dsize, bool vertical) {
   return e->tables.emplace(k, t).first->second;
 }
 
+// INTER_AREA tap tables (vertical == 2 / 3 in the cache key: area x / area y)
+const DevTable& get_area_table(mdb_engine* e, int ssize, int dsize, bool vertical) {
+  TableKey k{ssize, dsize, vertical ? 3 : 2};
+  auto it = e->tables.find(k);
+  if (it != e->tables.end()) return it->second;
+  std::vector<int32_t> first, si;
+  std::vector<float> alpha;
+  area_tables(ssize, dsize, first, si, alpha);
+  DevTable t;
+  MDB_CUDA(cudaMalloc(&t.ofs, first.size() * sizeof(int32_t)));
+  MDB_CUDA(cudaMalloc(&t.si, std::max<size_t>(1, si.size()) * sizeof(int32_t)));
+  MDB_CUDA(cudaMalloc(&t.alpha, std::max<size_t>(1, alpha.size()) * sizeof(float)));
+  MDB_CUDA(cudaMemcpy(t.ofs, first.data(), first.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+  MDB_CUDA(cudaMemcpy(t.si, si.data(), si.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+  MDB_CUDA(cudaMemcpy(t.alpha, alpha.data(), alpha.size() * sizeof(float), cudaMemcpyHostToDevice));
+  return e->tables.emplace(k, t).first->second;
+}
+
+// geometry of one raw image in the engine's compatibility mode
+LetterboxGeom geometry_for(const mdb_config& cfg, int h, int w) {
+  if (cfg.compat_mode == 1) return letterbox_geometry_modern(h, w, cfg.img_size, cfg.stride, cfg.use_ceil_for_resize != 0);
+  return letterbox_geometry(h, w, cfg.img_size, cfg.stride, cfg.letterbox_auto != 0, cfg.letterbox_scaleup != 0);
+}
+
+// fills the resize part of a PreImage (tables, mode) for source size (h, w) -> (g.new_h, g.new_w)
+void fill_resize(mdb_engine* e, PreImage& pi, int h, int w, const LetterboxGeom& g) {
+  pi.mode = 0;
+  pi.iscale_x = pi.iscale_y = 0;
+  pi.xa_first = pi.xa_si = pi.ya_first = pi.ya_si = nullptr;
+  pi.xa_alpha = pi.ya_alpha = nullptr;
+  const DevTable& tx = get_table(e, w, g.new_w, false);
+  const DevTable& ty = get_table(e, h, g.new_h, true);
+  pi.xofs = tx.ofs; pi.xcoef = tx.coef; pi.yofs = ty.ofs; pi.ycoef = ty.coef;
+  if (g.interp == 1 && (g.new_w != w || g.new_h != h)) {
+    // cv::resize(INTER_AREA): integer scales on both axes take the ResizeAreaFast path
+    const double sx = 1.0 / (static_cast<double>(g.new_w) / w), sy = 1.0 / (static_cast<double>(g.new_h) / h);
+    const int isx = static_cast<int>(std::lrint(sx)), isy = static_cast<int>(std::lrint(sy));
+    if (std::fabs(sx - isx) < 2.220446049250313e-16 && std::fabs(sy - isy) < 2.220446049250313e-16) {
+      pi.mode = 2;
+      pi.iscale_x = isx;
+      pi.iscale_y = isy;
+    } else {
+      pi.mode = 1;
+      const DevTable& ax = get_area_table(e, w, g.new_w, false);
+      const DevTable& ay = get_area_table(e, h, g.new_h, true);
+      pi.xa_first = ax.ofs; pi.xa_si = ax.si; pi.xa_alpha = ax.alpha;
+      pi.ya_first = ay.ofs; pi.ya_si = ay.si; pi.ya_alpha = ay.alpha;
+    }
+  }
+}
+
 void ensure_src(mdb_engine* e, int slot, size_t bytes) {
   if (e->d_src_bytes[slot] >= bytes) return;
   if (e->d_src[slot]) MDB_CUDA(cudaFree(e->d_src[slot]));
@@ -725,14 +779,13 @@ void enqueue_chunk(mdb_engine* e, Plan* P, const std::vector<ImgIn>& imgs, const
     PreImage& pi = e->h_pre[slot][i];
     pi.src = d; pi.src_stride = static_cast<long long>(row); pi.src_h = im.h; pi.src_w = im.w;
     pi.new_w = g.new_w; pi.new_h = g.new_h; pi.top = g.top; pi.left = g.left;
-    const DevTable& tx = get_table(e, im.w, g.new_w, false);
-    const DevTable& ty = get_table(e, im.h, g.new_h, true);
-    pi.xofs = tx.ofs; pi.xcoef = tx.coef; pi.yofs = ty.ofs; pi.ycoef = ty.coef;
+    fill_resize(e, pi, im.h, im.w, g);
     max_scale = std::max(max_scale, std::max(static_cast<float>(im.w) / g.new_w, static_cast<float>(im.h) / g.new_h));
-    // scale_coords(img1_shape=(H,W), coords, img0_shape) -- yolov5 utils.general, ratio_pad=None ("classic")
+    // scale_coords(img1_shape=(H,W), coords, img0_shape, ratio_pad) -- yolov5 utils.general; ratio_pad=None in "classic"
     NmsImageParams& np = e->h_nmsp[slot][i];
-    const double gain = std::min(static_cast<double>(P->H) / im.src_h, static_cast<double>(P->W) / im.src_w);
-    const double padx = (P->W - im.src_w * gain) / 2, pady = (P->H - im.src_h * gain) / 2;
+    double gain = std::min(static_cast<double>(P->H) / im.src_h, static_cast<double>(P->W) / im.src_w);
+    double padx = (P->W - im.src_w * gain) / 2, pady = (P->H - im.src_h * gain) / 2;
+    if (g.sc_gain > 0) { gain = g.sc_gain; padx = g.sc_pad_x; pady = g.sc_pad_y; }
     np.gain = static_cast<float>(gain); np.pad_x = static_cast<float>(padx); np.pad_y = static_cast<float>(pady);
     np.max_x = static_cast<float>(im.src_w); np.max_y = static_cast<float>(im.src_h);
   }
@@ -818,7 +871,7 @@ int batch_begin(mdb_engine* e, std::vector<ImgIn>& all, bool preprocessed, float
   if (B.active) return fail(e, MDB_ERR_STATE, "a batch is already in progress");
   if (e->tables.size() > 4096) {  // resize-coefficient tables are a few KB each; nothing is in flight here
     cudaDeviceSynchronize();
-    for (auto& kv : e->tables) { cudaFree(kv.second.ofs); cudaFree(kv.second.coef); }
+    for (auto& kv : e->tables) { cudaFree(kv.second.ofs); cudaFree(kv.second.coef); cudaFree(kv.second.si); cudaFree(kv.second.alpha); }
     e->tables.clear();
   }
   B = BatchState();
@@ -840,8 +893,9 @@ int batch_begin(mdb_engine* e, std::vector<ImgIn>& all, bool preprocessed, float
     LetterboxGeom g;
     if (preprocessed) {
       g = LetterboxGeom{}; g.src_h = im.h; g.src_w = im.w; g.new_w = im.w; g.new_h = im.h; g.out_h = im.h; g.out_w = im.w;
+      g.sc_gain = im.rp_gain; g.sc_pad_x = im.rp_pad_x; g.sc_pad_y = im.rp_pad_y;
     } else {
-      g = letterbox_geometry(im.h, im.w, cfg.img_size, cfg.stride, cfg.letterbox_auto != 0, cfg.letterbox_scaleup != 0);
+      g = geometry_for(cfg, im.h, im.w);
     }
     if (g.out_h % 64 != 0 || g.out_w % 64 != 0 || g.new_w < 1 || g.new_h < 1) {
       status[im.index] = MDB_IMG_INFER_FAILED; det_count[im.index] = 0;
@@ -944,7 +998,7 @@ const char* mdb_last_error(const mdb_engine* e) { return e ? e->err.c_str() : g_
 
 int mdb_letterbox_geometry(const mdb_config* cfg, int32_t h, int32_t w, int32_t* out8, double* ratio_pad3) {
   if (!cfg || !out8 || h <= 0 || w <= 0) return MDB_ERR_ARG;
-  const LetterboxGeom g = letterbox_geometry(h, w, cfg->img_size, cfg->stride, cfg->letterbox_auto != 0, cfg->letterbox_scaleup != 0);
+  const LetterboxGeom g = geometry_for(*cfg, h, w);
   out8[0] = g.new_w; out8[1] = g.new_h; out8[2] = g.top; out8[3] = g.bottom; out8[4] = g.left; out8[5] = g.right;
   out8[6] = g.out_h; out8[7] = g.out_w;
   if (ratio_pad3) { ratio_pad3[0] = g.ratio; ratio_pad3[1] = g.dw; ratio_pad3[2] = g.dh; }
@@ -1029,7 +1083,7 @@ void mdb_destroy(mdb_engine* e) {
   cudaDeviceSynchronize();
   e->plans.clear();
   for (auto& kv : e->weights) { cudaFree(kv.second.w); cudaFree(kv.second.b); }
-  for (auto& kv : e->tables) { cudaFree(kv.second.ofs); cudaFree(kv.second.coef); }
+  for (auto& kv : e->tables) { cudaFree(kv.second.ofs); cudaFree(kv.second.coef); cudaFree(kv.second.si); cudaFree(kv.second.alpha); }
   for (int i = 0; i < 2; ++i) {
     if (e->d_src[i]) cudaFree(e->d_src[i]);
     if (e->h_pre[i]) cudaFreeHost(e->h_pre[i]);
@@ -1168,6 +1222,24 @@ int mdb_infer_preprocessed(mdb_engine* e, const uint8_t* const* lb_hwc, const in
     std::vector<ImgIn> all(n);
     for (int i = 0; i < n; ++i)
       all[i] = ImgIn{lb_hwc[i], lh[i], lw[i], static_cast<long long>(lw[i]) * 3, src_h[i], src_w[i], i};
+    return infer_common(e, all, true, conf_thres, det_out, det_count, kept_anchor, status, n);
+  } catch (const CudaError& ex) {
+    return fail(e, MDB_ERR_CUDA, ex.msg);
+  }
+}
+
+int mdb_infer_preprocessed_rp(mdb_engine* e, const uint8_t* const* lb_hwc, const int32_t* lh, const int32_t* lw,
+                              const int32_t* src_h, const int32_t* src_w, const float* gain_pad, int32_t n, float conf_thres,
+                              float* det_out, int32_t* det_count, int32_t* kept_anchor, int32_t* status) {
+  if (!e || !lb_hwc || !lh || !lw || !src_h || !src_w || !det_out || !det_count || !status || n < 0)
+    return fail(e, MDB_ERR_ARG, "null argument");
+  try {
+    MDB_CUDA(cudaSetDevice(e->cfg.device));
+    std::vector<ImgIn> all(n);
+    for (int i = 0; i < n; ++i) {
+      all[i] = ImgIn{lb_hwc[i], lh[i], lw[i], static_cast<long long>(lw[i]) * 3, src_h[i], src_w[i], i};
+      if (gain_pad) { all[i].rp_gain = gain_pad[3 * i]; all[i].rp_pad_x = gain_pad[3 * i + 1]; all[i].rp_pad_y = gain_pad[3 * i + 2]; }
+    }
     return infer_common(e, all, true, conf_thres, det_out, det_count, kept_anchor, status, n);
   } catch (const CudaError& ex) {
     return fail(e, MDB_ERR_CUDA, ex.msg);
@@ -1540,7 +1612,7 @@ int mdb_op_letterbox(mdb_engine* e, const uint8_t* rgb_hwc, int32_t h, int32_t w
   try {
     MDB_CUDA(cudaSetDevice(e->cfg.device));
     const mdb_config& cfg = e->cfg;
-    const LetterboxGeom g = letterbox_geometry(h, w, cfg.img_size, cfg.stride, cfg.letterbox_auto != 0, cfg.letterbox_scaleup != 0);
+    const LetterboxGeom g = geometry_for(cfg, h, w);
     MDB_REQUIRE(g.out_h % 2 == 0 && g.out_w % 2 == 0, "letterboxed size must be even");
     cudaStream_t st = e->st_compute;
     const size_t row = static_cast<size_t>(w) * 3;
@@ -1555,9 +1627,7 @@ int mdb_op_letterbox(mdb_engine* e, const uint8_t* rgb_hwc, int32_t h, int32_t w
     PreImage pi;
     pi.src = d_src; pi.src_stride = static_cast<long long>(row); pi.src_h = h; pi.src_w = w;
     pi.new_w = g.new_w; pi.new_h = g.new_h; pi.top = g.top; pi.left = g.left;
-    const DevTable& tx = get_table(e, w, g.new_w, false);
-    const DevTable& ty = get_table(e, h, g.new_h, true);
-    pi.xofs = tx.ofs; pi.xcoef = tx.coef; pi.yofs = ty.ofs; pi.ycoef = ty.coef;
+    fill_resize(e, pi, h, w, g);
     MDB_CUDA(cudaMemcpy(d_pi, &pi, sizeof(pi), cudaMemcpyHostToDevice));
     const float max_scale = std::max(1.0f, std::max(static_cast<float>(w) / g.new_w, static_cast<float>(h) / g.new_h));
     preprocess_launch(d_pi, 1, g.out_h, g.out_w, d_dst, max_scale, st);

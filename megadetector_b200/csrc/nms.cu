@@ -39,6 +39,7 @@ constexpr int kNmsThreads = 1024;
 constexpr int kNmsWarps = kNmsThreads / 32;
 constexpr int kWin = 512;                  // candidates per suppression window
 constexpr int kWinWords = kWin / 32;       // words per row of the window's suppression bit-matrix
+constexpr int kClsLists = 4;               // per-class lists of kept boxes (models with more classes scan the whole kept list)
 constexpr int kSortSmemKeys = 8192;        // keys sorted per round in shared memory
 constexpr int kBins = 8192;                // confidence bins (2^15 float bit patterns each) used to cut long lists into rounds
 constexpr int kBinShift = 15;
@@ -114,6 +115,9 @@ __device__ __forceinline__ bool eval_anchor(const float* __restrict__ row, int n
 __device__ __forceinline__ bool iou_exceeds(const Cand& a, const Cand& b, float thr_floor) {
   const float xx1 = fmaxf(a.x1, b.x1), yy1 = fmaxf(a.y1, b.y1);
   const float xx2 = fminf(a.x2, b.x2), yy2 = fminf(a.y2, b.y2);
+  // disjoint boxes: inter == 0, ovr is 0 (or NaN for two empty boxes) and never exceeds a non-negative threshold -- the
+  // common case by far, decided without the division
+  if ((xx2 <= xx1 || yy2 <= yy1) && thr_floor >= 0.0f) return false;
   const float w = fmaxf(0.0f, __fsub_rn(xx2, xx1)), h = fmaxf(0.0f, __fsub_rn(yy2, yy1));
   const float inter = __fmul_rn(w, h);
   const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(a.area, b.area), inter));
@@ -231,6 +235,10 @@ nms_image_kernel(const float* __restrict__ pred, int anchors, int no, float thr,
   __shared__ int s_flag, s_kept, s_A;
   __shared__ Cand s_keep[kMaxDetCap];
   __shared__ int s_keep_anchor[kMaxDetCap];
+  // kept boxes by class: a candidate can only be suppressed by a kept box of its own class, so it is tested against that
+  // class's list only (a third of the pair tests for MegaDetector's three classes)
+  __shared__ uint16_t s_cls_list[kClsLists][kMaxDetCap];
+  __shared__ int s_cls_count[kClsLists];
 
   const int img = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -243,7 +251,9 @@ nms_image_kernel(const float* __restrict__ pred, int anchors, int no, float thr,
 
   uint32_t* s_cum = reinterpret_cast<uint32_t*>(s_dyn + 2 * static_cast<size_t>(kSortSmemKeys) * sizeof(unsigned long long));
   if (tid == 0) s_kept = 0;
+  if (tid < kClsLists) s_cls_count[tid] = 0;
   __syncthreads();
+  const bool by_class = (no - 5) <= kClsLists;
 
   // K7b on `m` sorted keys (window state lives in `spare`, >= 51 KB of shared memory that does not hold the keys);
   // continues from the boxes kept so far, returns when the keys are exhausted or max_det boxes are kept
@@ -273,7 +283,13 @@ nms_image_kernel(const float* __restrict__ pred, int anchors, int no, float thr,
       const int kc = s_kept;
       // (1) against the boxes kept so far: each half of the block scans half of the list
       bool dead = !valid;
-      {
+      if (valid && by_class) {
+        const int cc = s_cls_count[me.cls];
+        const uint16_t* lst = s_cls_list[me.cls];
+        const int k0 = half ? (cc >> 1) : 0, k1 = half ? cc : (cc >> 1);
+        for (int k = k0; k < k1 && !dead; ++k)
+          if (iou_exceeds(s_keep[lst[k]], me, iou_floor)) dead = true;
+      } else if (valid) {
         const int k0 = half ? (kc >> 1) : 0, k1 = half ? kc : (kc >> 1);
         for (int k = k0; k < k1 && !dead; ++k)
           if (s_keep[k].cls == me.cls && iou_exceeds(s_keep[k], me, iou_floor)) dead = true;
@@ -334,6 +350,10 @@ nms_image_kernel(const float* __restrict__ pred, int anchors, int no, float thr,
               const int src = s_alist[ri];
               if (lane < 7) reinterpret_cast<uint32_t*>(&s_keep[kept])[lane] = reinterpret_cast<const uint32_t*>(&s_win[src])[lane];
               if (lane == 7) s_keep_anchor[kept] = s_win_anchor[src];
+              if (lane == 8 && by_class) {
+                const int c = s_win[src].cls;
+                s_cls_list[c][s_cls_count[c]++] = static_cast<uint16_t>(kept);
+              }
               ++kept;
               if (kept >= max_det) break;
               removed |= row;

@@ -60,6 +60,66 @@ LetterboxGeom letterbox_geometry(int h, int w, int img_size, int stride, bool au
   return g;
 }
 
+LetterboxGeom letterbox_geometry_modern(int h, int w, int img_size, int stride, bool use_ceil) {
+  // pytorch_detector.py:1036-1101 + yolov5 letterbox(auto=False, scaleup=False) on the pre-resized image
+  LetterboxGeom g{};
+  g.src_h = h;
+  g.src_w = w;
+  const double r = static_cast<double>(img_size) / std::max(h, w);
+  g.new_w = w;
+  g.new_h = h;
+  g.interp = 0;
+  if (r != 1.0) {
+    g.interp = r > 1.0 ? 0 : 1;
+    g.new_w = use_ceil ? static_cast<int>(std::ceil(w * r)) : static_cast<int>(w * r);
+    g.new_h = use_ceil ? static_cast<int>(std::ceil(h * r)) : static_cast<int>(h * r);
+  }
+  // target_shape = ceil(normalized_shape * image_size / stride + 0.5) * stride, normalized by max(H, W, 3) of the resized image
+  const double maxd = std::max(std::max(g.new_h, g.new_w), 3);
+  const int th = static_cast<int>(std::ceil((g.new_h / maxd) * img_size / stride + 0.5)) * stride;
+  const int tw = static_cast<int>(std::ceil((g.new_w / maxd) * img_size / stride + 0.5)) * stride;
+  // letterbox(): r = min(th / H, tw / W) clipped to 1 (scaleup=False); th >= H and tw >= W, so no second resize
+  g.ratio = 1.0;
+  double dw = tw - g.new_w, dh = th - g.new_h;
+  dw /= 2;
+  dh /= 2;
+  g.dw = dw;
+  g.dh = dh;
+  g.top = static_cast<int>(std::nearbyint(dh - 0.1));
+  g.bottom = static_cast<int>(std::nearbyint(dh + 0.1));
+  g.left = static_cast<int>(std::nearbyint(dw - 0.1));
+  g.right = static_cast<int>(std::nearbyint(dw + 0.1));
+  g.out_h = g.new_h + g.top + g.bottom;
+  g.out_w = g.new_w + g.left + g.right;
+  // scale_coords(img1_shape, coords, scaling_shape, ratio_pad=((H'/H, W'/W), (dw, dh))): gain = ratio_pad[0][0], pad = ratio_pad[1]
+  g.sc_gain = static_cast<double>(g.new_h) / h;
+  g.sc_pad_x = dw;
+  g.sc_pad_y = dh;
+  return g;
+}
+
+void area_tables(int ssize, int dsize, std::vector<int32_t>& first, std::vector<int32_t>& si, std::vector<float>& alpha) {
+  // cv::computeResizeAreaTab (imgproc/src/resize.cpp); scale = 1 / (dsize / ssize) as cv::resize computes it
+  const double inv_scale = static_cast<double>(dsize) / ssize;
+  const double scale = 1.0 / inv_scale;
+  first.assign(dsize + 1, 0);
+  si.clear();
+  alpha.clear();
+  for (int dx = 0; dx < dsize; ++dx) {
+    first[dx] = static_cast<int32_t>(si.size());
+    const double fsx1 = dx * scale;
+    const double fsx2 = fsx1 + scale;
+    const double cell = std::min(scale, ssize - fsx1);
+    int sx1 = static_cast<int>(std::ceil(fsx1)), sx2 = static_cast<int>(std::floor(fsx2));
+    sx2 = std::min(sx2, ssize - 1);
+    sx1 = std::min(sx1, sx2);
+    if (sx1 - fsx1 > 1e-3) { si.push_back(sx1 - 1); alpha.push_back(static_cast<float>((sx1 - fsx1) / cell)); }
+    for (int sx = sx1; sx < sx2; ++sx) { si.push_back(sx); alpha.push_back(static_cast<float>(1.0 / cell)); }
+    if (fsx2 - sx2 > 1e-3) { si.push_back(sx2); alpha.push_back(static_cast<float>(std::min(std::min(fsx2 - sx2, 1.), cell) / cell)); }
+  }
+  first[dsize] = static_cast<int32_t>(si.size());
+}
+
 void linear_tables(int ssize, int dsize, bool vertical, std::vector<int32_t>& ofs, std::vector<int16_t>& coef) {
   // cv::resize, INTER_LINEAR, 8-bit: imgproc/src/resize.cpp (coefficient set-up before resizeGeneric_).
   ofs.resize(dsize);
@@ -118,10 +178,23 @@ __global__ void __launch_bounds__(kPreThreads) letterbox_s2d_kernel(const PreIma
   int row0 = 0, byte0 = 0;  // source window origin
   if (STAGED) {
     if (any_src) {
-      row0 = clampi(im.yofs[oy_lo - im.top], 0, im.src_h - 1);
-      const int row1 = clampi(im.yofs[oy_hi - im.top] + 1, 0, im.src_h - 1);
-      const int col0 = im.xofs[ox_lo - im.left];
-      const int col1 = min(im.xofs[ox_hi - im.left] + 1, im.src_w - 1);
+      int row1, col0, col1;
+      if (im.mode == 0) {
+        row0 = clampi(im.yofs[oy_lo - im.top], 0, im.src_h - 1);
+        row1 = clampi(im.yofs[oy_hi - im.top] + 1, 0, im.src_h - 1);
+        col0 = im.xofs[ox_lo - im.left];
+        col1 = min(im.xofs[ox_hi - im.left] + 1, im.src_w - 1);
+      } else if (im.mode == 1) {
+        row0 = im.ya_si[im.ya_first[oy_lo - im.top]];
+        row1 = im.ya_si[im.ya_first[oy_hi - im.top + 1] - 1];
+        col0 = im.xa_si[im.xa_first[ox_lo - im.left]];
+        col1 = im.xa_si[im.xa_first[ox_hi - im.left + 1] - 1];
+      } else {
+        row0 = (oy_lo - im.top) * im.iscale_y;
+        row1 = min((oy_hi - im.top + 1) * im.iscale_y - 1, im.src_h - 1);
+        col0 = (ox_lo - im.left) * im.iscale_x;
+        col1 = min((ox_hi - im.left + 1) * im.iscale_x - 1, im.src_w - 1);
+      }
       byte0 = col0 * 3;
       const int nbytes = (col1 + 1) * 3 - byte0;
       const int nrows = row1 - row0 + 1;
@@ -168,7 +241,7 @@ __global__ void __launch_bounds__(kPreThreads) letterbox_s2d_kernel(const PreIma
         int b0 = 0, b1 = 0;
         const uint8_t* r0 = nullptr;
         const uint8_t* r1 = nullptr;
-        if (in_y) {
+        if (in_y && im.mode == 0) {
           const int s = im.yofs[dy];
           r0 = row_ptr(clampi(s, 0, im.src_h - 1));
           r1 = row_ptr(clampi(s + 1, 0, im.src_h - 1));
@@ -180,7 +253,53 @@ __global__ void __launch_bounds__(kPreThreads) letterbox_s2d_kernel(const PreIma
           const int ox = 2 * sx2 + pxx;
           const int dx = ox - im.left;
           int v[3] = {114, 114, 114};
-          if (in_y && dx >= 0 && dx < im.new_w) {
+          if (im.mode != 0) {
+            if (dy >= 0 && dy < im.new_h && dx >= 0 && dx < im.new_w) {
+              if (im.mode == 1) {
+                // cv::ResizeArea_: buf[dx] = sum_k S[sx_k] * alpha_k per source row (float, in table order), then
+                // sum = beta * buf for the first row of the group and sum += beta * buf for the others; cvRound at the end
+                float acc[3] = {0.f, 0.f, 0.f};
+                const int y0 = im.ya_first[dy], y1 = im.ya_first[dy + 1];
+                const int x0 = im.xa_first[dx], x1 = im.xa_first[dx + 1];
+                for (int ky = y0; ky < y1; ++ky) {
+                  const uint8_t* rr = row_ptr(im.ya_si[ky]);
+                  const float beta = im.ya_alpha[ky];
+                  float b[3] = {0.f, 0.f, 0.f};
+                  for (int kx = x0; kx < x1; ++kx) {
+                    const int o = im.xa_si[kx] * 3;
+                    const float a = im.xa_alpha[kx];
+#pragma unroll
+                    for (int c = 0; c < 3; ++c)
+                      b[c] = __fadd_rn(b[c], __fmul_rn(static_cast<float>(STAGED ? rr[o + c] : __ldg(rr + o + c)), a));
+                  }
+#pragma unroll
+                  for (int c = 0; c < 3; ++c)
+                    acc[c] = (ky == y0) ? __fmul_rn(beta, b[c]) : __fadd_rn(acc[c], __fmul_rn(beta, b[c]));
+                }
+#pragma unroll
+                for (int c = 0; c < 3; ++c) v[c] = min(255, max(0, __float2int_rn(acc[c])));
+              } else {
+                // cv::ResizeAreaFast_: integer block sums; 2x2: (s + 2) >> 2, otherwise cvRound(s * (1.f / area))
+                int sum[3] = {0, 0, 0};
+                for (int ky = 0; ky < im.iscale_y; ++ky) {
+                  const uint8_t* rr = row_ptr(dy * im.iscale_y + ky);
+                  for (int kx = 0; kx < im.iscale_x; ++kx) {
+                    const int o = (dx * im.iscale_x + kx) * 3;
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) sum[c] += STAGED ? rr[o + c] : __ldg(rr + o + c);
+                  }
+                }
+                if (im.iscale_x == 2 && im.iscale_y == 2) {
+#pragma unroll
+                  for (int c = 0; c < 3; ++c) v[c] = (sum[c] + 2) >> 2;
+                } else {
+                  const float sc = __fdiv_rn(1.0f, static_cast<float>(im.iscale_x * im.iscale_y));
+#pragma unroll
+                  for (int c = 0; c < 3; ++c) v[c] = min(255, max(0, __float2int_rn(__fmul_rn(static_cast<float>(sum[c]), sc))));
+                }
+              }
+            }
+          } else if (in_y && dx >= 0 && dx < im.new_w) {
             const int sx0 = im.xofs[dx];
             const int o0 = sx0 * 3, o1 = min(sx0 + 1, im.src_w - 1) * 3;
             const int a0 = im.xcoef[2 * dx], a1 = im.xcoef[2 * dx + 1];

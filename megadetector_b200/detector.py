@@ -16,8 +16,10 @@ What runs where:
   * record formatting            -> vectorised numpy replica of pytorch_detector.py:1384-1411 (fp32 -> double ->
     decimal truncation, op for op)
 
-Not supported this round (raise NotImplementedError, never a silent approximation): compatibility modes other
-than 'classic' (SURVEY.md par. 8f-4), `augment=True` (TTA), `force_cpu` (there is no CPU path).
+Compatibility modes: 'classic' (and any mode string containing it) and the non-classic ("modern") behaviour of
+pytorch_detector.py:1036-1101,1318-1321,1372-1397: INTER_AREA / INTER_LINEAR pre-resize of the long side, padding to
+ceil(side / stride + 0.5) * stride, NMS IoU 0.6, scale_coords with ratio_pad, round() instead of truncation.
+Not supported (raise NotImplementedError, never a silent approximation): `augment=True` (TTA), `force_cpu` (no CPU path).
 """
 
 import gc
@@ -56,10 +58,11 @@ def _truncate(x, precision):
     return np.floor(x * f) / f
 
 
-def format_detections(det, count, src_h, src_w, use_model_native_classes=False):
+def format_detections(det, count, src_h, src_w, use_model_native_classes=False, classic=True):
     """
-    pytorch_detector.py:1367-1411 ("classic"): det rows = x1,y1,x2,y2 (rounded original pixels, fp32), conf, cls,
-    sorted by conf descending.  Returns (list of dicts in ascending conf order, max_conf).
+    pytorch_detector.py:1367-1411: det rows = x1,y1,x2,y2 (rounded original pixels, fp32), conf, cls, sorted by conf
+    descending.  Returns (list of dicts in ascending conf order, max_conf).  classic: truncate_float (:1392-1394), otherwise
+    Python round() (:1395-1397).
     """
     n = int(count)
     if n == 0:
@@ -77,9 +80,15 @@ def format_detections(det, count, src_h, src_w, use_model_native_classes=False):
     xc, yc, bw, bh = (a.astype(np.float64) for a in (xc, yc, bw, bh))
     x_min = xc - bw / 2.0
     y_min = yc - bh / 2.0
-    box = np.stack([_truncate(x_min, COORD_DIGITS), _truncate(y_min, COORD_DIGITS), _truncate(bw, COORD_DIGITS),
-                    _truncate(bh, COORD_DIGITS)], 1)
-    conf = _truncate(d[:, 4].astype(np.float64), CONF_DIGITS)
+    if classic:
+        box = np.stack([_truncate(x_min, COORD_DIGITS), _truncate(y_min, COORD_DIGITS), _truncate(bw, COORD_DIGITS),
+                        _truncate(bh, COORD_DIGITS)], 1)
+        conf = _truncate(d[:, 4].astype(np.float64), CONF_DIGITS)
+    else:
+        # ct_utils.round_float == Python's round() (correctly rounded decimal, half-to-even): not np.round
+        box = np.array([[round(v, COORD_DIGITS) for v in row] for row in np.stack([x_min, y_min, bw, bh], 1).tolist()],
+                       np.float64).reshape(-1, 4)
+        conf = np.array([round(v, CONF_DIGITS) for v in d[:, 4].astype(np.float64).tolist()], np.float64)
     cls = d[:, 5].astype(np.int64)
     if not use_model_native_classes:
         cls = cls + 1
@@ -118,9 +127,6 @@ class B200Detector:
         preprocess_only = bool(detector_options and detector_options.get('preprocess_only'))
         if compatibility_mode == 'default':
             compatibility_mode = default_compatibility_mode
-        if 'classic' not in compatibility_mode:
-            raise NotImplementedError(
-                'B200Detector implements compatibility_mode "classic" only (got {})'.format(compatibility_mode))
         if verbose or (not preprocess_only):
             print('Loading PT detector with compatibility mode {}'.format(compatibility_mode))
 
@@ -136,6 +142,8 @@ class B200Detector:
         self.printed_image_size_warning = False
         self.use_model_native_classes = use_model_native_classes
         self.compatibility_mode = compatibility_mode
+        self.classic = 'classic' in compatibility_mode
+        self.use_ceil_for_resize = 'use_ceil_for_resize' in compatibility_mode
         self.letterbox_stride = 64 if self.default_image_size == 1280 else 32
         print('Using model stride: {}'.format(self.letterbox_stride))
         self.half_precision = False
@@ -144,7 +152,8 @@ class B200Detector:
         self._current_image_size = self.default_image_size
         if preprocess_only:
             # geometry helper only; no weights, no GPU (pytorch_detector.py:785-789,850-851)
-            self._cfg = _capi.make_config(img_size=self.default_image_size, stride=self.letterbox_stride)
+            self._cfg = _capi.make_config(img_size=self.default_image_size, stride=self.letterbox_stride,
+                                          compat_mode=0 if self.classic else 1, use_ceil_for_resize=self.use_ceil_for_resize)
             return
 
         if force_cpu:
@@ -165,15 +174,17 @@ class B200Detector:
             raise NotImplementedError('only stride-64 (YOLOv5-P6, 1280 px) models are supported')
         self._cfg = _capi.make_config(device=ordinal, max_batch=max_batch, img_size=self.default_image_size,
                                       stride=self.letterbox_stride, letterbox_auto=True, letterbox_scaleup=True,
-                                      iou_thres=0.45, max_det=300, ch=arch['ch'], n_backbone=arch['n_backbone'],
-                                      n_head=arch['n_head'], nc=arch['nc'], anchors_px=arch.get('anchors_px'))
+                                      iou_thres=0.45 if self.classic else 0.6, max_det=300, ch=arch['ch'],
+                                      n_backbone=arch['n_backbone'], n_head=arch['n_head'], nc=arch['nc'],
+                                      anchors_px=arch.get('anchors_px'), compat_mode=0 if self.classic else 1,
+                                      use_ceil_for_resize=self.use_ceil_for_resize)
         self.engine = _capi.Engine(self._cfg)
         self.engine.load_weights(weights)
         self.nc = arch['nc']
 
     # ------------------------------------------------------------------------------------------
     def preprocess_image(self, img_original, image_id='unknown', image_size=None, verbose=False):
-        """pytorch_detector.py:964-1119 ("classic"): host-side letterbox for producer workers."""
+        """pytorch_detector.py:964-1119: host-side preprocessing for producer workers (both compatibility modes)."""
         import cv2
         result = {'file': image_id}
         img_original_pil = None
@@ -189,17 +200,21 @@ class B200Detector:
         else:
             image_size = self.default_image_size
             self.printed_image_size_warning = False
-        cfg = _capi.make_config(img_size=image_size, stride=self.letterbox_stride)
+        cfg = _capi.make_config(img_size=image_size, stride=self.letterbox_stride, compat_mode=0 if self.classic else 1,
+                                use_ceil_for_resize=self.use_ceil_for_resize)
         g = _capi.letterbox_geometry(cfg, img_original.shape[0], img_original.shape[1])
         img = img_original
         if (img.shape[1], img.shape[0]) != tuple(g['new_unpad']):
-            img = cv2.resize(img, tuple(g['new_unpad']), interpolation=cv2.INTER_LINEAR)
+            shrink = (not self.classic) and g['new_unpad'][0] < img.shape[1]
+            img = cv2.resize(img, tuple(g['new_unpad']), interpolation=cv2.INTER_AREA if shrink else cv2.INTER_LINEAR)
+        if not self.classic:
+            img_original = img  # the reference keeps the pre-resized image under this key (:1060-1062,1112)
         img = cv2.copyMakeBorder(img, g['top'], g['bottom'], g['left'], g['right'], cv2.BORDER_CONSTANT,
                                  value=(114, 114, 114))
         result['img_processed'] = img
         result['img_original'] = img_original
         result['img_original_pil'] = img_original_pil
-        result['target_shape'] = image_size
+        result['target_shape'] = image_size if self.classic else np.array(g['out_hw'])
         result['scaling_shape'] = scaling_shape
         result['letterbox_ratio'] = g['ratio']
         result['letterbox_pad'] = g['pad']
@@ -253,12 +268,16 @@ class B200Detector:
         ids = [None] * n
         arrays = [None] * n
         src_shapes = [None] * n
+        gain_pads = [None] * n
         for i, img in enumerate(img_original):
             try:
                 if dict_mode:
                     ids[i] = img['file']
                     arrays[i] = np.ascontiguousarray(img['img_processed'], dtype=np.uint8)
-                    src_shapes[i] = tuple(img['img_original'].shape[:2])
+                    src_shapes[i] = tuple(img['scaling_shape'][:2])
+                    if not self.classic:  # ratio_pad of scale_coords (:1372-1381)
+                        gain_pads[i] = (img['img_original'].shape[0] / img['scaling_shape'][0],
+                                        img['letterbox_pad'][0], img['letterbox_pad'][1])
                 else:
                     ids[i] = image_id[i]
                     a = img if isinstance(img, np.ndarray) else np.asarray(img)
@@ -285,7 +304,7 @@ class B200Detector:
             else:
                 try:
                     dets, max_conf = format_detections(det[j], cnt[j], src_shapes[i][0], src_shapes[i][1],
-                                                       self.use_model_native_classes)
+                                                       self.use_model_native_classes, self.classic)
                     results[i] = {'file': ids[i], 'detections': dets, 'max_detection_conf': max_conf}
                 except KeyError as e:
                     # the reference raises inside _process_batch_group and records an inference failure (:1236-1249)
@@ -298,19 +317,20 @@ class B200Detector:
         gc_was_enabled = gc.isenabled()
         gc.disable()
         try:
-            self._infer_and_format(good, dict_mode, arrays, src_shapes, detection_threshold, finish, results, ids)
+            self._infer_and_format(good, dict_mode, arrays, src_shapes, detection_threshold, finish, results, ids, gain_pads)
         finally:
             if gc_was_enabled:
                 gc.enable()
         return results
 
-    def _infer_and_format(self, good, dict_mode, arrays, src_shapes, detection_threshold, finish, results, ids):
+    def _infer_and_format(self, good, dict_mode, arrays, src_shapes, detection_threshold, finish, results, ids, gain_pads=None):
         if good:
             try:
                 if dict_mode:
+                    gp = None if self.classic else [gain_pads[i] for i in good]
                     det, cnt, _, status = self.engine.infer_preprocessed([arrays[i] for i in good],
                                                                          [src_shapes[i] for i in good],
-                                                                         detection_threshold, want_anchors=False)
+                                                                         detection_threshold, want_anchors=False, gain_pad=gp)
                     for j, i in enumerate(good):
                         finish(j, i, det, cnt, status)
                 else:
@@ -362,7 +382,7 @@ class B200Detector:
                     results.append({'file': iid, 'detections': None, 'failure': FAILURE_INFER})
                 else:
                     dets, max_conf = format_detections(det[i], cnt[i], int(hw[i, 0]), int(hw[i, 1]),
-                                                       self.use_model_native_classes)
+                                                       self.use_model_native_classes, self.classic)
                     results.append({'file': iid, 'detections': dets, 'max_detection_conf': max_conf})
         finally:
             if gc_was_enabled:

@@ -132,3 +132,97 @@ def to_stem_layout_fp16(img_letterboxed):
     for t in range(3):
         out[:, :, t * 16:t * 16 + 12] = s2d[:, t:t + w // 2, :]
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# "modern" compatibility mode (pytorch_detector.py:1036-1101): INTER_AREA / INTER_LINEAR pre-resize + pad
+# ---------------------------------------------------------------------------------------------------------------
+def _area_tab(ssize, dsize, scale):
+    """cv::computeResizeAreaTab (OpenCV imgproc/src/resize.cpp): [(dst index, src index, float32 weight)] in table order."""
+    import math
+    tab = []
+    for dx in range(dsize):
+        fsx1 = dx * scale
+        fsx2 = fsx1 + scale
+        cell = min(scale, ssize - fsx1)
+        sx1, sx2 = int(math.ceil(fsx1)), int(math.floor(fsx2))
+        sx2 = min(sx2, ssize - 1)
+        sx1 = min(sx1, sx2)
+        if sx1 - fsx1 > 1e-3:
+            tab.append((dx, sx1 - 1, np.float32((sx1 - fsx1) / cell)))
+        for sx in range(sx1, sx2):
+            tab.append((dx, sx, np.float32(1.0 / cell)))
+        if fsx2 - sx2 > 1e-3:
+            tab.append((dx, sx2, np.float32(min(min(fsx2 - sx2, 1.0), cell) / cell)))
+    return tab
+
+
+def resize_area_u8(src, dw, dh):
+    """
+    cv2.resize(src, (dw, dh), interpolation=cv2.INTER_AREA) for uint8 HWC images when shrinking on both axes, op for op:
+    integer scales on both axes -> cv::ResizeAreaFast_ (integer block sums; 2x2: (s + 2) >> 2, else cvRound(s * (1.f / area)));
+    otherwise cv::ResizeArea_ (float32 taps from computeResizeAreaTab, row buffer accumulated in table order, vertical
+    accumulation `sum = beta * buf` / `sum += beta * buf`, cvRound).  Pinned against the real cv2 in
+    tests/test_oracle_modern.py.
+    """
+    sh, sw, cn = src.shape
+    scale_x = 1.0 / (dw / sw)
+    scale_y = 1.0 / (dh / sh)
+    isx, isy = int(round(scale_x)), int(round(scale_y))
+    if abs(scale_x - isx) < np.finfo(np.float64).eps and abs(scale_y - isy) < np.finfo(np.float64).eps:
+        s = src[:dh * isy, :dw * isx].astype(np.int32).reshape(dh, isy, dw, isx, cn).sum(axis=(1, 3))
+        if isx == 2 and isy == 2:
+            return ((s + 2) >> 2).astype(np.uint8)
+        v = s.astype(np.float32) * (np.float32(1.0) / np.float32(isx * isy))
+        return np.clip(np.rint(v), 0, 255).astype(np.uint8)
+    S = src.astype(np.float32)
+    buf = np.zeros((sh, dw, cn), np.float32)
+    for dx, sx, a in _area_tab(sw, dw, scale_x):
+        buf[:, dx, :] = buf[:, dx, :] + S[:, sx, :] * a
+    out = np.zeros((dh, dw, cn), np.float32)
+    seen = set()
+    for dy, sy, b in _area_tab(sh, dh, scale_y):
+        if dy not in seen:
+            out[dy] = b * buf[sy]
+            seen.add(dy)
+        else:
+            out[dy] = out[dy] + b * buf[sy]
+    return np.clip(np.rint(out), 0, 255).astype(np.uint8)
+
+
+def preprocess_modern(img, image_size=1280, stride=64, use_ceil=False):
+    """
+    pytorch_detector.py:1036-1101 for a non-"classic" compatibility mode.  Returns a dict with the reference's keys:
+    img_processed, img_original (the PRE-RESIZED image, as in the reference), scaling_shape, letterbox_ratio, letterbox_pad,
+    target_shape.
+    """
+    import math
+    scaling_shape = img.shape
+    h, w = img.shape[:2]
+    resize_ratio = image_size / max(h, w)
+    if resize_ratio != 1:
+        if use_ceil:
+            tw, th = math.ceil(w * resize_ratio), math.ceil(h * resize_ratio)
+        else:
+            tw, th = int(w * resize_ratio), int(h * resize_ratio)
+        img = resize_linear_u8(img, tw, th) if resize_ratio > 1 else resize_area_u8(img, tw, th)
+    max_dimension = max(img.shape)
+    normalized_shape = [img.shape[0] / max_dimension, img.shape[1] / max_dimension]
+    target_shape = np.ceil(((np.array(normalized_shape) * image_size) / stride) + 0.5).astype(int) * stride
+    # yolov5 letterbox(img, new_shape=target_shape, stride, auto=False, scaleFill=False, scaleup=False)
+    shape = img.shape[:2]
+    r = min(target_shape[0] / shape[0], target_shape[1] / shape[1])
+    r = min(r, 1.0)
+    new_unpad = (int(round(shape[1] * r)), int(round(shape[0] * r)))
+    dw, dh = target_shape[1] - new_unpad[0], target_shape[0] - new_unpad[1]
+    dw /= 2
+    dh /= 2
+    lb = img
+    if shape[::-1] != new_unpad:
+        lb = resize_linear_u8(img, new_unpad[0], new_unpad[1])
+    top, bottom = int(round(dh - 0.1)), int(round(dh + 0.1))
+    left, right = int(round(dw - 0.1)), int(round(dw + 0.1))
+    out = np.full((lb.shape[0] + top + bottom, lb.shape[1] + left + right, 3), PAD_VALUE, np.uint8)
+    out[top:top + lb.shape[0], left:left + lb.shape[1]] = lb
+    return {'img_processed': out, 'img_original': img, 'scaling_shape': scaling_shape, 'letterbox_ratio': (r, r),
+            'letterbox_pad': (float(dw), float(dh)), 'target_shape': target_shape}

@@ -65,24 +65,31 @@ def xyxy2xywh(x):
     return y
 
 
-def rescale_and_format(det, letterboxed_hw, scaling_shape, detection_threshold):
+def rescale_and_format(det, letterboxed_hw, scaling_shape, detection_threshold, ratio_pad=None):
     """
-    det: torch float32 [N,6] in letterbox pixels (output of nms()).  Mirrors pytorch_detector.py:1352-1422
-    ("classic").  Returns (detections list, max_conf, rounded det tensor).
+    det: torch float32 [N,6] in letterbox pixels (output of nms()).  Mirrors pytorch_detector.py:1352-1422.
+    ratio_pad=None: "classic" (scale from the shapes, truncation); otherwise the non-classic branch (:1372-1381,1395-1397):
+    ratio_pad = ((h_resized / h, w_resized / w), letterbox_pad), Python round() instead of truncation.
+    Returns (detections list, max_conf, rounded det tensor).
     """
     detections = []
     max_conf = 0.0
     det = det.clone()
+    classic = ratio_pad is None
     if len(det) > 0:
         gn = torch.tensor(scaling_shape)[[1, 0, 1, 0]]
-        det[:, :4] = scale_coords(letterboxed_hw, det[:, :4], scaling_shape).round()
+        det[:, :4] = scale_coords(letterboxed_hw, det[:, :4], scaling_shape, ratio_pad).round()
         for *xyxy, conf, cls in reversed(det):
             if conf < detection_threshold:
                 continue
             xywh = (xyxy2xywh(torch.tensor(xyxy).view(1, 4)) / gn).view(-1).tolist()
             api_box = convert_yolo_to_xywh(xywh)
-            api_box = truncate_float_array(api_box, precision=COORD_DIGITS)
-            conf = truncate_float(conf.tolist(), precision=CONF_DIGITS)
+            if classic:
+                api_box = truncate_float_array(api_box, precision=COORD_DIGITS)
+                conf = truncate_float(conf.tolist(), precision=CONF_DIGITS)
+            else:
+                api_box = [round(x, COORD_DIGITS) for x in api_box]
+                conf = round(conf.tolist(), CONF_DIGITS)
             cls = int(cls.tolist()) + 1
             if cls not in (1, 2, 3):
                 raise KeyError(f'{cls} is not a valid class.')
