@@ -177,6 +177,7 @@ struct NmsScratch {
   // lists, and the candidate count
   unsigned long long* key[2];
   int32_t* count;
+  long long* dbg;  // 8 counters per image (phase cycles, -DMDB_NMS_TIMERS builds only)
   int cap;
 };
 size_t nms_scratch_bytes(int n_img, int anchors);

@@ -188,6 +188,7 @@ struct mdb_engine {
   float last_ms[4] = {0, 0, 0, 0};
   int64_t launches = 0;
   int pipeline_split = 4;
+  bool edge_taper = false;
   bool use_graphs = true;
   bool trace_all = false;
   std::vector<std::string> trace_names;
@@ -913,11 +914,28 @@ int batch_begin(mdb_engine* e, std::vector<ImgIn>& all, bool preprocessed, float
     size_t chunk = static_cast<size_t>(cfg.max_batch);
     if (ids.size() <= chunk && ids.size() > 16 && e->pipeline_split > 1)
       chunk = std::max<size_t>(8, (ids.size() + e->pipeline_split - 1) / e->pipeline_split);
-    for (size_t b = 0; b < ids.size(); b += chunk) {
+    // Nothing hides the upload of the FIRST chunk or the NMS + D2H + record formatting of the LAST one (the reference's call
+    // is synchronous per batch), so with `edge_taper` those two chunks are half-sized: [c/2, c, ..., c, c/2].
+    std::vector<size_t> sizes;
+    {
+      size_t left = ids.size();
+      const bool taper = e->edge_taper && chunk >= 16 && ids.size() > 2 * chunk && e->pipeline_split > 1;
+      if (taper) { sizes.push_back(chunk / 2); left -= chunk / 2; }
+      while (left > 0) {
+        size_t c = std::min(left, chunk);
+        if (taper && left > chunk / 2 && left - c < chunk / 2 && left - c > 0) c = left - chunk / 2;  // leave exactly c/2 for the tail
+        if (taper && left <= chunk && left > chunk / 2) c = left - chunk / 2;
+        sizes.push_back(c);
+        left -= c;
+      }
+    }
+    size_t b = 0;
+    for (size_t c : sizes) {
       ChunkJob job;
       job.H = kv.first.first; job.W = kv.first.second;
-      job.ids.assign(ids.begin() + b, ids.begin() + std::min(ids.size(), b + chunk));
+      job.ids.assign(ids.begin() + b, ids.begin() + b + c);
       B.jobs.push_back(job);
+      b += c;
     }
   }
   try {
@@ -1066,6 +1084,7 @@ int mdb_create(mdb_engine** out, const mdb_config* cfg) {
     conv_init_device();
     nms_init_device();
     if (const char* mp = getenv("MDB_MAX_PLANS")) e->max_plans = std::max(1, atoi(mp));
+    if (const char* et = getenv("MDB_EDGE_TAPER")) e->edge_taper = et[0] == '1';
     const char* ng = getenv("MDB_NO_GRAPHS");
     e->use_graphs = !(ng && ng[0] == '1');
   } catch (const CudaError& ex) {

@@ -28,13 +28,21 @@
 // intrinsic, so nvcc cannot contract a*b+c into an FMA; thresholds are compared in the reference's types
 // (conf: float32(thr); IoU: float promoted to double vs the double threshold == float > floor_f32(thr)).
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
+#include <vector>
 
 #include "common.h"
 #include "nms_cand.cuh"
 
 namespace mdb {
 
+// phase cycle counters of the per-image kernel exist only in -DMDB_NMS_TIMERS builds (MDB_LIB_VARIANT experiment builds)
+#ifdef MDB_NMS_TIMERS
+#define NMS_T(i) do { if (threadIdx.x == 0) { const long long _t = clock64(); s_tm[i] += _t - s_t0; s_t0 = _t; } } while (0)
+#else
+#define NMS_T(i) do {} while (0)
+#endif
 constexpr int kNmsThreads = 1024;
 constexpr int kNmsWarps = kNmsThreads / 32;
 constexpr int kWin = 512;                  // candidates per suppression window
@@ -54,7 +62,8 @@ float float_floor_of_double(double t) {
 }
 
 size_t nms_scratch_bytes(int n_img, int anchors) {
-  return static_cast<size_t>(n_img) * anchors * 16 + static_cast<size_t>(n_img) * sizeof(int32_t) + 256;
+  return static_cast<size_t>(n_img) * anchors * 16 + static_cast<size_t>(n_img) * sizeof(int32_t) + 256 +
+         static_cast<size_t>(n_img) * 8 * sizeof(long long);
 }
 
 void nms_bind_scratch(NmsScratch* s, void* mem, int n_img, int anchors) {
@@ -63,6 +72,7 @@ void nms_bind_scratch(NmsScratch* s, void* mem, int n_img, int anchors) {
   s->key[0] = reinterpret_cast<unsigned long long*>(p);
   s->key[1] = reinterpret_cast<unsigned long long*>(p + one);
   s->count = reinterpret_cast<int32_t*>(p + 2 * one);
+  s->dbg = reinterpret_cast<long long*>(p + 2 * one + ((static_cast<size_t>(n_img) * sizeof(int32_t) + 255) / 256) * 256);
   s->cap = anchors;
 }
 
@@ -240,6 +250,11 @@ nms_image_kernel(const float* __restrict__ pred, int anchors, int no, float thr,
   __shared__ uint16_t s_cls_list[kClsLists][kMaxDetCap];
   __shared__ int s_cls_count[kClsLists];
 
+#ifdef MDB_NMS_TIMERS
+  __shared__ long long s_tm[8];
+  __shared__ long long s_t0;
+  if (threadIdx.x == 0) { for (int i = 0; i < 8; ++i) s_tm[i] = 0; s_t0 = clock64(); }
+#endif
   const int img = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float* P = pred + static_cast<size_t>(img) * anchors * no;
@@ -279,6 +294,7 @@ nms_image_kernel(const float* __restrict__ pred, int anchors, int no, float thr,
         s_win_anchor[t] = anc;
       }
       __syncthreads();
+      NMS_T(2);
       const Cand me = s_win[t];
       const int kc = s_kept;
       // (1) against the boxes kept so far: each half of the block scans half of the list
@@ -296,6 +312,7 @@ nms_image_kernel(const float* __restrict__ pred, int anchors, int no, float thr,
       }
       if (half == 1) s_dead1[t] = dead ? 1 : 0;
       __syncthreads();
+      NMS_T(3);
       // (2) compact the survivors of the window, in rank order
       bool alive = false;
       if (half == 0) {
@@ -338,6 +355,7 @@ nms_image_kernel(const float* __restrict__ pred, int anchors, int no, float thr,
           s_sup[ri * kWinWords + w] = bits;
         }
         __syncthreads();
+        NMS_T(4);
         // (4) one warp resolves the window: lane l owns word l of the "removed" bit-vector
         if (warp == 0) {
           uint32_t removed = 0;
@@ -364,6 +382,7 @@ nms_image_kernel(const float* __restrict__ pred, int anchors, int no, float thr,
         }
       }
       __syncthreads();
+      NMS_T(5);
       if (s_kept >= max_det) break;
     }
     __syncthreads();
@@ -374,6 +393,7 @@ nms_image_kernel(const float* __restrict__ pred, int anchors, int no, float thr,
     for (int i = tid; i < n; i += kNmsThreads) sm0[i] = g0[i];
     __syncthreads();
     unsigned long long* res = radix_sort_keys(sm0, sm1, n, s_digit_off, s_warp_digit, &s_flag);
+    NMS_T(1);
     suppress_sorted(res, n, reinterpret_cast<unsigned char*>(res == sm0 ? sm1 : sm0));
   } else {
     // ------------------------------- long list: rounds of <= 8192 keys, highest confidences first -------------------------------
@@ -440,7 +460,9 @@ nms_image_kernel(const float* __restrict__ pred, int anchors, int no, float thr,
           if (take) sm0[wbase + __popc(bal & ((1u << lane) - 1u))] = k;
         }
         __syncthreads();
+        NMS_T(0);
         unsigned long long* res = radix_sort_keys(sm0, sm1, m, s_digit_off, s_warp_digit, &s_flag);
+        NMS_T(1);
         suppress_sorted(res, m, reinterpret_cast<unsigned char*>(res == sm0 ? sm1 : sm0));
       }
       lo = hi;
@@ -481,6 +503,14 @@ nms_image_kernel(const float* __restrict__ pred, int anchors, int no, float thr,
     if (kept_anchor) kept_anchor[static_cast<size_t>(img) * max_det + k] = s_keep_anchor[k];
   }
   if (tid == 0) det_count[img] = kept;
+#ifdef MDB_NMS_TIMERS
+  __syncthreads();
+  NMS_T(6);
+  if (tid == 0) {
+    for (int i = 0; i < 7; ++i) sc.dbg[img * 8 + i] = s_tm[i];
+    sc.dbg[img * 8 + 7] = n;
+  }
+#endif
 }
 
 void nms_init_device() {
@@ -508,6 +538,27 @@ void nms_launch(const float* pred, int n_img, int anchors, int no, float conf_th
   nms_image_kernel<<<n_img, kNmsThreads, kNmsDynSmem, st>>>(pred, anchors, no, conf_thres, iou_thres_floor, max_det,
                                                             d_params, scratch, det_out, det_count, kept_anchor);
   MDB_CUDA(cudaGetLastError());
+#ifdef MDB_NMS_TIMERS
+  {
+    static int prints = 0;
+    if (prints < 6 && getenv("MDB_NMS_DEBUG")) {
+      ++prints;
+      std::vector<long long> h(static_cast<size_t>(n_img) * 8);
+      MDB_CUDA(cudaStreamSynchronize(st));
+      MDB_CUDA(cudaMemcpy(h.data(), scratch.dbg, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+      int worst = 0;
+      long long wt = -1;
+      for (int i = 0; i < n_img; ++i) {
+        long long tot = 0;
+        for (int k = 0; k < 7; ++k) tot += h[i * 8 + k];
+        if (tot > wt) { wt = tot; worst = i; }
+      }
+      fprintf(stderr, "[nms dbg] %d images; slowest image %d: n=%lld cycles: select/hist %lld sort %lld load %lld kept-test %lld compact+matrix %lld resolve %lld tail %lld (total %lld)\n",
+              n_img, worst, h[worst * 8 + 7], h[worst * 8 + 0], h[worst * 8 + 1], h[worst * 8 + 2], h[worst * 8 + 3], h[worst * 8 + 4],
+              h[worst * 8 + 5], h[worst * 8 + 6], wt);
+    }
+  }
+#endif
 }
 
 }  // namespace mdb
