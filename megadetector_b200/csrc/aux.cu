@@ -1,6 +1,7 @@
 // K3 nearest-2x upsample into a concat buffer, K4 SPPF max-pools, K5 Detect decode.
 // All three are pure data movement / elementwise work on NHWC tensors: HBM-bound, 16-byte vector accesses,
 // one thread per (pixel, 8-channel group).
+#include <algorithm>
 #include <cfloat>
 
 #include "common.h"
@@ -12,33 +13,36 @@ namespace mdb {
 // K3: nn.Upsample(scale_factor=2, mode='nearest') (yolov5x6.yaml idx 13/17/21), written
 // straight into channels [c_off, c_off+C) of the following Concat's buffer.
 // ---------------------------------------------------------------------------------------------
+// One thread per SOURCE pixel and 8-channel group: one 16-byte load, four 16-byte stores (the 2x2 destination block);
+// grid.y walks the source rows so that no 64-bit division is needed (the first version spent its time on index arithmetic:
+// 73 % issue-slot utilisation at 44 % of the HBM rate, profiles/r02_ncu_upsample2x_key_metrics.csv).
 __global__ void upsample2x_kernel(const __half* __restrict__ src, long long src_px, int src_coff,
-                                  __half* __restrict__ dst, long long dst_px, int dst_coff, int Hs, int Ws, int C8,
-                                  long long total) {
-  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  const int c8 = static_cast<int>(i % C8);
-  long long p = i / C8;
-  const int Wd = Ws * 2, Hd = Hs * 2;
-  const int x = static_cast<int>(p % Wd);
-  p /= Wd;
-  const int y = static_cast<int>(p % Hd);
-  const long long n = p / Hd;
-  const long long sp = (n * Hs + (y >> 1)) * Ws + (x >> 1);
-  const long long dp = (n * Hd + y) * Wd + x;
-  const uint4 v = __ldg(reinterpret_cast<const uint4*>(src + sp * src_px + src_coff) + c8);
-  reinterpret_cast<uint4*>(dst + dp * dst_px + dst_coff)[c8] = v;
+                                  __half* __restrict__ dst, long long dst_px, int dst_coff, int Hs, int Ws, int C8) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= Ws * C8) return;
+  const int x = t / C8, c8 = t - x * C8;
+  const long long row = blockIdx.y;  // n * Hs + y
+  const long long n = row / Hs;
+  const int y = static_cast<int>(row - n * Hs);
+  const uint4 v = __ldg(reinterpret_cast<const uint4*>(src + (row * Ws + x) * src_px + src_coff) + c8);
+  const int Wd = 2 * Ws;
+  __half* d0 = dst + ((n * 2 * Hs + 2 * y) * Wd + 2 * x) * dst_px + dst_coff;
+  __half* d1 = d0 + static_cast<long long>(Wd) * dst_px;
+  reinterpret_cast<uint4*>(d0)[c8] = v;
+  reinterpret_cast<uint4*>(d0 + dst_px)[c8] = v;
+  reinterpret_cast<uint4*>(d1)[c8] = v;
+  reinterpret_cast<uint4*>(d1 + dst_px)[c8] = v;
 }
 
 void upsample2x_launch(const View& src, const View& dst, int n_img, cudaStream_t st) {
   MDB_REQUIRE(src.C == dst.C && src.C % 8 == 0 && dst.H == 2 * src.H && dst.W == 2 * src.W, "upsample view mismatch");
   const int C8 = src.C / 8;
-  const long long total = static_cast<long long>(n_img) * dst.H * dst.W * C8;
-  if (total == 0) return;
+  if (n_img <= 0 || src.H <= 0 || src.W <= 0) return;
+  MDB_REQUIRE(static_cast<long long>(n_img) * src.H <= 65535, "too many rows for one upsample launch");
   const int threads = 256;
-  upsample2x_kernel<<<static_cast<unsigned>((total + threads - 1) / threads), threads, 0, st>>>(
-      static_cast<const __half*>(src.base), src.Ctot, src.c_off, static_cast<__half*>(dst.base), dst.Ctot, dst.c_off,
-      src.H, src.W, C8, total);
+  dim3 grid(static_cast<unsigned>((src.W * C8 + threads - 1) / threads), static_cast<unsigned>(n_img * src.H));
+  upsample2x_kernel<<<grid, threads, 0, st>>>(static_cast<const __half*>(src.base), src.Ctot, src.c_off,
+                                              static_cast<__half*>(dst.base), dst.Ctot, dst.c_off, src.H, src.W, C8);
   MDB_CUDA(cudaGetLastError());
 }
 
@@ -88,10 +92,62 @@ __global__ void sppf_pool_kernel(const __half* __restrict__ s1, long long px, in
   reinterpret_cast<uint4*>(o + c_p3)[c8] = m13;
 }
 
+// Separable form for feature maps that fit shared memory (always, at MegaDetector's sizes: 12 x 20 at 768 x 1280): one CTA
+// owns the H x W plane of one image and one 8-channel group, and applies the 5-wide row maximum and the 5-high column maximum
+// three times (maxpool5 o maxpool5 o maxpool5, exactly the reference's chain) -- 30 comparisons per output instead of the
+// 169 loads of the direct 13 x 13 window (which ran at 1.7 % of the HBM rate, profiles/r02_ncu_sppf_pool_key_metrics.csv).
+__global__ void sppf_plane_kernel(const __half* __restrict__ s1, long long px, int c_s1, __half* __restrict__ out, int c_p1,
+                                  int c_p2, int c_p3, int H, int W, int C8) {
+  extern __shared__ uint4 s_plane[];
+  uint4* A = s_plane;
+  uint4* B = s_plane + H * W;
+  const int c8 = blockIdx.x % C8;
+  const long long n = blockIdx.x / C8;
+  const int HW = H * W;
+  const __half* base = s1 + n * HW * px;
+  for (int i = threadIdx.x; i < HW; i += blockDim.x) A[i] = __ldg(reinterpret_cast<const uint4*>(base + i * px + c_s1) + c8);
+  __syncthreads();
+  const int offs[3] = {c_p1, c_p2, c_p3};
+  for (int pass = 0; pass < 3; ++pass) {
+    for (int i = threadIdx.x; i < HW; i += blockDim.x) {
+      const int y = i / W, x = i - y * W;
+      uint4 m = A[i];
+      for (int dx = -2; dx <= 2; ++dx) {
+        const int xx = x + dx;
+        if (dx != 0 && xx >= 0 && xx < W) hmax8(m, A[y * W + xx]);
+      }
+      B[i] = m;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < HW; i += blockDim.x) {
+      const int y = i / W, x = i - y * W;
+      uint4 m = B[i];
+      for (int dy = -2; dy <= 2; ++dy) {
+        const int yy = y + dy;
+        if (dy != 0 && yy >= 0 && yy < H) hmax8(m, B[yy * W + x]);
+      }
+      A[i] = m;
+      reinterpret_cast<uint4*>(out + (n * HW + i) * px + offs[pass])[c8] = m;
+    }
+    __syncthreads();
+  }
+}
+
 void sppf_pool_launch(const View& s1, const View& p1, const View& p2, const View& p3, int n_img, cudaStream_t st) {
   MDB_REQUIRE(s1.base == p1.base && s1.base == p2.base && s1.base == p3.base, "SPPF views must share the concat buffer");
   MDB_REQUIRE(s1.C % 8 == 0, "SPPF channels must be a multiple of 8");
   const int C8 = s1.C / 8;
+  {
+    const size_t smem = static_cast<size_t>(s1.H) * s1.W * 2 * sizeof(uint4);
+    if (n_img > 0 && smem <= 48 * 1024) {
+      const int threads = std::min(256, std::max(32, ((s1.H * s1.W + 31) / 32) * 32));
+      sppf_plane_kernel<<<static_cast<unsigned>(n_img * C8), threads, smem, st>>>(
+          static_cast<const __half*>(s1.base), s1.Ctot, s1.c_off, static_cast<__half*>(s1.base), p1.c_off, p2.c_off, p3.c_off,
+          s1.H, s1.W, C8);
+      MDB_CUDA(cudaGetLastError());
+      return;
+    }
+  }
   const long long total = static_cast<long long>(n_img) * s1.H * s1.W * C8;
   if (total == 0) return;
   const int threads = 128;

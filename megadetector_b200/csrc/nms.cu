@@ -10,8 +10,10 @@
 //       In the engine this pass is the tail of the Detect decode kernel (aux.cu), i.e. the prediction tensor is
 //       thresholded by the thread that produced the row; `cand_from_pred_kernel` is the same pass over a given tensor.
 //   K7a one CTA per image: LSD radix sort of the keys, ascending == confidence descending, equal confidence: lower
-//       anchor first (torchvision's stable order).  Lists of up to 8192 candidates are sorted in shared memory, longer
-//       ones in global scratch; passes whose digit is constant (upper anchor bytes, exponent byte) are skipped.
+//       anchor first (torchvision's stable order).  Lists of up to 8192 candidates are sorted entirely in shared memory;
+//       longer ones are cut along a cumulative confidence histogram into rounds of <= 16384 keys, highest confidences
+//       first (sorted between shared memory and a global partner buffer), and stop as soon as max_det boxes are kept; only
+//       a tie group longer than a round falls back to a global sort.  Passes whose digit is constant are skipped.
 //   K7b greedy class-aware suppression over the sorted list in windows of 512 candidates: (1) every candidate of the
 //       window is tested against the boxes kept so far by two threads (half of the kept list each), (2) the survivors
 //       are compacted, (3) their pairwise suppression bit-matrix is computed by all threads, (4) ONE warp resolves the
@@ -427,17 +429,20 @@ nms_image_kernel(const float* __restrict__ pred, int anchors, int no, float thr,
       for (int j = 0; j < 8; ++j) { run += loc[j]; s_cum[tid * 8 + j] = run; }
       __syncthreads();
     }
+    // Rounds of up to 16384 keys: the round's keys are gathered into the whole 128 KB key area, radix-sorted with the global
+    // buffer g1 as ping-pong partner, left in g1, and the suppression windows then use the key area for their own state.
+    constexpr int kRound = 2 * kSortSmemKeys;
     int lo = -1;  // bins <= lo have been processed
     bool fallback = false;
     while (lo < kBins - 1 && s_kept < max_det) {
       const uint32_t done = lo >= 0 ? s_cum[lo] : 0u;
       if (done >= static_cast<uint32_t>(n)) break;
-      // largest hi with cum[hi] - done <= kSortSmemKeys (binary search; every thread computes the same value)
+      // largest hi with cum[hi] - done <= kRound (binary search; every thread computes the same value)
       int a = lo + 1, b = kBins - 1;
-      if (s_cum[a] - done > static_cast<uint32_t>(kSortSmemKeys)) { fallback = true; break; }  // one bin alone is too long
+      if (s_cum[a] - done > static_cast<uint32_t>(kRound)) { fallback = true; break; }  // one bin alone is too long
       while (a < b) {
         const int mid = (a + b + 1) >> 1;
-        if (s_cum[mid] - done <= static_cast<uint32_t>(kSortSmemKeys)) a = mid; else b = mid - 1;
+        if (s_cum[mid] - done <= static_cast<uint32_t>(kRound)) a = mid; else b = mid - 1;
       }
       const int hi = a;
       const int m = static_cast<int>(s_cum[hi] - done);
@@ -461,19 +466,25 @@ nms_image_kernel(const float* __restrict__ pred, int anchors, int no, float thr,
         }
         __syncthreads();
         NMS_T(0);
-        unsigned long long* res = radix_sort_keys(sm0, sm1, m, s_digit_off, s_warp_digit, &s_flag);
+        unsigned long long* res = radix_sort_keys(sm0, g1, m, s_digit_off, s_warp_digit, &s_flag);
+        if (res == sm0) {
+          for (int i = tid; i < m; i += kNmsThreads) g1[i] = sm0[i];
+          __threadfence_block();
+          __syncthreads();
+        }
         NMS_T(1);
-        suppress_sorted(res, m, reinterpret_cast<unsigned char*>(res == sm0 ? sm1 : sm0));
+        suppress_sorted(g1, m, s_dyn);
       }
       lo = hi;
       __syncthreads();
     }
     if (fallback) {
-      // a single confidence bin holds more than 8192 candidates (mass ties): sort the whole list in global memory and
+      // a single confidence bin holds more than 16384 candidates (mass ties): sort the whole list in global memory and
       // continue after the keys already processed (the rounds above consumed exactly the first cum[lo] sorted keys)
       const uint32_t done = lo >= 0 ? s_cum[lo] : 0u;
       __syncthreads();
       const unsigned long long* sorted = radix_sort_keys(g0, g1, n, s_digit_off, s_warp_digit, &s_flag);
+      NMS_T(1);
       suppress_sorted(sorted + done, n - static_cast<int>(done), s_dyn);
     }
   }

@@ -67,7 +67,7 @@ def test_nms_empty_and_all_below_threshold(engine):
 
 
 @pytest.mark.parametrize('n_cand,levels', [(1, 40), (31, 40), (511, 40), (512, 40), (513, 40), (1025, 40), (8191, 40),
-                                           (8192, 40), (8193, 40), (30000, 40), (30000, 4000), (20000, 2), (9000, 1)])
+                                           (8192, 40), (8193, 40), (30000, 40), (30000, 4000), (20000, 2), (9000, 1), (36000, 1), (36000, 3)])
 def test_nms_candidate_count_boundaries(engine, n_cand, levels):
     """Window (512) and shared-memory round (8192) boundaries of the kernel, with many exactly equal confidences (ties must
     resolve to the lower anchor index, torchvision's stable order), a batch whose images have different list lengths, long
