@@ -144,6 +144,12 @@ MDB_API int mdb_infer_preprocessed_rp(mdb_engine* e, const uint8_t* const* lb_hw
  * the letterbox for subsequent calls (default cfg.img_size). */
 MDB_API int mdb_set_image_size(mdb_engine* e, int32_t img_size);
 
+/* Test-time augmentation for the following infer calls: `augment=True` of generate_detections_one_batch
+ * (pytorch_detector.py:1313 `self.model(batch_tensor, augment=augment)`), i.e. yolov5 `_forward_augment`: three passes at
+ * scales 1 / 0.83 (left-right flipped) / 0.67 (bilinear `scale_img`, padded with 0.447 to a multiple of 64), predictions
+ * de-scaled, `_clip_augmented`, concatenated (111 768 rows at 768x1280), then one nms() over all of them. */
+MDB_API int mdb_set_augment(mdb_engine* e, int32_t on);
+
 /* Letterbox geometry exactly as the reference computes it (pytorch_detector.py:434-452,1104-1109):
  * out[0..7] = new_unpad_w, new_unpad_h, top, bottom, left, right, out_h, out_w ; ratio_pad[0..2] = r, dw, dh */
 MDB_API int mdb_letterbox_geometry(const mdb_config* cfg, int32_t h, int32_t w, int32_t* out8, double* ratio_pad3);

@@ -21,7 +21,7 @@ EXPORTS = [
     'mdb_create', 'mdb_load_weights', 'mdb_destroy', 'mdb_last_error', 'mdb_infer_batch', 'mdb_batch_begin', 'mdb_batch_next', 'mdb_infer_preprocessed',
     'mdb_letterbox_geometry', 'mdb_set_image_size', 'mdb_debug_fetch', 'mdb_last_timing', 'mdb_bench_resident', 'mdb_profile_steps', 'mdb_set_pipeline_split', 'mdb_launch_count', 'mdb_op_letterbox',
     'mdb_op_conv2d', 'mdb_op_nms', 'mdb_alloc_pinned', 'mdb_free_pinned', 'mdb_version',
-    'mdb_infer_jpeg_batch', 'mdb_op_decode_jpeg', 'mdb_infer_preprocessed_rp',
+    'mdb_infer_jpeg_batch', 'mdb_op_decode_jpeg', 'mdb_infer_preprocessed_rp', 'mdb_set_augment',
     'mdb_debug_set_trace', 'mdb_debug_trace_names', 'mdb_debug_fetch_trace', 'mdb_op_upsample2x', 'mdb_op_sppf_pool', 'mdb_op_decode',
 ]
 
@@ -109,6 +109,8 @@ def load_library():
     lib.mdb_op_conv2d.restype = C.c_int
     lib.mdb_op_nms.argtypes = [vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_double, C.c_int32, vp, vp, vp]
     lib.mdb_op_nms.restype = C.c_int
+    lib.mdb_set_augment.argtypes = [vp, C.c_int32]
+    lib.mdb_set_augment.restype = C.c_int
     lib.mdb_infer_preprocessed_rp.argtypes = [vp, P(vp), P(C.c_int32), P(C.c_int32), P(C.c_int32), P(C.c_int32), vp,
                                               C.c_int32, C.c_float, vp, vp, vp, vp]
     lib.mdb_infer_preprocessed_rp.restype = C.c_int
@@ -378,6 +380,9 @@ class Engine:
         self._check(self.lib.mdb_op_decode_jpeg(self.h, a.ctypes.data, a.size, out.ctypes.data, out.nbytes, hw, C.byref(be)),
                     'mdb_op_decode_jpeg')
         return out, int(be.value)
+
+    def set_augment(self, on):
+        self._check(self.lib.mdb_set_augment(self.h, int(bool(on))), 'mdb_set_augment')
 
     def set_image_size(self, img_size):
         self._check(self.lib.mdb_set_image_size(self.h, int(img_size)), 'mdb_set_image_size')

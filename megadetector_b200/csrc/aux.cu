@@ -172,9 +172,11 @@ __device__ __forceinline__ float sigmoid_acc(float x) { return __fdiv_rn(1.0f, _
 
 // With `keys != nullptr` the kernel also runs K6 on the row it just produced (confidence threshold, best class,
 // candidate key append; see nms.cu): the prediction tensor is thresholded at HBM rate by the thread that wrote it.
+// TTA (yolov5 _forward_augment): a pass writes its rows at `out_base` of a longer per-image tensor of `out_rows` rows, with
+// _descale_pred applied: xywh /= scale, and x = flip_w - x for the left-right flipped pass (flip_w == 0: no flip).
 __global__ void decode_kernel(const DecodeArgs args, int no, int rows_per_img, float* __restrict__ pred,
                               long long total_rows, float thr, unsigned long long* __restrict__ keys,
-                              int32_t* __restrict__ counts, int cap) {
+                              int32_t* __restrict__ counts, int cap, int out_base, int out_rows, float scale, float flip_w) {
   const long long r = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const bool in = r < total_rows;
   int n = -1, row = 0;
@@ -193,13 +195,19 @@ __global__ void decode_kernel(const DecodeArgs args, int no, int rows_per_img, f
     const int iy = (local / L.nx) % L.ny;
     const int a = local / (L.nx * L.ny);
     const float* src = L.raw + ((static_cast<long long>(n) * L.ny + iy) * L.nx + ix) * L.c_stride + a * no;
-    float* dst = pred + r * no;
+    row += out_base;
+    float* dst = pred + (static_cast<long long>(n) * out_rows + row) * no;
     const float s0 = sigmoid_acc(src[0]), s1 = sigmoid_acc(src[1]), s2 = sigmoid_acc(src[2]), s3 = sigmoid_acc(src[3]);
-    dst[0] = __fmul_rn(__fadd_rn(__fmul_rn(s0, 2.0f), static_cast<float>(ix) - 0.5f), L.stride);
-    dst[1] = __fmul_rn(__fadd_rn(__fmul_rn(s1, 2.0f), static_cast<float>(iy) - 0.5f), L.stride);
+    float bx = __fmul_rn(__fadd_rn(__fmul_rn(s0, 2.0f), static_cast<float>(ix) - 0.5f), L.stride);
+    float by = __fmul_rn(__fadd_rn(__fmul_rn(s1, 2.0f), static_cast<float>(iy) - 0.5f), L.stride);
     const float w2 = __fmul_rn(s2, 2.0f), h2 = __fmul_rn(s3, 2.0f);
-    dst[2] = __fmul_rn(__fmul_rn(w2, w2), L.anchors[a][0]);
-    dst[3] = __fmul_rn(__fmul_rn(h2, h2), L.anchors[a][1]);
+    float bw = __fmul_rn(__fmul_rn(w2, w2), L.anchors[a][0]);
+    float bh = __fmul_rn(__fmul_rn(h2, h2), L.anchors[a][1]);
+    if (scale != 1.0f) {
+      bx = __fdiv_rn(bx, scale); by = __fdiv_rn(by, scale); bw = __fdiv_rn(bw, scale); bh = __fdiv_rn(bh, scale);
+    }
+    if (flip_w != 0.0f) bx = __fsub_rn(flip_w, bx);
+    dst[0] = bx; dst[1] = by; dst[2] = bw; dst[3] = bh;
     const float obj = sigmoid_acc(src[4]);
     dst[4] = obj;
     float best = -INFINITY;
@@ -217,15 +225,88 @@ __global__ void decode_kernel(const DecodeArgs args, int no, int rows_per_img, f
 }
 
 void decode_launch(const DecodeLevel* lv4, int n_img, int no, int rows_per_img, float* pred, cudaStream_t st, float thr,
-                   unsigned long long* cand_keys, int32_t* cand_counts, int cand_cap) {
+                   unsigned long long* cand_keys, int32_t* cand_counts, int cand_cap, const DecodePass* pass) {
   DecodeArgs args;
   for (int i = 0; i < 4; ++i) args.lv[i] = lv4[i];
   const long long total = static_cast<long long>(n_img) * rows_per_img;
   if (total == 0) return;
-  if (cand_keys != nullptr) MDB_CUDA(cudaMemsetAsync(cand_counts, 0, sizeof(int32_t) * n_img, st));
+  const bool first = pass == nullptr || pass->out_base == 0;
+  if (cand_keys != nullptr && first) MDB_CUDA(cudaMemsetAsync(cand_counts, 0, sizeof(int32_t) * n_img, st));
   const int threads = 256;
   decode_kernel<<<static_cast<unsigned>((total + threads - 1) / threads), threads, 0, st>>>(
-      args, no, rows_per_img, pred, total, thr, cand_keys, cand_counts, cand_cap);
+      args, no, rows_per_img, pred, total, thr, cand_keys, cand_counts, cand_cap, pass ? pass->out_base : 0,
+      pass ? pass->out_rows : rows_per_img, pass ? pass->scale : 1.0f, pass ? pass->flip_w : 0.0f);
+  MDB_CUDA(cudaGetLastError());
+}
+
+// ---------------------------------------------------------------------------------------------
+// TTA input: yolov5 utils/torch_utils.py scale_img(x.flip(3) if flip else x, ratio, gs=64) on the normalised image:
+// F.interpolate(size=(int(H*r), int(W*r)), mode='bilinear', align_corners=False), then pad right/bottom with 0.447 to the
+// next multiple of 64.  Source = the stem-input tensor K1 wrote (its centre tap holds every pixel's fp16(v / 255): v is
+// recovered exactly and the interpolation runs on float(v) / 255 in fp32 like the reference's); destination = the stem-input
+// tensor of the plan of the scaled shape, in the same tap-packed space-to-depth layout.
+// ---------------------------------------------------------------------------------------------
+__global__ void tta_scale_s2d_kernel(const __half* __restrict__ src, int H, int W, __half* __restrict__ dst, int Hd, int Wd,
+                                     int hs, int ws, float sc_h, float sc_w, int flip, long long total) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int W2d = Wd >> 1, H2d = Hd >> 1, W2 = W >> 1;
+  const int x2 = static_cast<int>(i % W2d);
+  const int y2 = static_cast<int>((i / W2d) % H2d);
+  const long long n = i / (static_cast<long long>(W2d) * H2d);
+  const __half* S = src + n * (H >> 1) * W2 * 48;
+  auto pix = [&](int sy, int sx, int c) -> float {  // exact float(v) / 255 of source pixel (sy, sx), channel c
+    if (flip) sx = W - 1 - sx;
+    const __half h = S[(static_cast<long long>(sy >> 1) * W2 + (sx >> 1)) * 48 + 16 + ((sy & 1) * 2 + (sx & 1)) * 3 + c];
+    const float v = rintf(__half2float(h) * 255.0f);
+    return __fdiv_rn(v, 255.0f);
+  };
+  __half out[12];
+#pragma unroll
+  for (int py = 0; py < 2; ++py) {
+    const int Y = 2 * y2 + py;
+#pragma unroll
+    for (int px = 0; px < 2; ++px) {
+      const int X = 2 * x2 + px;
+      float v[3] = {0.447f, 0.447f, 0.447f};
+      if (Y < hs && X < ws) {
+        // PyTorch upsample_bilinear2d, align_corners=False: src = scale * (dst + 0.5) - 0.5 clamped at 0
+        float fy = sc_h * (static_cast<float>(Y) + 0.5f) - 0.5f;
+        float fx = sc_w * (static_cast<float>(X) + 0.5f) - 0.5f;
+        fy = fy < 0.f ? 0.f : fy;
+        fx = fx < 0.f ? 0.f : fx;
+        const int y0 = static_cast<int>(fy), x0 = static_cast<int>(fx);
+        const int y1 = y0 + (y0 < H - 1 ? 1 : 0), x1 = x0 + (x0 < W - 1 ? 1 : 0);
+        const float ly1 = fy - y0, lx1 = fx - x0, ly0 = 1.f - ly1, lx0 = 1.f - lx1;
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+          v[c] = ly0 * (lx0 * pix(y0, x0, c) + lx1 * pix(y0, x1, c)) + ly1 * (lx0 * pix(y1, x0, c) + lx1 * pix(y1, x1, c));
+      }
+#pragma unroll
+      for (int c = 0; c < 3; ++c) out[(py * 2 + px) * 3 + c] = __float2half_rn(v[c]);
+    }
+  }
+  // this pixel's 2x2 block is tap 1 of itself, tap 0 of its right neighbour and tap 2 of its left neighbour
+  __half* D = dst + (n * H2d + y2) * static_cast<long long>(W2d) * 48;
+#pragma unroll
+  for (int t = 0; t < 3; ++t) {
+    const int xd = x2 + 1 - t;
+    if (xd < 0 || xd >= W2d) continue;
+    __half* d = D + static_cast<long long>(xd) * 48 + t * 16;
+#pragma unroll
+    for (int k = 0; k < 12; ++k) d[k] = out[k];
+  }
+}
+
+void tta_scale_launch(const __half* src, int H, int W, __half* dst, int Hd, int Wd, double ratio, bool flip, int n_img,
+                      cudaStream_t st) {
+  const int hs = static_cast<int>(H * ratio), ws = static_cast<int>(W * ratio);
+  MDB_REQUIRE(hs >= 1 && ws >= 1 && hs <= Hd && ws <= Wd, "TTA scaled size does not fit its plan");
+  const long long total = static_cast<long long>(n_img) * (Hd >> 1) * (Wd >> 1);
+  if (total == 0) return;
+  const float sc_h = static_cast<float>(H) / static_cast<float>(hs), sc_w = static_cast<float>(W) / static_cast<float>(ws);
+  tta_scale_s2d_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(src, H, W, dst, Hd, Wd, hs, ws, sc_h, sc_w,
+                                                                                   flip ? 1 : 0, total);
   MDB_CUDA(cudaGetLastError());
 }
 

@@ -162,9 +162,17 @@ struct DecodeLevel {
   float anchors[3][2];
   int row_off;
 };
+struct DecodePass {  // one pass of test-time augmentation: where its rows go in the concatenated tensor and how to de-scale them
+  int out_base, out_rows;
+  float scale, flip_w;
+};
 // thr / cand_*: when cand_keys != nullptr the kernel also runs the candidate pass (K6, nms.cu) on the rows it writes
 void decode_launch(const DecodeLevel* lv4, int n_img, int no, int rows_per_img, float* pred, cudaStream_t st,
-                   float thr = 0.0f, unsigned long long* cand_keys = nullptr, int32_t* cand_counts = nullptr, int cand_cap = 0);
+                   float thr = 0.0f, unsigned long long* cand_keys = nullptr, int32_t* cand_counts = nullptr, int cand_cap = 0,
+                   const DecodePass* pass = nullptr);
+// TTA input scaling (yolov5 scale_img) from one plan's stem-input tensor into another's
+void tta_scale_launch(const __half* src, int H, int W, __half* dst, int Hd, int Wd, double ratio, bool flip, int n_img,
+                      cudaStream_t st);
 
 // ---------------------------------------------------------------------------------------------
 // K6-K8 (nms.cu)

@@ -65,6 +65,11 @@ struct Plan {
   NmsScratch nms_scratch{};
   double macs_per_image = 0;
   std::map<int, cudaGraphExec_t> graphs;  // forward pass per batch size
+  // test-time augmentation (mdb_set_augment): concatenated predictions of the three passes and their NMS scratch
+  float* pred_tta = nullptr;
+  int anchors_tta = 0;
+  void* nms_mem_tta = nullptr;
+  NmsScratch nms_scratch_tta{};
   // parity harness (mdb_debug_set_trace): dense copies of the traced steps' input / output / residual views
   struct TraceRec {
     size_t off[3] = {0, 0, 0};      // in, out, res
@@ -77,6 +82,8 @@ struct Plan {
   size_t trace_cap = 0;
   ~Plan() {
     if (trace_mem) cudaFree(trace_mem);
+    if (pred_tta) cudaFree(pred_tta);
+    if (nms_mem_tta) cudaFree(nms_mem_tta);
     for (auto& kv : graphs) cudaGraphExecDestroy(kv.second);
     for (auto& s : steps)
       if (s.op) conv_free(s.op);
@@ -190,6 +197,8 @@ struct mdb_engine {
   int pipeline_split = 4;
   bool edge_taper = false;
   bool use_graphs = true;
+  bool augment = false;  // TTA for the following infer calls (generate_detections_one_batch(..., augment=True))
+  bool last_augment = false;
   bool trace_all = false;
   std::vector<std::string> trace_names;
   BatchState batch;
@@ -719,10 +728,43 @@ void stage_compute(mdb_engine* e, Plan* P, int n, int slot, float conf_thres, in
     e->launches++;
   }
   if (timing) MDB_CUDA(cudaEventRecord(e->ev_tt[slot][1], st));
+  // test-time augmentation (yolov5 _forward_augment): scales 1, 0.83 (left-right flipped), 0.67 -- the two extra inputs are
+  // derived from K1's output and run through the plans of their own (64-aligned) shapes
+  static const double kTtaScale[3] = {1.0, 0.83, 0.67};
+  static const bool kTtaFlip[3] = {false, true, false};
+  Plan* tp[3] = {P, nullptr, nullptr};
+  const bool tta = e->augment;
+  if (tta) {
+    for (int k = 1; k < 3; ++k) {
+      const int hk = static_cast<int>(std::ceil(P->H * kTtaScale[k] / 64.0)) * 64, wk = static_cast<int>(std::ceil(P->W * kTtaScale[k] / 64.0)) * 64;
+      tp[k] = get_plan(e, hk, wk);
+    }
+    tp[0] = get_plan(e, P->H, P->W);  // refresh its LRU position
+    if (P->pred_tta == nullptr) {
+      // _clip_augmented: the first pass loses its coarsest level, the last pass its finest
+      P->anchors_tta = (tp[0]->anchors - 3 * tp[0]->lv[3].ny * tp[0]->lv[3].nx) + tp[1]->anchors +
+                       (tp[2]->anchors - 3 * tp[2]->lv[0].ny * tp[2]->lv[0].nx);
+      MDB_CUDA(cudaMalloc(&P->pred_tta, static_cast<size_t>(P->nb) * P->anchors_tta * no * sizeof(float)));
+      MDB_CUDA(cudaMalloc(&P->nms_mem_tta, nms_scratch_bytes(P->nb, P->anchors_tta)));
+      nms_bind_scratch(&P->nms_scratch_tta, P->nms_mem_tta, P->nb, P->anchors_tta);
+    }
+  }
   if (stages_mask & 2) {
     // the Detect heads of this pass overwrite the raw buffers the previous pass's decode reads
     MDB_CUDA(cudaStreamWaitEvent(st, e->ev_decode_done, 0));
+    if (tta) {
+      const __half* stem0 = static_cast<const __half*>(P->view(VView{P->stem_buf, 0, 48}).base);
+      for (int k = 1; k < 3; ++k) {
+        __half* stemk = static_cast<__half*>(tp[k]->view(VView{tp[k]->stem_buf, 0, 48}).base);
+        tta_scale_launch(stem0, P->H, P->W, stemk, tp[k]->H, tp[k]->W, kTtaScale[k], kTtaFlip[k], n, st);
+        e->launches++;
+      }
+    }
     run_network(e, P, n, st);
+    if (tta) {
+      run_network(e, tp[1], n, st);
+      run_network(e, tp[2], n, st);
+    }
   }
   if (timing) MDB_CUDA(cudaEventRecord(e->ev_tt[slot][2], st));
   if (stages_mask & 4) {
@@ -731,12 +773,38 @@ void stage_compute(mdb_engine* e, Plan* P, int n, int slot, float conf_thres, in
     cudaStream_t sp = e->st_post;
     MDB_CUDA(cudaEventRecord(e->ev_net_done[slot], st));
     MDB_CUDA(cudaStreamWaitEvent(sp, e->ev_net_done[slot], 0));
-    decode_launch(P->lv, n, no, P->anchors, P->pred, sp, conf_thres, P->nms_scratch.key[0], P->nms_scratch.count,
-                  P->nms_scratch.cap);
-    MDB_CUDA(cudaEventRecord(e->ev_decode_done, sp));
-    nms_launch(P->pred, n, P->anchors, no, conf_thres, float_floor_of_double(static_cast<double>(e->cfg.iou_thres)),
-               max_det, e->d_nmsp[slot], P->nms_scratch, e->d_det[slot], e->d_cnt[slot], e->d_anchor[slot], sp);
-    e->launches += 2;  // decode + candidate pass (one kernel), per-image sort + suppression
+    if (!tta) {
+      decode_launch(P->lv, n, no, P->anchors, P->pred, sp, conf_thres, P->nms_scratch.key[0], P->nms_scratch.count,
+                    P->nms_scratch.cap);
+      MDB_CUDA(cudaEventRecord(e->ev_decode_done, sp));
+      nms_launch(P->pred, n, P->anchors, no, conf_thres, float_floor_of_double(static_cast<double>(e->cfg.iou_thres)),
+                 max_det, e->d_nmsp[slot], P->nms_scratch, e->d_det[slot], e->d_cnt[slot], e->d_anchor[slot], sp);
+      e->launches += 2;  // decode + candidate pass (one kernel), per-image sort + suppression
+    } else {
+      // three decodes into one concatenated tensor (_descale_pred + _clip_augmented + torch.cat), then one NMS over it
+      int base = 0;
+      for (int k = 0; k < 3; ++k) {
+        DecodeLevel lv[4];
+        int cnt = 0, off = 0;
+        for (int l = 0; l < 4; ++l) {
+          if ((k == 0 && l == 3) || (k == 2 && l == 0)) continue;  // clipped level
+          lv[cnt] = tp[k]->lv[l];
+          lv[cnt].row_off = off;
+          off += 3 * lv[cnt].ny * lv[cnt].nx;
+          ++cnt;
+        }
+        for (; cnt < 4; ++cnt) { lv[cnt] = lv[0]; lv[cnt].row_off = 0x7fffffff; }
+        DecodePass dp{base, P->anchors_tta, static_cast<float>(kTtaScale[k]), kTtaFlip[k] ? static_cast<float>(P->W) : 0.0f};
+        decode_launch(lv, n, no, off, P->pred_tta, sp, conf_thres, P->nms_scratch_tta.key[0], P->nms_scratch_tta.count,
+                      P->nms_scratch_tta.cap, &dp);
+        base += off;
+      }
+      MDB_CUDA(cudaEventRecord(e->ev_decode_done, sp));
+      nms_launch(P->pred_tta, n, P->anchors_tta, no, conf_thres, float_floor_of_double(static_cast<double>(e->cfg.iou_thres)),
+                 max_det, e->d_nmsp[slot], P->nms_scratch_tta, e->d_det[slot], e->d_cnt[slot], e->d_anchor[slot], sp);
+      e->launches += 4;
+    }
+    e->last_augment = tta;
     MDB_CUDA(cudaMemcpyAsync(e->h_det[slot], e->d_det[slot], sizeof(float) * n * max_det * 6, cudaMemcpyDeviceToHost, sp));
     MDB_CUDA(cudaMemcpyAsync(e->h_cnt[slot], e->d_cnt[slot], sizeof(int32_t) * n, cudaMemcpyDeviceToHost, sp));
     MDB_CUDA(cudaMemcpyAsync(e->h_anchor[slot], e->d_anchor[slot], sizeof(int32_t) * n * max_det, cudaMemcpyDeviceToHost, sp));
@@ -1315,6 +1383,13 @@ int mdb_set_image_size(mdb_engine* e, int32_t img_size) {
   return MDB_OK;
 }
 
+int mdb_set_augment(mdb_engine* e, int32_t on) {
+  if (!e) return MDB_ERR_ARG;
+  e->augment = on != 0;
+  if (e->augment) e->max_plans = std::max(e->max_plans, 7);  // three plans per shape group, two groups in flight
+  return MDB_OK;
+}
+
 int mdb_set_pipeline_split(mdb_engine* e, int32_t parts) {
   if (!e || parts < 1 || parts > 8) return fail(e, MDB_ERR_ARG, "pipeline split out of range");
   e->pipeline_split = parts;
@@ -1443,8 +1518,10 @@ int mdb_debug_fetch(mdb_engine* e, int32_t what, int32_t index, void* host_dst, 
       need = static_cast<size_t>(n) * v.H * v.W * 48 * 2;
     } else if (what == MDB_FETCH_PRED) {
       const int no = e->cfg.arch.nc + 5;
-      src = P->pred; shp[0] = n; shp[1] = P->anchors; shp[2] = no; shp[3] = 1;
-      need = static_cast<size_t>(n) * P->anchors * no * 4;
+      const bool tta = e->last_augment && P->pred_tta != nullptr;
+      const int rows = tta ? P->anchors_tta : P->anchors;
+      src = tta ? P->pred_tta : P->pred; shp[0] = n; shp[1] = rows; shp[2] = no; shp[3] = 1;
+      need = static_cast<size_t>(n) * rows * no * 4;
     } else if (what == MDB_FETCH_LAYER) {
       int ci = -1;
       const Step* st = nullptr;

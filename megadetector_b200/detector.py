@@ -19,7 +19,8 @@ What runs where:
 Compatibility modes: 'classic' (and any mode string containing it) and the non-classic ("modern") behaviour of
 pytorch_detector.py:1036-1101,1318-1321,1372-1397: INTER_AREA / INTER_LINEAR pre-resize of the long side, padding to
 ceil(side / stride + 0.5) * stride, NMS IoU 0.6, scale_coords with ratio_pad, round() instead of truncation.
-Not supported (raise NotImplementedError, never a silent approximation): `augment=True` (TTA), `force_cpu` (no CPU path).
+`augment=True` runs yolov5's test-time augmentation (three scaled / flipped passes) inside the engine (mdb_set_augment).
+Not supported (raises NotImplementedError, never a silent approximation): `force_cpu` (there is no CPU path).
 """
 
 import gc
@@ -247,8 +248,6 @@ class B200Detector:
                         i_img))
         if self.engine is None:
             raise RuntimeError('this B200Detector was created with preprocess_only; it cannot run inference')
-        if augment:
-            raise NotImplementedError('augment=True (TTA) is not implemented in B200Detector')
         if detection_threshold is None:
             detection_threshold = 0.0
         size = self.default_image_size if image_size is None else image_size
@@ -317,8 +316,10 @@ class B200Detector:
         gc_was_enabled = gc.isenabled()
         gc.disable()
         try:
+            self.engine.set_augment(bool(augment))  # yolov5 _forward_augment: 3 scaled / flipped passes (:1313)
             self._infer_and_format(good, dict_mode, arrays, src_shapes, detection_threshold, finish, results, ids, gain_pads)
         finally:
+            self.engine.set_augment(False)
             if gc_was_enabled:
                 gc.enable()
         return results

@@ -207,3 +207,58 @@ def forward(x, w, arch=None, trace=None):
         raw = _conv(f, w, 'model.33.m.%d' % l, act=False, trace=trace)
         z.append(decode_level(raw, l, arch))
     return torch.cat(z, 1)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Test-time augmentation: `model(x, augment=True)` (pytorch_detector.py:1313 with augment) -> yolov5 models/yolo.py
+# `DetectionModel._forward_augment` / `_descale_pred` / `_clip_augmented` and utils/torch_utils.py `scale_img`
+# (ultralytics-yolov5 0.1.1, absent offline: restated from the public source, PARITY UNPINNED like the rest of this file)
+# ---------------------------------------------------------------------------------------------------------------
+TTA_SCALES = (1, 0.83, 0.67)
+TTA_FLIPS = (None, 3, None)  # 3 = left-right
+
+
+def scale_img(img, ratio=1.0, gs=64):
+    """yolov5 scale_img(img, ratio, same_shape=False, gs): bilinear resize, then pad right/bottom to a gs multiple with 0.447."""
+    import math
+    if ratio == 1.0:
+        return img
+    h, w = img.shape[2:]
+    s = (int(h * ratio), int(w * ratio))
+    img = F.interpolate(img, size=s, mode='bilinear', align_corners=False)
+    h, w = (math.ceil(x * ratio / gs) * gs for x in (h, w))
+    return F.pad(img, [0, w - s[1], 0, h - s[0]], value=0.447)
+
+
+def _descale_pred(p, flips, scale, img_size):
+    p = p.clone()
+    p[..., :4] /= scale
+    if flips == 2:
+        p[..., 1] = img_size[0] - p[..., 1]
+    elif flips == 3:
+        p[..., 0] = img_size[1] - p[..., 0]
+    return p
+
+
+def _clip_augmented(y, nl=4):
+    g = sum(4 ** x for x in range(nl))
+    e = 1
+    i = (y[0].shape[1] // g) * sum(4 ** x for x in range(e))
+    y[0] = y[0][:, :-i]
+    i = (y[-1].shape[1] // g) * sum(4 ** (nl - 1 - x) for x in range(e))
+    y[-1] = y[-1][:, i:]
+    return y
+
+
+@torch.no_grad()
+def forward_augment(x, w, arch=None):
+    """pred of `model(x, augment=True)[0]`: the three scaled / flipped passes, de-scaled, clipped and concatenated."""
+    arch = arch or Arch()
+    img_size = x.shape[-2:]
+    y = []
+    for si, fi in zip(TTA_SCALES, TTA_FLIPS):
+        xi = scale_img(x.flip(fi) if fi else x, si, gs=STRIDES[-1])
+        yi = forward(xi, w, arch)
+        y.append(_descale_pred(yi, fi, si, img_size))
+    y = _clip_augmented(y)
+    return torch.cat(y, 1)

@@ -3,7 +3,7 @@ The non-"classic" compatibility mode ("modern", SURVEY.md par. 8f-4) on the GPU,
 /root/reference/megadetector/detection/pytorch_detector.py:1036-1101 (INTER_AREA / INTER_LINEAR pre-resize, padding to
 ceil(side / stride + 0.5) * stride), :1318-1321 (NMS IoU 0.6), :1372-1381 (scale_coords with ratio_pad) and :1395-1397
 (round() instead of truncation).  The oracle's preprocessing is pinned to the real cv2 in tests/test_oracle_modern.py.
-TTA (`augment=True`) is not implemented and raises.
+TTA (`augment=True`) is covered by tests/test_gpu_tta.py.
 """
 import numpy as np
 import pytest
@@ -82,6 +82,4 @@ def test_modern_mode_end_to_end():
     for dd, p in zip(dicts, pre):
         assert np.array_equal(dd['img_processed'], p['img_processed']) and dd['letterbox_pad'] == p['letterbox_pad']
     assert det.generate_detections_one_batch(dicts, None, detection_threshold=0.005) == recs
-    with pytest.raises(NotImplementedError):
-        det.generate_detections_one_batch(imgs[:1], ids[:1], augment=True)
     det.close()
