@@ -98,3 +98,43 @@ def test_b200_detector_on_a_4k_clip_equals_the_per_frame_reference_loop(tmp_path
     assert got['frame_filenames'] == ref['frame_filenames'] == ['frame000000.jpg', 'frame000010.jpg', 'frame000020.jpg', 'frame000030.jpg']
     assert got['results'] == ref['results']
     assert all(r['detections'] is not None for r in got['results'])
+
+
+@needs_ref
+@pytest.mark.gpu
+def test_reference_process_videos_with_the_hook_equals_the_batched_driver(tmp_path):
+    """The reference's own `process_video.process_videos` (process_video.py:123-280) driven through the INTEGRATION.md hook
+    (B200Detector behind load_detector, one frame per call) writes the same "images" entries as
+    megadetector_b200.video.process_videos (frames batched within each video)."""
+    import json
+    sys.path.insert(0, os.path.join(ROOT, 'tools'))
+    import run_config1
+    from megadetector_b200 import video
+    from megadetector_b200.detector import B200Detector
+    from megadetector_b200.synth_checkpoint import write_synthetic_checkpoint
+    run_config1.install_hook()
+    from megadetector.detection import process_video
+    folder = tmp_path / 'videos'
+    os.makedirs(str(folder / 'sub'))
+    _write_video(str(folder / 'a.mp4'), 12, 270, 480)
+    _write_video(str(folder / 'sub' / 'b.mp4'), 7, 300, 400, fps=15.0)
+    model = str(tmp_path / 'md_synth_tiny.pt')
+    write_synthetic_checkpoint('synthetic://tiny?seed=0', model)
+    opt = process_video.ProcessVideoOptions()
+    opt.model_file = model
+    opt.input_video_file = str(folder)
+    opt.output_json_file = str(tmp_path / 'ref.json')
+    opt.recursive = True
+    opt.frame_sample = 3
+    opt.json_confidence_threshold = 0.01
+    opt.detector_options = {'engine': 'b200', 'max_batch': 8}
+    process_video.process_videos(opt)
+    ref = json.load(open(opt.output_json_file))
+    det = B200Detector(model, {'max_batch': 8})
+    got = video.process_videos(det, str(folder), str(tmp_path / 'got.json'), frame_sample=3, batch_size=8,
+                               json_confidence_threshold=0.01, recursive=True)
+    det.close()
+    assert got['detection_categories'] == ref['detection_categories']
+    key = lambda im: im['file']
+    assert sorted(got['images'], key=key) == sorted(ref['images'], key=key)
+    assert sum(len(im['detections']) for im in got['images']) > 0

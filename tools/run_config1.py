@@ -48,6 +48,11 @@ def install_hook():
 
     run_detector.load_detector = load_detector
     run_detector_batch.load_detector = load_detector
+    try:  # process_video binds the name at import time too (process_video.py:158 `detector = load_detector(...)`)
+        from megadetector.detection import process_video
+        process_video.load_detector = load_detector
+    except Exception:
+        pass
     return run_detector, run_detector_batch
 
 
