@@ -181,6 +181,8 @@ def write_results(results, output_file, relative_path_base=None, detector_file=N
         if relative_path_base is not None:
             r['file'] = os.path.relpath(r['file'], relative_path_base).replace('\\', '/')
         r.pop('max_detection_conf', None)  # include_max_conf=False is the reference's default
+        if r.get('detections') is not None:  # run_detector_batch.py:1634-1637: descending confidence (stable)
+            r['detections'] = sorted(r['detections'], key=lambda d: d['conf'], reverse=True)
         images.append(r)
     images.sort(key=lambda r: r['file'])
     info = {'detection_completion_time': time.strftime('%Y-%m-%d %H:%M:%S', time.gmtime()), 'format_version': '1.4'}

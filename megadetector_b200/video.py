@@ -209,6 +209,10 @@ def process_videos(detector, input_video_file, output_json_file=None, frame_samp
         except Exception as e:
             print('Video {} failed: {}'.format(v, e))
             images.append(video_results_to_md_format(rel, -1, {'failure': FAILURE_VIDEO_OPEN}))
+    images.sort(key=lambda im: im['file'])  # write_results_to_file: by file, detections by descending confidence (stable)
+    for im in images:
+        if im.get('detections') is not None:
+            im['detections'] = sorted(im['detections'], key=lambda d: d['conf'], reverse=True)
     out = {'images': images, 'detection_categories': {'1': 'animal', '2': 'person', '3': 'vehicle'},
            'info': {'detection_completion_time': time.strftime('%Y-%m-%d %H:%M:%S', time.gmtime()), 'format_version': '1.4'}}
     if detector_file is not None:

@@ -78,7 +78,9 @@ def test_md_format_assembly_and_folder_driver(tmp_path):
     by = {im['file']: im for im in out['images']}
     assert set(by) == {'a.mp4', 'broken.mp4', 'sub/b.mp4'}
     assert by['a.mp4']['frames_processed'] == [0, 2, 4, 6, 8] and by['sub/b.mp4']['frame_rate'] == 15.0
-    assert [d['frame_number'] for d in by['a.mp4']['detections']] == [0, 2, 4, 6, 8]
+    assert sorted(d['frame_number'] for d in by['a.mp4']['detections']) == [0, 2, 4, 6, 8]
+    confs = [d['conf'] for d in by['a.mp4']['detections']]
+    assert confs == sorted(confs, reverse=True)
     assert by['broken.mp4']['detections'] is None and by['broken.mp4']['failure'] == video.FAILURE_VIDEO_OPEN
     assert all(set(d) == {'category', 'conf', 'bbox', 'frame_number'} for d in by['a.mp4']['detections'])
 
@@ -100,17 +102,14 @@ def test_b200_detector_on_a_4k_clip_equals_the_per_frame_reference_loop(tmp_path
     assert all(r['detections'] is not None for r in got['results'])
 
 
-@needs_ref
-@pytest.mark.gpu
-def test_reference_process_videos_with_the_hook_equals_the_batched_driver(tmp_path):
+def _process_videos_both_ways(tmp_path, engine, make_detector):
     """The reference's own `process_video.process_videos` (process_video.py:123-280) driven through the INTEGRATION.md hook
-    (B200Detector behind load_detector, one frame per call) writes the same "images" entries as
-    megadetector_b200.video.process_videos (frames batched within each video)."""
+    (one frame per detector call) must write the same "images" entries as megadetector_b200.video.process_videos (frames
+    batched within each video)."""
     import json
     sys.path.insert(0, os.path.join(ROOT, 'tools'))
     import run_config1
     from megadetector_b200 import video
-    from megadetector_b200.detector import B200Detector
     from megadetector_b200.synth_checkpoint import write_synthetic_checkpoint
     run_config1.install_hook()
     from megadetector.detection import process_video
@@ -127,14 +126,28 @@ def test_reference_process_videos_with_the_hook_equals_the_batched_driver(tmp_pa
     opt.recursive = True
     opt.frame_sample = 3
     opt.json_confidence_threshold = 0.01
-    opt.detector_options = {'engine': 'b200', 'max_batch': 8}
+    opt.detector_options = {'engine': engine, 'max_batch': 8}
     process_video.process_videos(opt)
     ref = json.load(open(opt.output_json_file))
-    det = B200Detector(model, {'max_batch': 8})
+    det = make_detector(model)
     got = video.process_videos(det, str(folder), str(tmp_path / 'got.json'), frame_sample=3, batch_size=8,
                                json_confidence_threshold=0.01, recursive=True)
-    det.close()
+    if hasattr(det, 'close'):
+        det.close()
     assert got['detection_categories'] == ref['detection_categories']
     key = lambda im: im['file']
     assert sorted(got['images'], key=key) == sorted(ref['images'], key=key)
     assert sum(len(im['detections']) for im in got['images']) > 0
+
+
+@needs_ref
+def test_reference_process_videos_vs_batched_driver_cpu_oracle(tmp_path):
+    from oracle.pt_detector import OraclePTDetector
+    _process_videos_both_ways(tmp_path, 'oracle', lambda m: OraclePTDetector(m))
+
+
+@needs_ref
+@pytest.mark.gpu
+def test_reference_process_videos_vs_batched_driver_b200(tmp_path):
+    from megadetector_b200.detector import B200Detector
+    _process_videos_both_ways(tmp_path, 'b200', lambda m: B200Detector(m, {'max_batch': 8}))
