@@ -11,6 +11,7 @@
 #include <map>
 #include <memory>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/mdb200.h"
@@ -173,6 +174,9 @@ struct mdb_engine {
   // staging (double-buffered across chunks)
   uint8_t* d_src[2] = {nullptr, nullptr};
   size_t d_src_bytes[2] = {0, 0};
+  uint8_t* h_stage[2] = {nullptr, nullptr};  // page-locked staging for images handed in as PAGEABLE host memory
+  size_t h_stage_bytes[2] = {0, 0};
+  int stage_threads = 8;
   PreImage* h_pre[2] = {nullptr, nullptr};  // pinned
   PreImage* d_pre[2] = {nullptr, nullptr};
   NmsImageParams* h_nmsp[2] = {nullptr, nullptr};  // pinned
@@ -831,6 +835,56 @@ void enqueue_chunk(mdb_engine* e, Plan* P, const std::vector<ImgIn>& imgs, const
   // the previous user of this slot must be done with its staging buffers before we overwrite them
   MDB_CUDA(cudaEventSynchronize(e->ev_compute_done[slot]));
   ensure_src(e, slot, total + 64);
+  // Images in PAGEABLE host memory (what PIL / numpy callers hand in): CUDA would stage them through its own small bounce
+  // buffer on this thread (measured: 64 images cost 10 ms more than from page-locked memory).  They are copied into the
+  // slot's page-locked staging area by a few host threads instead, and uploaded from there by the copy engine.
+  std::vector<char> pageable(n, 0);
+  size_t stage_total = 0;
+  for (int i = 0; i < n; ++i) {
+    if (imgs[i].on_device) continue;
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, imgs[i].ptr) != cudaSuccess) { cudaGetLastError(); at.type = cudaMemoryTypeUnregistered; }
+    if (at.type == cudaMemoryTypeUnregistered) { pageable[i] = 1; stage_total += static_cast<size_t>(imgs[i].h) * imgs[i].w * 3; }
+  }
+  if (stage_total > 0) {
+    if (e->h_stage_bytes[slot] < total) {
+      if (e->h_stage[slot]) MDB_CUDA(cudaFreeHost(e->h_stage[slot]));
+      e->h_stage[slot] = nullptr; e->h_stage_bytes[slot] = 0;
+      const size_t want = total + total / 4 + 4096;
+      MDB_CUDA(cudaHostAlloc(&e->h_stage[slot], want, cudaHostAllocDefault));
+      e->h_stage_bytes[slot] = want;
+    }
+    // rows of all pageable images, dealt to the threads in contiguous byte ranges
+    const int T = std::max(1, std::min<int>(e->stage_threads, static_cast<int>(stage_total >> 20) + 1));
+    auto copy_range = [&](size_t lo, size_t hi) {  // byte range of the concatenation of the pageable images
+      size_t pos = 0;
+      for (int i = 0; i < n && pos < hi; ++i) {
+        if (!pageable[i]) continue;
+        const size_t row = static_cast<size_t>(imgs[i].w) * 3, sz = row * imgs[i].h;
+        if (pos + sz > lo) {
+          const size_t a = std::max(lo, pos) - pos, b = std::min(hi, pos + sz) - pos;
+          uint8_t* dst = e->h_stage[slot] + offs[i];
+          if (imgs[i].stride == static_cast<long long>(row)) {
+            memcpy(dst + a, imgs[i].ptr + a, b - a);
+          } else {
+            for (size_t r = a / row; r * row < b; ++r) {
+              const size_t c0 = std::max(a, r * row) - r * row, c1 = std::min(b, (r + 1) * row) - r * row;
+              memcpy(dst + r * row + c0, imgs[i].ptr + static_cast<size_t>(imgs[i].stride) * r + c0, c1 - c0);
+            }
+          }
+        }
+        pos += sz;
+      }
+    };
+    if (T == 1) {
+      copy_range(0, stage_total);
+    } else {
+      std::vector<std::thread> th;
+      const size_t per = (stage_total + T - 1) / T;
+      for (int t = 0; t < T; ++t) th.emplace_back(copy_range, std::min(stage_total, per * t), std::min(stage_total, per * (t + 1)));
+      for (auto& x : th) x.join();
+    }
+  }
   float max_scale = 1.0f;
   for (int i = 0; i < n; ++i) {
     const ImgIn& im = imgs[i];
@@ -838,6 +892,8 @@ void enqueue_chunk(mdb_engine* e, Plan* P, const std::vector<ImgIn>& imgs, const
     const size_t row = static_cast<size_t>(im.w) * 3;
     if (im.on_device) {
       d = const_cast<uint8_t*>(im.ptr);  // decoded by nvJPEG on the copy stream, ordered before ev_copy_done below
+    } else if (pageable[i]) {
+      MDB_CUDA(cudaMemcpyAsync(d, e->h_stage[slot] + offs[i], row * im.h, cudaMemcpyHostToDevice, e->st_copy));
     } else if (im.stride == static_cast<long long>(row)) {
       MDB_CUDA(cudaMemcpyAsync(d, im.ptr, row * im.h, cudaMemcpyHostToDevice, e->st_copy));
     } else {
@@ -1153,6 +1209,7 @@ int mdb_create(mdb_engine** out, const mdb_config* cfg) {
     nms_init_device();
     if (const char* mp = getenv("MDB_MAX_PLANS")) e->max_plans = std::max(1, atoi(mp));
     if (const char* et = getenv("MDB_EDGE_TAPER")) e->edge_taper = et[0] == '1';
+    if (const char* stg = getenv("MDB_STAGE_THREADS")) e->stage_threads = std::max(0, atoi(stg));
     const char* ng = getenv("MDB_NO_GRAPHS");
     e->use_graphs = !(ng && ng[0] == '1');
   } catch (const CudaError& ex) {
@@ -1172,6 +1229,7 @@ void mdb_destroy(mdb_engine* e) {
   for (auto& kv : e->weights) { cudaFree(kv.second.w); cudaFree(kv.second.b); }
   for (auto& kv : e->tables) { cudaFree(kv.second.ofs); cudaFree(kv.second.coef); cudaFree(kv.second.si); cudaFree(kv.second.alpha); }
   for (int i = 0; i < 2; ++i) {
+    if (e->h_stage[i]) cudaFreeHost(e->h_stage[i]);
     if (e->d_src[i]) cudaFree(e->d_src[i]);
     if (e->h_pre[i]) cudaFreeHost(e->h_pre[i]);
     if (e->d_pre[i]) cudaFree(e->d_pre[i]);

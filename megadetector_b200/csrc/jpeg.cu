@@ -264,7 +264,7 @@ int jpeg_decode_batch(JpegDecoder* d, const uint8_t* const* jpeg, const size_t* 
     backend = 2;
     static const int n_threads = [] {
       const char* e = getenv("MDB_JPEG_THREADS");
-      int t = e ? atoi(e) : 8;
+      int t = e ? atoi(e) : 16;
       return t < 1 ? 1 : (t > 32 ? 32 : t);
     }();
     const int T = std::min(n_threads, m);
