@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_config_struct_layout_matches_header():
     assert C.sizeof(_capi.MdbArch) == 4 * (6 + 5 + 1 + 1) + 4 * 24
-    assert C.sizeof(_capi.MdbConfig) == 4 * 9 + C.sizeof(_capi.MdbArch)
+    assert C.sizeof(_capi.MdbConfig) == 4 * 11 + C.sizeof(_capi.MdbArch)  # + compat_mode, use_ceil_for_resize
 
 
 @pytest.mark.parametrize('hw', [(1080, 1920), (450, 600), (450, 800), (600, 800), (1281, 1919), (333, 77), (64, 64),

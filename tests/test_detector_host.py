@@ -54,6 +54,32 @@ def test_api_misuse_raises_like_the_reference(pre):
 
 def test_unsupported_modes_fail_loudly():
     with pytest.raises(NotImplementedError):
-        B200Detector('synthetic://tiny', {'compatibility_mode': 'modern', 'preprocess_only': True})
-    with pytest.raises(NotImplementedError):
         B200Detector('synthetic://tiny', {'force_cpu': True})
+
+
+@pytest.mark.parametrize('hw', [(1080, 1920), (450, 600), (2160, 3840)])
+def test_modern_mode_producer_preprocessing_matches_the_oracle(hw):
+    """Non-classic compatibility mode on a producer worker (pytorch_detector.py:1036-1101): cv2 INTER_AREA / INTER_LINEAR
+    pre-resize + pad, with the reference's dict keys (img_original = the PRE-RESIZED image, scaling_shape = the original)."""
+    pre = B200Detector('synthetic://tiny?seed=0', {'preprocess_only': True, 'compatibility_mode': 'modern'})
+    assert not pre.classic
+    rng = np.random.default_rng(hw[1])
+    img = rng.integers(0, 256, (hw[0], hw[1], 3), dtype=np.uint8)
+    d = pre.preprocess_image(img, image_id='m.jpg')
+    want = olb.preprocess_modern(img, 1280, 64)
+    assert np.array_equal(d['img_processed'], want['img_processed'])
+    assert np.array_equal(d['img_original'], want['img_original'])
+    assert d['scaling_shape'] == img.shape and tuple(d['letterbox_pad']) == want['letterbox_pad']
+    assert tuple(d['target_shape']) == tuple(want['target_shape'])
+
+
+def test_format_detections_round_vs_truncate():
+    """pytorch_detector.py:1392-1397: classic truncates (ct_utils.truncate_float), every other mode uses Python round()."""
+    from megadetector_b200.detector import format_detections
+    det = np.array([[100.0, 50.0, 301.0, 250.0, 0.98765, 0.0], [0.0, 0.0, 7.0, 9.0, 0.1235, 2.0]], np.float32)
+    c, _ = format_detections(det, 2, 1080, 1920, classic=True)
+    m, _ = format_detections(det, 2, 1080, 1920, classic=False)
+    assert [x['conf'] for x in c] == [0.123, 0.987] and [x['conf'] for x in m] == [round(float(np.float32(0.1235)), 3), 0.988]
+    x_min = (np.float32(100.0) + np.float32(301.0)) / np.float32(2) / np.float32(1920) - (np.float32(201.0) / np.float32(1920)) / 2.0
+    assert c[1]['bbox'][0] == np.floor(float(x_min) * 1e4) / 1e4 and m[1]['bbox'][0] == round(float(x_min), 4)
+    assert c[0]['category'] == '3' and m[1]['category'] == '1'

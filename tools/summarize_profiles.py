@@ -8,7 +8,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OUT = os.path.join(ROOT, 'profiles')
 GO = os.path.join(ROOT, 'gpurun_out')
-TAG = sys.argv[1] if len(sys.argv) > 1 else 'r01_final'
+TAG = sys.argv[1] if len(sys.argv) > 1 else 'r02'
 
 
 def read_ncu_csv(path):
@@ -21,8 +21,8 @@ def read_ncu_csv(path):
 
 
 def short(name):
-    for key in ('conv_pair_kernel', 'conv_igemm_kernel', 'letterbox_s2d_kernel', 'nms_image_kernel', 'decode_kernel',
-                'upsample2x_kernel', 'sppf_pool_kernel'):
+    for key in ('conv_pair_kernel', 'letterbox_s2d_kernel', 'nms_image_kernel', 'decode_kernel', 'upsample2x_kernel',
+                'sppf_plane_kernel', 'sppf_pool_kernel', 'tta_scale_s2d_kernel', 'cand_from_pred_kernel', 'rotate_rgb_kernel'):
         if key in name:
             return key
     return name.split('(')[0][-60:]
