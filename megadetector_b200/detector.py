@@ -225,27 +225,23 @@ class B200Detector:
     def generate_detections_one_batch(self, img_original, image_id=None, detection_threshold=0.00001, image_size=None,
                                       augment=False, verbose=False):
         """pytorch_detector.py:1124-1252; returns a list of result dicts aligned with the inputs."""
+        # API misuse raises the reference's ValueErrors with the reference's messages (pytorch_detector.py:1156-1182)
         if not isinstance(img_original, list):
             raise ValueError('img_original must be a list for batch processing')
         if len(img_original) == 0:
             return []
         dict_mode = isinstance(img_original[0], dict)
-        if dict_mode:
-            for i, img in enumerate(img_original):
-                if not isinstance(img, dict):
-                    raise ValueError(f'Mixed input types in batch: item {i} is not a dict, but item 0 is a dict')
-        else:
-            if image_id is None:
-                raise ValueError('image_id must be a list when img_original contains PIL/numpy images')
+        if not dict_mode:
             if not isinstance(image_id, list):
-                raise ValueError('image_id must be a list for batch processing')
+                raise ValueError('image_id must be a list when img_original contains PIL/numpy images' if image_id is None
+                                 else 'image_id must be a list for batch processing')
             if len(image_id) != len(img_original):
                 raise ValueError('Length mismatch: img_original has {} items, image_id has {} items'.format(
                     len(img_original), len(image_id)))
-            for i_img, img in enumerate(img_original):
-                if isinstance(img, dict):
-                    raise ValueError('Mixed input types in batch: item {} is a dict, but item 0 is not a dict'.format(
-                        i_img))
+        for i, img in enumerate(img_original):
+            if isinstance(img, dict) != dict_mode:
+                raise ValueError('Mixed input types in batch: item {} is {} a dict, but item 0 is {} a dict'.format(
+                    i, *(('not', '') if dict_mode else ('', 'not'))).replace('is  a', 'is a'))
         if self.engine is None:
             raise RuntimeError('this B200Detector was created with preprocess_only; it cannot run inference')
         if detection_threshold is None:
