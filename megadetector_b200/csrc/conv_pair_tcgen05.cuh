@@ -56,6 +56,11 @@ constexpr bool kProbes = false;
 #define MDB_EPI_WARPS 16
 #endif
 constexpr int kPairEpiWarps = MDB_EPI_WARPS;  // a multiple of four: each TMEM lane quadrant gets kPairEpiWarps / 4
+#ifndef MDB_EPI_CW
+#define MDB_EPI_CW 16
+#endif
+constexpr int kCW = MDB_EPI_CW;  // accumulator columns an epilogue warp handles per step (16 or 8)
+static_assert(kCW == 16 || kCW == 8, "epilogue chunk width must be 16 or 8");
 constexpr int kPairThreads = 64 + 32 * kPairEpiWarps;
 constexpr int kPairMaxStages = 12;
 constexpr int kPairMaxCout = 1280;  // padded output channels per layer (bias staging in shared memory)
@@ -577,7 +582,7 @@ conv_pair_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
     const uint32_t row = quad * 32u + lane;
     const int ty = static_cast<int>(row) / p.tw;
     const int tx = static_cast<int>(row) - ty * p.tw;
-    const int nchunks = p.BN >> 4;
+    const int nchunks = p.BN / kCW;
     const uint32_t acc_empty_remote = mapa_rank(acc_empty0, 0);
     uint32_t tcount = 0;
     long long e_wait = 0, e_proc = 0;
@@ -600,17 +605,14 @@ conv_pair_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
       const long long te1 = kTimers ? clock64() : 0;
       const uint32_t taddr = tmem_base + ((quad * 32u) << 16) + acc * acc_stride;
 
-      // ---- fast path: half output, 32-byte aligned row segments, every chunk full (all but the Detect heads)
+      // ---- fast path: half output, aligned row segments, every chunk full (all but the Detect heads)
       __half* const orow = reinterpret_cast<__half*>(p.out) + pix * p.out_pix_stride + p.out_c_off + n0;
       const __half* const rrow = p.res != nullptr ? p.res + pix * p.res_pix_stride + p.res_c_off + n0 : nullptr;
-      auto process_fast = [&](const uint32_t (&vv)[16], int jj) {
-        if (!valid || (kProbes && p.probe & 4)) return;
-        uint4 r0 = make_uint4(0, 0, 0, 0), r1 = make_uint4(0, 0, 0, 0);
-        if (rrow != nullptr && !(kProbes && (p.probe & 8))) ldg256(rrow + jj * 16, r0, r1);
-        float f[16];
-        const float4* b4 = reinterpret_cast<const float4*>(bs + jj * 16);
+      // bias + SiLU + residual of one chunk of kCW columns, fp32, in registers
+      auto math = [&](const uint32_t (&vv)[kCW], float (&f)[kCW], int jj, const uint4& r0, const uint4& r1, bool have_res) {
+        const float4* b4 = reinterpret_cast<const float4*>(bs + jj * kCW);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < kCW / 4; ++q) {
           const float4 bb = b4[q];
           const F2 lo = add2(F2{__uint_as_float(vv[4 * q + 0]), __uint_as_float(vv[4 * q + 1])}, F2{bb.x, bb.y});
           const F2 hi = add2(F2{__uint_as_float(vv[4 * q + 2]), __uint_as_float(vv[4 * q + 3])}, F2{bb.z, bb.w});
@@ -618,129 +620,118 @@ conv_pair_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
         }
         if (p.act && !(kProbes && p.probe & 16)) {
 #pragma unroll
-          for (int e = 0; e < 16; e += 4) silu4(f[e], f[e + 1], f[e + 2], f[e + 3]);
+          for (int e = 0; e < kCW; e += 4) silu4(f[e], f[e + 1], f[e + 2], f[e + 3]);
         }
-        if (rrow != nullptr) {
+        if (have_res) {
           const __half2* h0 = reinterpret_cast<const __half2*>(&r0);
           const __half2* h1 = reinterpret_cast<const __half2*>(&r1);
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const float2 a = __half22float2(h0[e]);
-            const float2 b = __half22float2(h1[e]);
             const F2 s0 = add2(F2{f[2 * e], f[2 * e + 1]}, F2{a.x, a.y});
-            const F2 s1 = add2(F2{f[8 + 2 * e], f[8 + 2 * e + 1]}, F2{b.x, b.y});
-            f[2 * e] = s0.x; f[2 * e + 1] = s0.y; f[8 + 2 * e] = s1.x; f[8 + 2 * e + 1] = s1.y;
+            f[2 * e] = s0.x; f[2 * e + 1] = s0.y;
+            if (kCW == 16) {
+              const float2 b = __half22float2(h1[e]);
+              const F2 s1 = add2(F2{f[(8 + 2 * e) % kCW], f[(8 + 2 * e + 1) % kCW]}, F2{b.x, b.y});
+              f[(8 + 2 * e) % kCW] = s1.x; f[(8 + 2 * e + 1) % kCW] = s1.y;
+            }
           }
         }
-        uint4 o0, o1;
+      };
+      auto pack = [&](const float (&f)[kCW], uint4& o0, uint4& o1) {
         __half2* q0 = reinterpret_cast<__half2*>(&o0);
         __half2* q1 = reinterpret_cast<__half2*>(&o1);
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           q0[e] = __floats2half2_rn(f[2 * e], f[2 * e + 1]);
-          q1[e] = __floats2half2_rn(f[8 + 2 * e], f[8 + 2 * e + 1]);
+          if (kCW == 16) q1[e] = __floats2half2_rn(f[(8 + 2 * e) % kCW], f[(8 + 2 * e + 1) % kCW]);
         }
+      };
+      auto process_fast = [&](const uint32_t (&vv)[kCW], int jj) {
+        if (!valid || (kProbes && p.probe & 4)) return;
+        uint4 r0 = make_uint4(0, 0, 0, 0), r1 = make_uint4(0, 0, 0, 0);
+        const bool have_res = rrow != nullptr;
+        if (have_res && !(kProbes && (p.probe & 8))) {
+          if (kCW == 16) ldg256(rrow + jj * kCW, r0, r1);
+          else r0 = *reinterpret_cast<const uint4*>(rrow + jj * kCW);
+        }
+        float f[kCW];
+        math(vv, f, jj, r0, r1, have_res);
+        uint4 o0, o1;
+        pack(f, o0, o1);
         if (kProbes && p.probe & 8) {
-          if (o0.x == 0x7fff7fffu && o1.w == 0x7fff7fffu) stg256(orow + jj * 16, o0, o1);  // keeps the math alive, never true
+          if (o0.x == 0x7fff7fffu && o0.w == 0x7fff7fffu) *reinterpret_cast<uint4*>(orow + jj * kCW) = o0;  // keeps the math alive, never true
+        } else if (kCW == 16) {
+          stg256(orow + jj * kCW, o0, o1);
         } else {
-          stg256(orow + jj * 16, o0, o1);
+          *reinterpret_cast<uint4*>(orow + jj * kCW) = o0;
         }
       };
       // ---- general path: fp32 outputs, partial chunks, unaligned views
-      auto process = [&](const uint32_t (&vv)[16], int jj) {
-        const int col0 = n0 + jj * 16;
+      auto process = [&](const uint32_t (&vv)[kCW], int jj) {
+        const int col0 = n0 + jj * kCW;
         if (!(valid && col0 < p.Cout) || (kProbes && p.probe & 4)) return;
         uint4 r0 = make_uint4(0, 0, 0, 0), r1 = make_uint4(0, 0, 0, 0);
         if (p.res != nullptr) {
           const __half* rp = p.res + pix * p.res_pix_stride + p.res_c_off + col0;
           r0 = *reinterpret_cast<const uint4*>(rp);
-          r1 = *(reinterpret_cast<const uint4*>(rp) + 1);
+          if (kCW == 16) r1 = *(reinterpret_cast<const uint4*>(rp) + 1);
         }
-        float f[16];
-        const float4* b4 = reinterpret_cast<const float4*>(bs + jj * 16);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float4 bb = b4[q];
-          const F2 lo = add2(F2{__uint_as_float(vv[4 * q + 0]), __uint_as_float(vv[4 * q + 1])}, F2{bb.x, bb.y});
-          const F2 hi = add2(F2{__uint_as_float(vv[4 * q + 2]), __uint_as_float(vv[4 * q + 3])}, F2{bb.z, bb.w});
-          f[4 * q + 0] = lo.x; f[4 * q + 1] = lo.y; f[4 * q + 2] = hi.x; f[4 * q + 3] = hi.y;
-        }
-        if (p.act) {
-#pragma unroll
-          for (int e = 0; e < 16; e += 4) silu4(f[e], f[e + 1], f[e + 2], f[e + 3]);
-        }
-        if (p.res != nullptr) {
-          const __half2* h0 = reinterpret_cast<const __half2*>(&r0);
-          const __half2* h1 = reinterpret_cast<const __half2*>(&r1);
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float2 a = __half22float2(h0[e]);
-            const float2 b = __half22float2(h1[e]);
-            const F2 s0 = add2(F2{f[2 * e], f[2 * e + 1]}, F2{a.x, a.y});
-            const F2 s1 = add2(F2{f[8 + 2 * e], f[8 + 2 * e + 1]}, F2{b.x, b.y});
-            f[2 * e] = s0.x; f[2 * e + 1] = s0.y; f[8 + 2 * e] = s1.x; f[8 + 2 * e + 1] = s1.y;
-          }
-        }
+        float f[kCW];
+        math(vv, f, jj, r0, r1, p.res != nullptr);
         if (p.out_fp32) {
           float* op = reinterpret_cast<float*>(p.out) + pix * p.out_pix_stride + p.out_c_off + col0;
-          if (col0 + 16 <= p.Cout) {
+          if (col0 + kCW <= p.Cout) {
 #pragma unroll
-            for (int e = 0; e < 4; ++e)
+            for (int e = 0; e < kCW / 4; ++e)
               reinterpret_cast<float4*>(op)[e] = make_float4(f[4 * e], f[4 * e + 1], f[4 * e + 2], f[4 * e + 3]);
           } else {
 #pragma unroll
-            for (int e = 0; e < 16; ++e)
+            for (int e = 0; e < kCW; ++e)
               if (col0 + e < p.Cout) op[e] = f[e];
           }
         } else {
           __half* op = reinterpret_cast<__half*>(p.out) + pix * p.out_pix_stride + p.out_c_off + col0;
-          if (col0 + 16 <= p.Cout) {
+          if (col0 + kCW <= p.Cout) {
             uint4 o0, o1;
-            __half2* q0 = reinterpret_cast<__half2*>(&o0);
-            __half2* q1 = reinterpret_cast<__half2*>(&o1);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              q0[e] = __floats2half2_rn(f[2 * e], f[2 * e + 1]);
-              q1[e] = __floats2half2_rn(f[8 + 2 * e], f[8 + 2 * e + 1]);
-            }
+            pack(f, o0, o1);
             reinterpret_cast<uint4*>(op)[0] = o0;
-            reinterpret_cast<uint4*>(op)[1] = o1;
+            if (kCW == 16) reinterpret_cast<uint4*>(op)[1] = o1;
           } else {
 #pragma unroll
-            for (int e = 0; e < 16; ++e)
+            for (int e = 0; e < kCW; ++e)
               if (col0 + e < p.Cout) op[e] = __float2half_rn(f[e]);
           }
         }
       };
       // TMEM loads run one chunk ahead of the math (two register buffers, statically indexed)
-      uint32_t va[16], vb[16];
+      uint32_t va[kCW], vb[kCW];
       // When the chunk count is not a multiple of the parts (10 chunks at BN = 160, 5 at BN = 80), some warps of a
       // quadrant get one chunk more than the others.  Rotating the assignment from tile to tile by that remainder
       // evens the work out over consecutive tiles; the accumulator ring (2-4 stages) lets the early warps run ahead.
-      static_assert(kParts == 4, "the rotation below assumes four parts");
-      int j = static_cast<int>((part + tcount * static_cast<uint32_t>(nchunks & 3)) & 3u);
-      if (j < nchunks) tmem_ld16(taddr + static_cast<uint32_t>(j * 16), va);
+      int j = static_cast<int>((part + tcount * static_cast<uint32_t>(nchunks % kParts)) % static_cast<uint32_t>(kParts));
+      if (j < nchunks) tmem_ldN(taddr + static_cast<uint32_t>(j * kCW), va);
       if (p.fast) {
         while (j < nchunks) {
           tmem_ld_wait();
-          if (j + kParts < nchunks) tmem_ld16(taddr + static_cast<uint32_t>((j + kParts) * 16), vb);
+          if (j + kParts < nchunks) tmem_ldN(taddr + static_cast<uint32_t>((j + kParts) * kCW), vb);
           process_fast(va, j);
           j += kParts;
           if (j >= nchunks) break;
           tmem_ld_wait();
-          if (j + kParts < nchunks) tmem_ld16(taddr + static_cast<uint32_t>((j + kParts) * 16), va);
+          if (j + kParts < nchunks) tmem_ldN(taddr + static_cast<uint32_t>((j + kParts) * kCW), va);
           process_fast(vb, j);
           j += kParts;
         }
       } else {
         while (j < nchunks) {
           tmem_ld_wait();
-          if (j + kParts < nchunks) tmem_ld16(taddr + static_cast<uint32_t>((j + kParts) * 16), vb);
+          if (j + kParts < nchunks) tmem_ldN(taddr + static_cast<uint32_t>((j + kParts) * kCW), vb);
           process(va, j);
           j += kParts;
           if (j >= nchunks) break;
           tmem_ld_wait();
-          if (j + kParts < nchunks) tmem_ld16(taddr + static_cast<uint32_t>((j + kParts) * 16), va);
+          if (j + kParts < nchunks) tmem_ldN(taddr + static_cast<uint32_t>((j + kParts) * kCW), va);
           process(vb, j);
           j += kParts;
         }
