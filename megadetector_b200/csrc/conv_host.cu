@@ -100,6 +100,13 @@ ConvOp* conv_build(const ConvDesc& d, int num_sms) {
     q.taps = d.k * kw;
     q.chunks = d.cin_pad / kc;
     q.total_chunks = q.taps * q.chunks;
+    {
+      // channels beyond in.C are TMA zero fill meeting zero weights: the MMA steps over them are skipped (exact: they add 0).
+      // C_in = 80 runs 5 instead of 8 steps per tap, 160: 10 of 12, 480: 30 of 32, the stem's 48: 3 of 4.  MDB_CONV_TAILK=0: off.
+      static const bool tailk = !(getenv("MDB_CONV_TAILK") && getenv("MDB_CONV_TAILK")[0] == '0');
+      const int rest = in.C - (q.chunks - 1) * kc;
+      q.tail_k = tailk ? std::min(kc / 16, std::max(1, (rest + 15) / 16)) : kc / 16;
+    }
     MDB_REQUIRE(q.taps <= 9, "at most 9 filter taps");
     MDB_REQUIRE(d.cout_pad <= kPairMaxCout, "at most 1280 (padded) output channels");
     if (op->flat) {

@@ -80,6 +80,7 @@ struct PairParams {
   int chunks;        // 64-channel chunks per tap
   int total_chunks;  // taps * chunks
   int cps;           // chunks per pipeline stage
+  int tail_k;        // 16-channel MMA steps the LAST chunk of a tap needs (1..4): the zero-filled rest of a padded chunk is skipped
   int stages;
   // per filter tap: (dx + 8) | (dy + 8) << 8 | parity_map << 16 -- input offset of the tap relative to the output tile
   // origin (stride 2: in the coordinates of the parity view the tap reads).  One spare entry: the producer reads one ahead.
@@ -521,6 +522,7 @@ conv_pair_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
           for (int c = 0; c < p.chunks; ++c) {
             mbar_wait_addr_timed(a_full0 + 8u * as, aph, w_full);
             const uint32_t abase = smem_base + as * a_stage_bytes;
+            const int nk = c == p.chunks - 1 ? p.tail_k : KC / 16;
 #pragma unroll 1
             for (int kh = 0; kh < 3; ++kh) {
               mbar_wait_addr_timed(full0 + 8u * s, ph, w_full);
@@ -534,7 +536,7 @@ conv_pair_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
                   if (mmas) {
 #pragma unroll
                     for (int k = 0; k < KC / 16; ++k)
-                      umma2_f16_lo(d_tmem, a_lo + 2u * k, b_lo + 2u * k, desc_hi, p.idesc, (c | kh | kw | k) != 0 ? 1u : 0u);
+                      if (k < nk) umma2_f16_lo(d_tmem, a_lo + 2u * k, b_lo + 2u * k, desc_hi, p.idesc, (c | kh | kw | k) != 0 ? 1u : 0u);
                   }
                 }
                 umma2_commit_mc_addr(empty0 + 8u * s);
@@ -545,22 +547,27 @@ conv_pair_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
             if (++as == static_cast<uint32_t>(p.a_stages)) { as = 0; aph ^= 1u; }
           }
         } else {
+          int cc = 0;  // chunk index within the tap at the start of the stage
           for (int q0 = 0; q0 < p.total_chunks; q0 += p.cps) {
             const int nch = min(p.cps, p.total_chunks - q0);
             mbar_wait_addr_timed(full0 + 8u * s, ph, w_full);
             tc_fence_after();
             uint32_t a_lo = desc_lo | ((smem_base + s * stage_bytes) >> 4);
             if (el) {
+              int c2 = cc;
               for (int j = 0; j < nch; ++j, a_lo += chunk_bytes >> 4) {
+                const int nk = c2 == p.chunks - 1 ? p.tail_k : KC / 16;
+                if (++c2 == p.chunks) c2 = 0;
                 if (mmas) {
 #pragma unroll
                   for (int k = 0; k < KC / 16; ++k)
-                    umma2_f16_lo(d_tmem, a_lo + 2u * k, a_lo + (A_CHUNK >> 4) + 2u * k, desc_hi, p.idesc,
-                                 (q0 | j | k) != 0 ? 1u : 0u);
+                    if (k < nk) umma2_f16_lo(d_tmem, a_lo + 2u * k, a_lo + (A_CHUNK >> 4) + 2u * k, desc_hi, p.idesc,
+                                             (q0 | j | k) != 0 ? 1u : 0u);
                 }
               }
               umma2_commit_mc_addr(empty0 + 8u * s);
             }
+            cc = (cc + nch) % p.chunks;
             if (++s == S) { s = 0; ph ^= 1u; }
           }
         }
