@@ -80,3 +80,100 @@ def test_two_gpus_give_the_single_gpu_records(tmp_path):
     one, _ = run_batch.run_sharded(spec, files, 1, batch_size=4)
     two, _ = run_batch.run_sharded(spec, files, 2, batch_size=4)
     assert one == two and len(two) == 10 and all('detections' in r for r in two)
+
+
+class FlakyDetector(FakeDetector):
+    """Dies on the batch that contains the file named in MDB_TEST_FAIL_ON (a crash in the middle of a job)."""
+
+    def generate_detections_one_batch(self, images, ids, detection_threshold=1e-5):
+        bad = os.environ.get('MDB_TEST_FAIL_ON', '')
+        if bad and any(f.endswith(bad) for f in ids):
+            raise RuntimeError('simulated crash')
+        return super().generate_detections_one_batch(images, ids, detection_threshold)
+
+
+def test_checkpoint_and_resume_use_the_reference_format(tmp_path, monkeypatch):
+    """run_detector_batch.py:1465-1520: {"checkpoint": [records]}; a job that dies resumes from it and ends with the records of
+    an uninterrupted run; nothing is processed twice."""
+    _make_images(str(tmp_path / 'in'), 11)
+    found = [os.path.abspath(f) for f in run_batch.find_images(str(tmp_path / 'in'))]
+    want, _ = run_batch.run_sharded('m.pt', found, 1, batch_size=2, detector_factory='test_run_batch:FakeDetector')
+    ckpt = str(tmp_path / 'md_checkpoint_test.json')
+    monkeypatch.setenv('MDB_TEST_FAIL_ON', 'img008.jpg')  # the last batch of worker 1
+    with pytest.raises(RuntimeError, match='simulated crash'):
+        run_batch.run_sharded('m.pt', found, 2, batch_size=2, detector_factory='test_run_batch:FlakyDetector',
+                              checkpoint_path=ckpt, checkpoint_frequency=3)
+    assert not os.path.exists(ckpt + '_tmp')
+    data = json.load(open(ckpt))
+    assert set(data) == {'checkpoint'} and 0 < len(data['checkpoint']) < len(found)
+    assert all(os.path.isabs(r['file']) for r in data['checkpoint'])
+    monkeypatch.delenv('MDB_TEST_FAIL_ON')
+    restored = run_batch.load_checkpoint(ckpt)
+    got, _ = run_batch.run_sharded('m.pt', found, 2, batch_size=2, detector_factory='test_run_batch:FlakyDetector',
+                                   checkpoint_path=ckpt, checkpoint_frequency=3, results=restored)
+    assert got == want
+    # everything already in the checkpoint: no worker is started
+    again, times = run_batch.run_sharded('m.pt', found, 2, batch_size=2, detector_factory='no_such_module:X', results=got)
+    assert again == want and times == []
+    with pytest.raises(ValueError, match='missing "checkpoint" field'):
+        bad = tmp_path / 'bad.json'
+        bad.write_text('{"images": []}')
+        run_batch.load_checkpoint(str(bad))
+
+
+def test_checkpoints_interoperate_with_the_reference_driver(tmp_path):
+    ref_root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'baseline', '_ref')
+    if not os.path.isdir(os.path.join(ref_root, 'megadetector')):
+        pytest.skip('baseline/_ref is not installed (tools/install_reference.sh)')
+    import sys
+    for p in (ref_root, os.path.join(os.path.dirname(os.path.abspath(__file__)), 'stubs')):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    from megadetector.detection import run_detector_batch as ref
+    recs = [{'file': '/a/b.jpg', 'detections': [{'category': '1', 'conf': 0.5, 'bbox': [0.1, 0.2, 0.3, 0.4]}]},
+            {'file': '/a/c.jpg', 'failure': 'image access failure'}]
+    ours, theirs = str(tmp_path / 'ours.json'), str(tmp_path / 'theirs.json')
+    run_batch.write_checkpoint(ours, recs)
+    ref.write_checkpoint(theirs, recs)
+    assert ref.load_checkpoint(ours) == recs and run_batch.load_checkpoint(theirs) == recs
+    assert json.load(open(ours)) == json.load(open(theirs))
+
+
+def test_cli_checkpoint_flags(tmp_path, monkeypatch, capsys):
+    """--checkpoint_frequency / --checkpoint_path / --resume_from_checkpoint auto / overwrite guard / deletion at the end
+    (run_detector_batch.py:1983-2003, 2095-2118, 2179-2181)."""
+    _make_images(str(tmp_path / 'in'), 7)
+    out_dir = tmp_path / 'out'
+    out_dir.mkdir()
+    real = run_batch.run_sharded
+    monkeypatch.setattr(run_batch, 'run_sharded',
+                        lambda *a, **k: real(*a, detector_factory='test_run_batch:FakeDetector', **k))
+    found = [os.path.abspath(f) for f in run_batch.find_images(str(tmp_path / 'in'))]
+    first, _ = real('m.pt', found[:3], 1, batch_size=2, detector_factory='test_run_batch:FakeDetector')
+    run_batch.write_checkpoint(str(out_dir / 'md_checkpoint_20250101000000.json'), first)
+    with pytest.raises(AssertionError, match='already exists'):
+        run_batch.main(['m.pt', str(tmp_path / 'in'), str(out_dir / 'o.json'), '--recursive', '--checkpoint_frequency', '2',
+                        '--checkpoint_path', str(out_dir / 'md_checkpoint_20250101000000.json')])
+    rc = run_batch.main(['m.pt', str(tmp_path / 'in'), str(out_dir / 'o.json'), '--recursive', '--batch_size', '2',
+                         '--checkpoint_frequency', '2', '--resume_from_checkpoint', 'auto',
+                         '--checkpoint_path', str(out_dir / 'ck.json'), '--output_relative_filenames'])
+    assert rc == 0
+    text = capsys.readouterr().out
+    assert 'Restored 3 entries' in text and 'Bypassing 3 images' in text and 'Deleted checkpoint file' in text
+    assert not (out_dir / 'ck.json').exists()
+    d = json.load(open(out_dir / 'o.json'))
+    assert len(d['images']) == 8 and d['images'][0]['file'] == 'cam0/broken.jpg'
+    with pytest.raises(ValueError, match='no checkpoints found'):
+        run_batch.find_checkpoint(str(tmp_path / 'in'))
+
+
+def test_image_file_argument_forms(tmp_path):
+    files = _make_images(str(tmp_path), 4)
+    (tmp_path / 'l.json').write_text(json.dumps(files[:3]))
+    (tmp_path / 'l.txt').write_text('\n'.join(files[1:]) + '\n\n')
+    assert run_batch.resolve_image_list(str(tmp_path / 'l.json')) == files[:3]
+    assert run_batch.resolve_image_list(str(tmp_path / 'l.txt')) == files[1:]
+    assert run_batch.resolve_image_list(files[2]) == [files[2]]
+    assert len(run_batch.resolve_image_list(str(tmp_path))) == 5
+    with pytest.raises(ValueError):
+        run_batch.resolve_image_list(str(tmp_path / 'nothing.bin'))
