@@ -169,6 +169,7 @@ ConvOp* conv_build(const ConvDesc& d, int num_sms) {
       q.backoff_ns = (q.total_chunks * kc <= 1024) ? ns : 0;
     }
     q.halo = 0;
+    q.a_base_off = 0;
     q.a_stages = 0;
     {
       static const char* ep = getenv("MDB_CONV_PROBE");  // honoured by -DMDB_CONV_PROBES builds only
@@ -193,15 +194,21 @@ ConvOp* conv_build(const ConvDesc& d, int num_sms) {
       const double eff = static_cast<double>(Ho) * Wo / (static_cast<double>((Wo + 7) / 8 * 8) * ((Ho + 15) / 16 * 16));
       // measured (one filter row per weight stage): -26% time at 80 ch, -16% at 160, -9% at 320
       if (allow && d.k == 3 && kw == 3 && d.s == 1 && d.pad == 1 && pad_x == 1 && eff >= 0.85 && q.chunks >= halo_min_chunks) {
-        q.halo = 1;
-        q.a_stages = 2;
+        // MDB_CONV_HALO1=1: single-box halo (one 10-pixel-wide box per chunk instead of three 8-pixel ones); =2: the same with the
+        // descriptor's base-offset field filled
+        static const char* eh1 = getenv("MDB_CONV_HALO1");
+        const int h1 = eh1 ? atoi(eh1) : 0;
+        q.halo = h1 ? 2 : 1;
+        q.a_base_off = h1 == 2 ? 1 : 0;
+        static const char* eas = getenv("MDB_CONV_HALO_ASTAGES");
+        q.a_stages = eas ? std::max(2, std::min(kHaloMaxA, atoi(eas))) : (h1 ? 3 : 2);
         q.tw = kHaloTw;
         q.th = kHaloTh;
-        make_act_tmap(&op->tmA[0], in, kc, kHaloTw, kHaloRows, -1, -1);
+        make_act_tmap(&op->tmA[0], in, kc, h1 ? kHaloTw + 2 : kHaloTw, kHaloRows, -1, -1);
         for (int i = 0; i < 4; ++i) op->maps.a[i] = op->tmA[0];
         op->maps.b = op->tmB;
         const size_t budget = 227 * 1024 - 8192 - 1024;  // static: barriers + the bias vector; alignment slack
-        const size_t a_bytes = static_cast<size_t>(q.a_stages) * 3 * kHaloBox;
+        const size_t a_bytes = static_cast<size_t>(q.a_stages) * (h1 ? kHalo1Stage : 3 * kHaloBox);
         int stages = static_cast<int>(std::min<size_t>(kPairMaxStages, (budget - a_bytes) / (3 * b_chunk)));  // a stage = one filter row
         MDB_REQUIRE(stages >= 2, "not enough shared memory for the halo pipeline");
         q.stages = stages;
@@ -261,7 +268,23 @@ static void conv_launch_pair(ConvOp* op, int n_img, cudaStream_t st) {
     MDB_CUDA(cudaMemsetAsync(d_dbg, 0, sizeof(long long) * 16 * grid, st));
   }
   p.dbg = d_dbg;
-  conv_pair_kernel<64><<<grid, kPairThreads, op->smem, st>>>(op->maps, p);
+  static const bool pdl = getenv("MDB_CONV_PDL") && getenv("MDB_CONV_PDL")[0] == '1';
+  p.pdl = pdl ? 1 : 0;
+  if (pdl) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kPairThreads);
+    cfg.dynamicSmemBytes = op->smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    MDB_CUDA(cudaLaunchKernelEx(&cfg, conv_pair_kernel<64>, op->maps, p));
+  } else {
+    conv_pair_kernel<64><<<grid, kPairThreads, op->smem, st>>>(op->maps, p);
+  }
   MDB_CUDA(cudaGetLastError());
   if (debug) {
     std::vector<long long> h(static_cast<size_t>(16) * grid);

@@ -67,7 +67,13 @@ constexpr int kPairMaxCout = 1280;  // padded output channels per layer (bias st
 constexpr int kHaloRows = 18;                       // th + 2
 constexpr int kHaloTw = 8, kHaloTh = 16;
 constexpr uint32_t kHaloBox = kHaloRows * kHaloTw * 128;  // bytes of one {64 ch, 8 px, 18 rows} box
-constexpr int kHaloMaxA = 3;
+constexpr int kHaloMaxA = 4;
+// single-box halo (halo == 2): ONE {64 ch, 10 px, 18 rows} box per chunk serves all nine taps: the kw shift is a 128-byte
+// (one pixel) offset of the A descriptor's start address, the kh shift one 1280-byte image row; the eight MMA rows of a
+// core-matrix group are the eight pixels of one image row, the stride between groups (SBO) is the 1280-byte row pitch
+constexpr uint32_t kHalo1Pitch = (kHaloTw + 2) * 128;
+constexpr uint32_t kHalo1Box = kHaloRows * kHalo1Pitch;             // 23040 bytes
+constexpr uint32_t kHalo1Stage = (kHalo1Box + 1023u) & ~1023u;      // 23552
 
 struct PairParams {
   int n_img, H_out, W_out;
@@ -95,7 +101,10 @@ struct PairParams {
   int act;
   int wide;        // 1: every epilogue row segment is 32-byte aligned -> 256-bit global accesses
   int fast;        // 1: half output, wide, every 16-column chunk full -> the branch-free epilogue path
-  int halo;        // 1: 3x3/s1 row-halo main loop (tile 8 x 16; A fetched per kw shift, reused across kh)
+  int halo;        // 1: 3x3/s1 row-halo main loop (tile 8 x 16; A fetched per kw shift, reused across kh); 2: single-box halo
+  int pdl;         // launched with programmatic stream serialization: let the next kernel's CTAs start as SMs free up, and wait for
+                   // the previous kernel's results only after this CTA's own set-up (barriers, TMEM, bias)
+  int a_base_off;  // halo 2: fill the descriptor's base-offset field with (start address >> 7) & 7
   int a_stages;    // halo mode: number of A (3-box) buffers
   uint32_t idesc;  // M = 256
   long long* dbg;  // per-CTA cycle counters (MDB_CONV_DEBUG=1 in a -DMDB_CONV_TIMERS build), null otherwise
@@ -258,6 +267,21 @@ __device__ __forceinline__ void umma2_f16_lo(uint32_t tmem_d, uint32_t a_lo, uin
       "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// the same with separate high words for A and B (single-box halo: A has its own SBO)
+__device__ __forceinline__ void umma2_f16_lo2(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                              uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void umma2_commit_mc_addr(uint32_t bar_addr) {
   const uint16_t mask = 3;
   asm volatile(
@@ -383,6 +407,12 @@ conv_pair_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
+  if (p.pdl) {
+    // everything above touched only this layer's weights; activations (TMA loads, residual reads, output stores that may
+    // reuse a buffer the previous layer still reads) come after the previous kernel has completed
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+  }
 
   const uint32_t full0 = smem_u32(&full_bar[0]);
   const uint32_t empty0 = smem_u32(&empty_bar[0]);
@@ -410,7 +440,9 @@ conv_pair_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
       // ---- 3x3 / stride 1: per 64-channel chunk, three {64 ch, 8 px, 18 rows} boxes (one per kw shift) are
       // fetched once and serve all three kh taps (the kh shift is a 1024-byte offset in shared memory);
       // weights stream through their own ring, one filter row per stage.  A bytes per chunk: 55 KB instead of 147 KB.
-      const uint32_t a_stage_bytes = 3u * kHaloBox;
+      const bool single = p.halo == 2;
+      const uint32_t a_stage_bytes = single ? kHalo1Stage : 3u * kHaloBox;
+      const uint32_t a_tx = single ? kHalo1Box : 3u * kHaloBox;
       const uint32_t b_region = smem_base + static_cast<uint32_t>(p.a_stages) * a_stage_bytes;
       const uint32_t b_bytes = half_n * ROW_BYTES;
       uint32_t as = 0, aph = 0;
@@ -423,14 +455,18 @@ conv_pair_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
           if (kTimers) mbar_wait_addr_timed(a_empty0 + 8u * as, aph ^ 1u, w_empty);
           else mbar_wait_addr_backoff(a_empty0 + 8u * as, aph ^ 1u, bo);
           if (el) {
-            if (leader) mbar_arrive_expect_tx_addr(a_full0 + 8u * as, loads ? 2u * a_stage_bytes : 0u);
+            if (leader) mbar_arrive_expect_tx_addr(a_full0 + 8u * as, loads ? 2u * a_tx : 0u);
             else mbar_arrive_cluster_addr(a_full0_remote + 8u * as);
             const uint32_t abase = smem_base + as * a_stage_bytes;
             if (loads) {
+              if (single) {
+                tma2_load_4d_addr(&maps.a[0], a_full0_tma + 8u * as, abase, c * KC, ox0, oy0, img);
+              } else {
 #pragma unroll
-              for (int kw = 0; kw < 3; ++kw)
-                tma2_load_4d_addr(&maps.a[0], a_full0_tma + 8u * as, abase + static_cast<uint32_t>(kw) * kHaloBox, c * KC,
-                                  ox0 + kw, oy0, img);
+                for (int kw = 0; kw < 3; ++kw)
+                  tma2_load_4d_addr(&maps.a[0], a_full0_tma + 8u * as, abase + static_cast<uint32_t>(kw) * kHaloBox, c * KC,
+                                    ox0 + kw, oy0, img);
+              }
             }
           }
           if (++as == static_cast<uint32_t>(p.a_stages)) { as = 0; aph ^= 1u; }
@@ -517,7 +553,12 @@ conv_pair_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * acc_stride;
         if (p.halo) {
-          const uint32_t a_stage_bytes = 3u * kHaloBox;
+          const bool single = p.halo == 2;
+          const uint32_t a_stage_bytes = single ? kHalo1Stage : 3u * kHaloBox;
+          const uint32_t kw_step = single ? 128u : kHaloBox;
+          const uint32_t kh_step = single ? kHalo1Pitch : 1024u;
+          // A's high word: SBO = the byte distance between consecutive image rows of the box
+          const uint32_t a_hi0 = single ? ((desc_hi & ~0x3FFFu) | (kHalo1Pitch >> 4)) : desc_hi;
           const uint32_t b_region = smem_base + static_cast<uint32_t>(p.a_stages) * a_stage_bytes;
           for (int c = 0; c < p.chunks; ++c) {
             mbar_wait_addr_timed(a_full0 + 8u * as, aph, w_full);
@@ -531,12 +572,14 @@ conv_pair_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
 #pragma unroll
                 for (int kw = 0; kw < 3; ++kw) {
                   // rows of the tile for this tap: halo rows kh .. kh+15 of the kw-shifted box (8 px = 1024 B per row)
-                  const uint32_t a_lo = desc_lo | ((abase + static_cast<uint32_t>(kw) * kHaloBox + static_cast<uint32_t>(kh) * 1024u) >> 4);
+                  const uint32_t a_addr = abase + static_cast<uint32_t>(kw) * kw_step + static_cast<uint32_t>(kh) * kh_step;
+                  const uint32_t a_lo = desc_lo | (a_addr >> 4);
+                  const uint32_t a_hi = a_hi0 | (p.a_base_off ? ((a_addr >> 7) & 7u) << 17 : 0u);
                   const uint32_t b_lo = desc_lo | ((b_region + (s * 3u + static_cast<uint32_t>(kw)) * b_chunk) >> 4);
                   if (mmas) {
 #pragma unroll
                     for (int k = 0; k < KC / 16; ++k)
-                      if (k < nk) umma2_f16_lo(d_tmem, a_lo + 2u * k, b_lo + 2u * k, desc_hi, p.idesc, (c | kh | kw | k) != 0 ? 1u : 0u);
+                      if (k < nk) umma2_f16_lo2(d_tmem, a_lo + 2u * k, a_hi, b_lo + 2u * k, desc_hi, p.idesc, (c | kh | kw | k) != 0 ? 1u : 0u);
                   }
                 }
                 umma2_commit_mc_addr(empty0 + 8u * s);
