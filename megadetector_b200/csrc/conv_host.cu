@@ -169,7 +169,9 @@ ConvOp* conv_build(const ConvDesc& d, int num_sms) {
       q.backoff_ns = (q.total_chunks * kc <= 1024) ? ns : 0;
     }
     q.halo = 0;
-    q.a_base_off = 0;
+    q.n_boxes = 0; q.a_stage_bytes = 0; q.a_tx = 0;
+    for (int i = 0; i < 4; ++i) { q.box_off[i] = 0; q.box_map[i] = 0; q.box_dx[i] = 0; q.box_dy[i] = 0; }
+    for (int i = 0; i < 9; ++i) { q.tap_off[i] = 0; q.tap_sbo[i] = 0; }
     q.a_stages = 0;
     {
       static const char* ep = getenv("MDB_CONV_PROBE");  // honoured by -DMDB_CONV_PROBES builds only
@@ -185,30 +187,90 @@ ConvOp* conv_build(const ConvDesc& d, int num_sms) {
     }
     const size_t a_chunk = static_cast<size_t>(kTileM) * kc * 2;
     const size_t b_chunk = (static_cast<size_t>(q.BN / 2) * kc * 2 + 1023) & ~static_cast<size_t>(1023);
-    // 3x3 / stride-1 layers whose output tiles well with 8 x 16 blocks use the row-halo main loop
+    // 3x3 layers (stride 1 or 2) whose output tiles well with 8 x 16 blocks use the halo main loop
     {
       static const char* eh = getenv("MDB_CONV_HALO");
       const bool allow = !(eh && eh[0] == '0');
       static const char* ehm = getenv("MDB_CONV_HALO_MIN");
       const int halo_min_chunks = ehm ? atoi(ehm) : 2;
+      // MDB_CONV_HALO1=0: stride 1 fetches three 8-pixel boxes (one per kw shift) instead of one 10-pixel box
+      static const char* eh1 = getenv("MDB_CONV_HALO1");
+      const bool single = !(eh1 && eh1[0] == '0');
+      // MDB_CONV_HALO_S2=0: stride 2 keeps the per-tap main loop
+      static const char* eh2 = getenv("MDB_CONV_HALO_S2");
+      const bool allow_s2 = !(eh2 && eh2[0] == '0');
+      static const char* eas = getenv("MDB_CONV_HALO_ASTAGES");
       const double eff = static_cast<double>(Ho) * Wo / (static_cast<double>((Wo + 7) / 8 * 8) * ((Ho + 15) / 16 * 16));
-      // measured (one filter row per weight stage): -26% time at 80 ch, -16% at 160, -9% at 320
-      if (allow && d.k == 3 && kw == 3 && d.s == 1 && d.pad == 1 && pad_x == 1 && eff >= 0.85 && q.chunks >= halo_min_chunks) {
-        // MDB_CONV_HALO1=1: single-box halo (one 10-pixel-wide box per chunk instead of three 8-pixel ones); =2: the same with the
-        // descriptor's base-offset field filled
-        static const char* eh1 = getenv("MDB_CONV_HALO1");
-        const int h1 = eh1 ? atoi(eh1) : 0;
-        q.halo = h1 ? 2 : 1;
-        q.a_base_off = h1 == 2 ? 1 : 0;
-        static const char* eas = getenv("MDB_CONV_HALO_ASTAGES");
-        q.a_stages = eas ? std::max(2, std::min(kHaloMaxA, atoi(eas))) : (h1 ? 3 : 2);
+      const bool shape_ok = allow && d.k == 3 && kw == 3 && d.pad == 1 && pad_x == 1 && eff >= 0.85 && q.chunks >= halo_min_chunks;
+      const size_t budget = 227 * 1024 - 8192 - 1024;  // static: barriers + the bias vector; alignment slack
+      auto align1k = [](uint32_t v) { return (v + 1023u) & ~1023u; };
+      bool use = false;
+      if (shape_ok && d.s == 1) {
+        // measured (one filter row per weight stage): -26% time at 80 ch, -16% at 160, -9% at 320; single box: another -2..-6 %
+        use = true;
+        q.a_stages = eas ? std::max(2, std::min(kHaloMaxA, atoi(eas))) : (single ? 3 : 2);
+        if (single) {
+          make_act_tmap(&op->tmA[0], in, kc, kHaloTw + 2, kHaloRows, -1, -1);
+          q.n_boxes = 1;
+          q.box_off[0] = 0; q.box_map[0] = 0; q.box_dx[0] = -1; q.box_dy[0] = -1;
+          q.a_tx = kHalo1Box;
+          q.a_stage_bytes = kHalo1Stage;
+          for (int t = 0; t < 9; ++t) {
+            q.tap_off[t] = static_cast<uint32_t>(t % 3) * 128u + static_cast<uint32_t>(t / 3) * kHalo1Pitch;
+            q.tap_sbo[t] = kHalo1Pitch >> 4;
+          }
+        } else {
+          make_act_tmap(&op->tmA[0], in, kc, kHaloTw, kHaloRows, -1, -1);
+          q.n_boxes = 3;
+          for (int b = 0; b < 3; ++b) {
+            q.box_off[b] = static_cast<uint32_t>(b) * kHaloBox; q.box_map[b] = 0; q.box_dx[b] = b - 1; q.box_dy[b] = -1;
+          }
+          q.a_tx = 3 * kHaloBox;
+          q.a_stage_bytes = 3 * kHaloBox;
+          for (int t = 0; t < 9; ++t) {
+            q.tap_off[t] = static_cast<uint32_t>(t % 3) * kHaloBox + static_cast<uint32_t>(t / 3) * 1024u;
+            q.tap_sbo[t] = 1024u >> 4;
+          }
+        }
+        for (int i = 1; i < 4; ++i) op->tmA[i] = op->tmA[0];
+      } else if (shape_ok && d.s == 2 && allow_s2) {
+        // parity view (py, px) = in[2r + py][2c + px]; output (y, x), tap (kh, kw) reads in[2y + kh - 1][2x + kw - 1]:
+        // kh = 0 -> view row y - 1 of the odd rows, kh = 1 -> row y of the even rows, kh = 2 -> row y of the odd rows (columns alike)
+        uint32_t off = 0, tx = 0;
+        uint32_t view_off[4], view_pitch[4];
+        for (int v = 0; v < 4; ++v) {
+          const int bw = kHaloTw + (v & 1), bh = kHaloTh + (v >> 1);
+          view_off[v] = off;
+          view_pitch[v] = static_cast<uint32_t>(bw) * 128u;
+          tx += static_cast<uint32_t>(bw * bh) * 128u;
+          off += align1k(static_cast<uint32_t>(bw * bh) * 128u);
+        }
+        use = 2 * static_cast<size_t>(off) + 2 * 3 * b_chunk <= budget;  // two A stages + two weight stages must fit
+        if (use) {
+          q.n_boxes = 4;
+          q.a_tx = tx;
+          q.a_stage_bytes = off;
+          q.a_stages = 2;
+          for (int v = 0; v < 4; ++v) {
+            const int py = v >> 1, px = v & 1;
+            make_act_tmap(&op->tmA[v], in, kc, kHaloTw + px, kHaloTh + py, py, px);
+            q.box_off[v] = view_off[v]; q.box_map[v] = v; q.box_dx[v] = -px; q.box_dy[v] = -py;
+          }
+          for (int t = 0; t < 9; ++t) {
+            const int kh = t / 3, kx = t % 3;
+            const int v = (kh != 1 ? 2 : 0) | (kx != 1 ? 1 : 0);
+            q.tap_off[t] = view_off[v] + (kh == 2 ? view_pitch[v] : 0u) + (kx == 2 ? 128u : 0u);
+            q.tap_sbo[t] = view_pitch[v] >> 4;
+          }
+        }
+      }
+      if (use) {
+        q.halo = 1;
         q.tw = kHaloTw;
         q.th = kHaloTh;
-        make_act_tmap(&op->tmA[0], in, kc, h1 ? kHaloTw + 2 : kHaloTw, kHaloRows, -1, -1);
-        for (int i = 0; i < 4; ++i) op->maps.a[i] = op->tmA[0];
+        for (int i = 0; i < 4; ++i) op->maps.a[i] = op->tmA[i];
         op->maps.b = op->tmB;
-        const size_t budget = 227 * 1024 - 8192 - 1024;  // static: barriers + the bias vector; alignment slack
-        const size_t a_bytes = static_cast<size_t>(q.a_stages) * (h1 ? kHalo1Stage : 3 * kHaloBox);
+        const size_t a_bytes = static_cast<size_t>(q.a_stages) * q.a_stage_bytes;
         int stages = static_cast<int>(std::min<size_t>(kPairMaxStages, (budget - a_bytes) / (3 * b_chunk)));  // a stage = one filter row
         MDB_REQUIRE(stages >= 2, "not enough shared memory for the halo pipeline");
         q.stages = stages;
@@ -268,7 +330,9 @@ static void conv_launch_pair(ConvOp* op, int n_img, cudaStream_t st) {
     MDB_CUDA(cudaMemsetAsync(d_dbg, 0, sizeof(long long) * 16 * grid, st));
   }
   p.dbg = d_dbg;
-  static const bool pdl = getenv("MDB_CONV_PDL") && getenv("MDB_CONV_PDL")[0] == '1';
+  // programmatic dependent launch: the next layer's CTAs start (barrier init, TMEM allocation, bias) as SMs free up and wait
+  // for this layer's completion before touching activations.  -3 % network time at 8 images, neutral at 64; MDB_CONV_PDL=0: off
+  static const bool pdl = !(getenv("MDB_CONV_PDL") && getenv("MDB_CONV_PDL")[0] == '0');
   p.pdl = pdl ? 1 : 0;
   if (pdl) {
     cudaLaunchConfig_t cfg = {};

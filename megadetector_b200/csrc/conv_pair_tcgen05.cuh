@@ -68,9 +68,16 @@ constexpr int kHaloRows = 18;                       // th + 2
 constexpr int kHaloTw = 8, kHaloTh = 16;
 constexpr uint32_t kHaloBox = kHaloRows * kHaloTw * 128;  // bytes of one {64 ch, 8 px, 18 rows} box
 constexpr int kHaloMaxA = 4;
-// single-box halo (halo == 2): ONE {64 ch, 10 px, 18 rows} box per chunk serves all nine taps: the kw shift is a 128-byte
-// (one pixel) offset of the A descriptor's start address, the kh shift one 1280-byte image row; the eight MMA rows of a
-// core-matrix group are the eight pixels of one image row, the stride between groups (SBO) is the 1280-byte row pitch
+// single-box halo (stride 1, the default): ONE {64 ch, 10 px, 18 rows} box per chunk serves all nine taps: the kw shift is a
+// 128-byte (one pixel) offset of the A descriptor's start address, the kh shift one 1280-byte image row; the eight MMA rows of
+// a core-matrix group are the eight pixels of one image row, the stride between groups (SBO) is the 1280-byte row pitch.
+// Neither offset is a multiple of the 1024-byte swizzle period: this relies on the 128-byte swizzle being a function of the
+// ABSOLUTE shared-memory address (bits 4-6 ^= bits 7-9) on both the TMA write and the MMA read side -- measured: every conv
+// parity test passes with the descriptor's base-offset field left 0, and fails when it is set to (start >> 7) & 7
+// (profiles/r02_conv_ab_experiments.txt par. 13).  A bytes per chunk and CTA: 23 KB instead of 55 KB.
+// Stride 2 works the same way on the four parity views of the input (even/odd rows x even/odd columns): tap (kh, kw) reads view
+// (kh != 1, kw != 1) at row offset (kh == 2), column offset (kw == 2), so four boxes of 8|9 px x 16|17 rows (70 KB) replace nine
+// 8 x 16 boxes (147 KB).
 constexpr uint32_t kHalo1Pitch = (kHaloTw + 2) * 128;
 constexpr uint32_t kHalo1Box = kHaloRows * kHalo1Pitch;             // 23040 bytes
 constexpr uint32_t kHalo1Stage = (kHalo1Box + 1023u) & ~1023u;      // 23552
@@ -101,11 +108,19 @@ struct PairParams {
   int act;
   int wide;        // 1: every epilogue row segment is 32-byte aligned -> 256-bit global accesses
   int fast;        // 1: half output, wide, every 16-column chunk full -> the branch-free epilogue path
-  int halo;        // 1: 3x3/s1 row-halo main loop (tile 8 x 16; A fetched per kw shift, reused across kh); 2: single-box halo
+  int halo;        // != 0: 3x3 halo main loop (tile 8 x 16 output pixels; A fetched once per chunk and shared by the taps, weights
+                   // streamed one filter row per stage); see the tables below
   int pdl;         // launched with programmatic stream serialization: let the next kernel's CTAs start as SMs free up, and wait for
                    // the previous kernel's results only after this CTA's own set-up (barriers, TMEM, bias)
-  int a_base_off;  // halo 2: fill the descriptor's base-offset field with (start address >> 7) & 7
-  int a_stages;    // halo mode: number of A (3-box) buffers
+  int a_stages;    // halo mode: depth of the A ring
+  // halo mode, table-driven: per chunk `n_boxes` TMA boxes land at box_off[] of the A stage (tensor map box_map[], origin =
+  // tile origin + box_dx / box_dy in that map's coordinates); tap (kh, kw) reads its 128 rows at tap_off[kh * 3 + kw] with the
+  // 8-row group stride tap_sbo[] (bytes >> 4)
+  int n_boxes;
+  uint32_t a_stage_bytes, a_tx;
+  uint32_t box_off[4];
+  int box_map[4], box_dx[4], box_dy[4];
+  uint32_t tap_off[9], tap_sbo[9];
   uint32_t idesc;  // M = 256
   long long* dbg;  // per-CTA cycle counters (MDB_CONV_DEBUG=1 in a -DMDB_CONV_TIMERS build), null otherwise
   int backoff_ns;  // > 0: the producer / MMA role threads sleep this long between polls of the barriers they are BLOCKED on when
@@ -440,16 +455,15 @@ conv_pair_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
       // ---- 3x3 / stride 1: per 64-channel chunk, three {64 ch, 8 px, 18 rows} boxes (one per kw shift) are
       // fetched once and serve all three kh taps (the kh shift is a 1024-byte offset in shared memory);
       // weights stream through their own ring, one filter row per stage.  A bytes per chunk: 55 KB instead of 147 KB.
-      const bool single = p.halo == 2;
-      const uint32_t a_stage_bytes = single ? kHalo1Stage : 3u * kHaloBox;
-      const uint32_t a_tx = single ? kHalo1Box : 3u * kHaloBox;
+      const uint32_t a_stage_bytes = p.a_stage_bytes;
+      const uint32_t a_tx = p.a_tx;
       const uint32_t b_region = smem_base + static_cast<uint32_t>(p.a_stages) * a_stage_bytes;
       const uint32_t b_bytes = half_n * ROW_BYTES;
       uint32_t as = 0, aph = 0;
       for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
         int n_tile, txi, tyi, img;
         decode_tile(p, tile, rank, n_tile, txi, tyi, img);
-        const int ox0 = txi * kHaloTw - 1, oy0 = tyi * kHaloTh - 1;
+        const int ox0 = txi * kHaloTw, oy0 = tyi * kHaloTh;
         const int nb0 = n_tile * p.BN + static_cast<int>(rank * half_n);
         for (int c = 0; c < p.chunks; ++c) {
           if (kTimers) mbar_wait_addr_timed(a_empty0 + 8u * as, aph ^ 1u, w_empty);
@@ -459,14 +473,9 @@ conv_pair_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
             else mbar_arrive_cluster_addr(a_full0_remote + 8u * as);
             const uint32_t abase = smem_base + as * a_stage_bytes;
             if (loads) {
-              if (single) {
-                tma2_load_4d_addr(&maps.a[0], a_full0_tma + 8u * as, abase, c * KC, ox0, oy0, img);
-              } else {
-#pragma unroll
-                for (int kw = 0; kw < 3; ++kw)
-                  tma2_load_4d_addr(&maps.a[0], a_full0_tma + 8u * as, abase + static_cast<uint32_t>(kw) * kHaloBox, c * KC,
-                                    ox0 + kw, oy0, img);
-              }
+              for (int b = 0; b < p.n_boxes; ++b)
+                tma2_load_4d_addr(&maps.a[p.box_map[b]], a_full0_tma + 8u * as, abase + p.box_off[b], c * KC, ox0 + p.box_dx[b],
+                                  oy0 + p.box_dy[b], img);
             }
           }
           if (++as == static_cast<uint32_t>(p.a_stages)) { as = 0; aph ^= 1u; }
@@ -553,12 +562,7 @@ conv_pair_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * acc_stride;
         if (p.halo) {
-          const bool single = p.halo == 2;
-          const uint32_t a_stage_bytes = single ? kHalo1Stage : 3u * kHaloBox;
-          const uint32_t kw_step = single ? 128u : kHaloBox;
-          const uint32_t kh_step = single ? kHalo1Pitch : 1024u;
-          // A's high word: SBO = the byte distance between consecutive image rows of the box
-          const uint32_t a_hi0 = single ? ((desc_hi & ~0x3FFFu) | (kHalo1Pitch >> 4)) : desc_hi;
+          const uint32_t a_stage_bytes = p.a_stage_bytes;
           const uint32_t b_region = smem_base + static_cast<uint32_t>(p.a_stages) * a_stage_bytes;
           for (int c = 0; c < p.chunks; ++c) {
             mbar_wait_addr_timed(a_full0 + 8u * as, aph, w_full);
@@ -572,14 +576,14 @@ conv_pair_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
 #pragma unroll
                 for (int kw = 0; kw < 3; ++kw) {
                   // rows of the tile for this tap: halo rows kh .. kh+15 of the kw-shifted box (8 px = 1024 B per row)
-                  const uint32_t a_addr = abase + static_cast<uint32_t>(kw) * kw_step + static_cast<uint32_t>(kh) * kh_step;
-                  const uint32_t a_lo = desc_lo | (a_addr >> 4);
-                  const uint32_t a_hi = a_hi0 | (p.a_base_off ? ((a_addr >> 7) & 7u) << 17 : 0u);
+                  // A's high word carries the tap's SBO = the byte distance between consecutive image rows of its box
+                  const uint32_t a_lo = desc_lo | ((abase + p.tap_off[kh * 3 + kw]) >> 4);
+                  const uint32_t a_hi0 = (desc_hi & ~0x3FFFu) | p.tap_sbo[kh * 3 + kw];
                   const uint32_t b_lo = desc_lo | ((b_region + (s * 3u + static_cast<uint32_t>(kw)) * b_chunk) >> 4);
                   if (mmas) {
 #pragma unroll
                     for (int k = 0; k < KC / 16; ++k)
-                      if (k < nk) umma2_f16_lo2(d_tmem, a_lo + 2u * k, a_hi, b_lo + 2u * k, desc_hi, p.idesc, (c | kh | kw | k) != 0 ? 1u : 0u);
+                      if (k < nk) umma2_f16_lo2(d_tmem, a_lo + 2u * k, a_hi0, b_lo + 2u * k, desc_hi, p.idesc, (c | kh | kw | k) != 0 ? 1u : 0u);
                   }
                 }
                 umma2_commit_mc_addr(empty0 + 8u * s);

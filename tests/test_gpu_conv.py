@@ -36,6 +36,11 @@ CASES = [
     # row-halo main loop from 80 channels (two chunks per tap, the second mostly zero-filled), filter-row weight stages
     ('3x3_c80_halo_many', 4, 96, 160, 80, 80, 3, 1, 1, 1, True, False),
     ('3x3_c160_halo_many', 4, 48, 80, 160, 160, 3, 1, 1, 1, True, False),
+    # stride-2 halo main loop: four parity-view boxes per chunk (8|9 px x 16|17 rows), taps addressed by row / pixel offsets
+    ('3x3_s2_c80_halo', 2, 64, 96, 80, 160, 3, 2, 1, 1, False, False),
+    ('3x3_s2_c160_halo', 2, 96, 160, 160, 320, 3, 2, 1, 1, False, False),
+    ('3x3_s2_c320_halo_many', 4, 96, 160, 320, 640, 3, 2, 1, 1, False, False),
+    ('3x3_s2_halo_ragged', 1, 60, 80, 128, 64, 3, 2, 1, 1, False, False),
 ]
 
 

@@ -30,6 +30,10 @@ CASES = {
     'b64_c1x1_320': (64, 48, 80, 320, 320, 1, 1, 0, False),
     'b64_c3x3_160': (64, 96, 160, 160, 160, 3, 1, 1, True),
     'b64_c3x3_320': (64, 48, 80, 320, 320, 3, 1, 1, True),
+    'b64_s2_80_160': (64, 384, 640, 80, 160, 3, 2, 1, False),
+    'b64_s2_160_320': (64, 192, 320, 160, 320, 3, 2, 1, False),
+    'b64_s2_320_640': (64, 96, 160, 320, 640, 3, 2, 1, False),
+    'b64_s2_320_320': (64, 96, 160, 320, 320, 3, 2, 1, False),
 }
 names = sys.argv[1].split(',') if len(sys.argv) > 1 else list(CASES)
 iters = int(sys.argv[2]) if len(sys.argv) > 2 else 10
