@@ -103,5 +103,53 @@ def _build_locked(stamp, stamp_file, verbose):
     return OUT
 
 
+FMT_SRC = os.path.join(CSRC, 'pyformat.c')
+FMT_FLAGS = ['-O2', '-ffp-contract=off', '-fno-fast-math', '-shared', '-fPIC', '-Wall']
+
+
+def formatter_path():
+    import sysconfig
+    return os.path.join(HERE, '_mdbfmt' + sysconfig.get_config_var('EXT_SUFFIX'))
+
+
+def build_formatter(force=False):
+    """Compile csrc/pyformat.c (the host-side record formatter, a CPython extension) with gcc, in-tree.  Same locking and
+    atomic-rename discipline as the CUDA library."""
+    import fcntl
+    import sysconfig
+    out = formatter_path()
+    fmt_dir = os.path.join(HERE, 'csrc', 'build')
+    os.makedirs(fmt_dir, exist_ok=True)
+    stamp_file = os.path.join(fmt_dir, 'fmt_stamp')
+    with open(FMT_SRC, 'rb') as f:
+        stamp = hashlib.sha256(f.read() + ' '.join(FMT_FLAGS).encode() + sys.version.encode()).hexdigest()
+
+    def fresh():
+        return os.path.exists(out) and os.path.exists(stamp_file) and open(stamp_file).read() == stamp
+
+    if not force and fresh():
+        return out
+    with open(os.path.join(fmt_dir, 'fmt_lock'), 'w') as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and fresh():
+                return out
+            tmp = out + '.tmp.{}'.format(os.getpid())
+            cmd = [os.environ.get('CC', 'gcc')] + FMT_FLAGS + ['-I' + sysconfig.get_paths()['include'], FMT_SRC, '-o', tmp, '-lm']
+            r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+            if r.returncode != 0:
+                sys.stderr.write(r.stdout)
+                if os.path.exists(tmp):
+                    os.remove(tmp)
+                raise RuntimeError('building the record formatter failed')
+            os.replace(tmp, out)
+            with open(stamp_file, 'w') as f:
+                f.write(stamp)
+            return out
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
 if __name__ == '__main__':
     print(build(force='--force' in sys.argv, verbose='--verbose' in sys.argv))
+    print(build_formatter(force='--force' in sys.argv))

