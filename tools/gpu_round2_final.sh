@@ -17,4 +17,8 @@ unset MDB_NO_GRAPHS
 for k in upsample2x sppf_plane nms_image decode_kernel; do
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:$k -s 1 -c 1 -f -o gpurun_out/ncu_final_$k python tools/profile_one_pass.py 64 > gpurun_out/ncu_final_$k.log 2>&1; echo "$k capture exit $?"
 done
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:conv_pair -s 1 -c 1 -f -o gpurun_out/ncu_final_c3x3_320 python tools/conv_cases.py b64_c3x3_320 2 > gpurun_out/ncu_final_c3x3_320.log 2>&1; echo "conv capture exit $?"
+for c in c3x3_320 c3x3_160 s2_80_160 c1x1_160; do
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:conv_pair -s 1 -c 1 -f -o gpurun_out/ncu_final_$c python tools/conv_cases.py b64_$c 2 > gpurun_out/ncu_final_$c.log 2>&1; echo "conv capture $c exit $?"
+done
+timeout 300 python tools/profile_layers.py 64 gpurun_out/r02_layers_bs64.csv > gpurun_out/profile_layers.log 2>&1; echo "layers exit $?"; tail -2 gpurun_out/profile_layers.log
+bash tools/gpu_sanitizer.sh
