@@ -9,7 +9,7 @@ reference's own chunking rule (sharding.split_list_into_n_chunks == ct_utils.spl
 process per GPU owns one `B200Detector` (one `mdb_engine`, images independent end to end, NO collective on the data path),
 decodes its images with a thread pool, runs them in batches and returns its records; the parent merges them with the
 notebook's uniqueness check and writes one results file in the reference's format (run_detector_batch.py:1546-1700,
-format_version 1.4 fields: info / detection_categories / images).
+format_version 1.6: info incl. detector_metadata / detection_categories / images).
 
 Checkpoint / resume use the reference's own file format and flags (run_detector_batch.py:1465-1520, 1983-2003, 2095-2118,
 2179-2181): a JSON dict {"checkpoint": [records with absolute file names]} rewritten every --checkpoint_frequency images
@@ -33,6 +33,28 @@ from . import sharding
 
 IMAGE_EXTENSIONS = ('.jpg', '.jpeg', '.gif', '.png', '.tif', '.tiff', '.bmp')  # path_utils.IMG_EXTENSIONS
 DEFAULT_OUTPUT_CONFIDENCE_THRESHOLD = 0.005  # run_detector.py DEFAULT_OUTPUT_CONFIDENCE_THRESHOLD
+CURRENT_FORMAT_VERSION = '1.6'               # run_detector_batch.py:119
+
+# The MDv5 part of run_detector.known_models / model_string_to_model_version (run_detector.py:88-216): what
+# write_results_to_file records as info.detector_metadata for the models this engine runs.  Order matters (first match wins).
+_MDV5_FILENAME_STRINGS = (('mdv5a', 'v5a.0.1'), ('mdv5b', 'v5b.0.1'), ('v5a.0.0', 'v5a.0.1'), ('v5b.0.0', 'v5b.0.1'),
+                          ('v5a.0.1', 'v5a.0.1'), ('v5b.0.1', 'v5b.0.1'), ('mdv5', 'v5a.0.1'), ('md5', 'v5a.0.1'),
+                          ('default', 'v5a.0.1'), ('megadetector', 'v5a.0.1'))
+_MDV5_MD5 = {'v5a.0.0': 'ec1d7603ec8cf642d6e0cd008ba2be8c', 'v5b.0.0': 'bc235e73f53c5c95e66ea0d1b2cbf542',
+             'v5a.0.1': '60f8e7ec1308554df258ed1f4040bc4f', 'v5b.0.1': 'f17ed6fedfac2e403606a08c89984905'}
+
+
+def detector_metadata_from_filename(detector_file):
+    """get_detector_version_from_filename + get_detector_metadata_from_version_string (run_detector.py:276-350) for the
+    MDv5 family; any other name gets the reference's 'unknown' block."""
+    fn = os.path.basename(detector_file).lower()
+    version = next((v for key, v in _MDV5_FILENAME_STRINGS if key in fn), 'unknown')
+    if version not in _MDV5_MD5:
+        return {'megadetector_version': 'unknown', 'typical_detection_threshold': 0.2, 'conservative_detection_threshold': 0.1}
+    return {'url': 'https://github.com/agentmorris/MegaDetector/releases/download/v5.0/md_{}.pt'.format(version),
+            'typical_detection_threshold': 0.2, 'conservative_detection_threshold': 0.05, 'image_size': 1280,
+            'model_type': 'yolov5', 'normalized_typical_inference_speed': 1.0, 'md5': _MDV5_MD5[version],
+            'megadetector_version': version}
 
 
 def find_images(folder, recursive=True):
@@ -165,8 +187,8 @@ def write_checkpoint(checkpoint_path, results):
     if os.path.isfile(checkpoint_path):
         tmp = checkpoint_path + '_tmp'
         shutil.copyfile(checkpoint_path, tmp)
-    with open(checkpoint_path, 'w') as f:
-        json.dump({'checkpoint': results}, f, indent=1, default=str)
+    with open(checkpoint_path, 'w', newline='\n', encoding='utf-8') as f:
+        json.dump({'checkpoint': results}, f, indent=1, default=str, ensure_ascii=True)
     if tmp is not None:
         try:
             os.remove(tmp)
@@ -279,24 +301,37 @@ def run_sharded(model_file, files, n_gpus, batch_size=64, confidence_threshold=D
     return sorted(merged, key=lambda r: r['file']), times
 
 
-def write_results(results, output_file, relative_path_base=None, detector_file=None):
-    """The subset of run_detector_batch.write_results_to_file (:1546-1700) this driver needs; same JSON layout."""
+def write_results(results, output_file, relative_path_base=None, detector_file=None, include_max_conf=False):
+    """run_detector_batch.write_results_to_file (:1546-1662) with its default arguments: same JSON (format 1.6)."""
     images = []
     for r in results:
         r = dict(r)
         if relative_path_base is not None:
-            r['file'] = os.path.relpath(r['file'], relative_path_base).replace('\\', '/')
-        r.pop('max_detection_conf', None)  # include_max_conf=False is the reference's default
-        if r.get('detections') is not None:  # run_detector_batch.py:1634-1637: descending confidence (stable)
+            r['file'] = os.path.relpath(r['file'], relative_path_base)
+        r['file'] = r['file'].replace('\\', '/')
+        if not include_max_conf:
+            r.pop('max_detection_conf', None)
+        if r.get('detections') is not None:  # :1634-1637: descending confidence (stable)
             r['detections'] = sorted(r['detections'], key=lambda d: d['conf'], reverse=True)
+        if 'failure' in r:                   # :1639-1644
+            assert r.get('detections') is None, 'Illegal failure/detection combination'
+            r['detections'] = None
         images.append(r)
     images.sort(key=lambda r: r['file'])
-    info = {'detection_completion_time': time.strftime('%Y-%m-%d %H:%M:%S', time.gmtime()), 'format_version': '1.4'}
+    info = {'detection_completion_time': datetime.now().strftime('%Y-%m-%d %H:%M:%S'), 'format_version': CURRENT_FORMAT_VERSION}
     if detector_file is not None:
         info['detector'] = os.path.basename(detector_file)
+        info['detector_metadata'] = detector_metadata_from_filename(detector_file)
+    else:
+        info['detector'] = 'unknown'
+        info['detector_metadata'] = detector_metadata_from_filename('unknown')
     out = {'images': images, 'detection_categories': {'1': 'animal', '2': 'person', '3': 'vehicle'}, 'info': info}
-    with open(output_file, 'w') as f:
-        json.dump(out, f, indent=1)
+    try:
+        os.makedirs(os.path.dirname(output_file), exist_ok=True)
+    except Exception:
+        pass
+    with open(output_file, 'w', newline='\n', encoding='utf-8') as f:  # ct_utils.write_json(force_str=True) (:210-250)
+        json.dump(out, f, indent=1, default=str, ensure_ascii=True)
     return output_file
 
 

@@ -177,3 +177,32 @@ def test_image_file_argument_forms(tmp_path):
     assert len(run_batch.resolve_image_list(str(tmp_path))) == 5
     with pytest.raises(ValueError):
         run_batch.resolve_image_list(str(tmp_path / 'nothing.bin'))
+
+
+def test_results_file_equals_the_reference_writer(tmp_path):
+    """write_results against the reference's own write_results_to_file (run_detector_batch.py:1546-1662) on the same records:
+    byte-identical files except for the completion time."""
+    ref_root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'baseline', '_ref')
+    if not os.path.isdir(os.path.join(ref_root, 'megadetector')):
+        pytest.skip('baseline/_ref is not installed (tools/install_reference.sh)')
+    import copy
+    import re
+    import sys
+    for p in (ref_root, os.path.join(os.path.dirname(os.path.abspath(__file__)), 'stubs')):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    from megadetector.detection import run_detector_batch as ref
+    base = str(tmp_path)
+    recs = [{'file': os.path.join(base, 'b', 'z.jpg'), 'max_detection_conf': 0.9,
+             'detections': [{'category': '2', 'conf': 0.1, 'bbox': [0.1, 0.2, 0.3, 0.4]},
+                            {'category': '1', 'conf': 0.9, 'bbox': [0.5, 0.5, 0.25, 0.125]},
+                            {'category': '3', 'conf': 0.1, 'bbox': [0.0, 0.0, 1.0, 1.0]}]},
+            {'file': os.path.join(base, 'a.jpg'), 'failure': 'image access failure'},
+            {'file': os.path.join(base, 'b', 'c.jpg'), 'max_detection_conf': 0.0, 'detections': []}]
+    for det_file in ('/models/md_v5a.0.1.pt', '/models/MDV5B.pt', 'synthetic://yolov5x6?seed=0', None):
+        for rel in (None, base):
+            ours, theirs = str(tmp_path / 'ours.json'), str(tmp_path / 'theirs.json')
+            run_batch.write_results(copy.deepcopy(recs), ours, relative_path_base=rel, detector_file=det_file)
+            ref.write_results_to_file(copy.deepcopy(recs), theirs, relative_path_base=rel, detector_file=det_file)
+            strip = lambda t: re.sub(r'"detection_completion_time": "[^"]*"', '"detection_completion_time": ""', t)
+            assert strip(open(ours).read()) == strip(open(theirs).read()), (det_file, rel)
