@@ -301,8 +301,9 @@ def run_sharded(model_file, files, n_gpus, batch_size=64, confidence_threshold=D
     return sorted(merged, key=lambda r: r['file']), times
 
 
-def write_results(results, output_file, relative_path_base=None, detector_file=None, include_max_conf=False):
-    """run_detector_batch.write_results_to_file (:1546-1662) with its default arguments: same JSON (format 1.6)."""
+def results_document(results, relative_path_base=None, detector_file=None, include_max_conf=False):
+    """The dict run_detector_batch.write_results_to_file (:1546-1662, default arguments) builds: images sorted by file,
+    detections by descending confidence, failure records with detections None, info with format 1.6 + detector metadata."""
     images = []
     for r in results:
         r = dict(r)
@@ -325,7 +326,12 @@ def write_results(results, output_file, relative_path_base=None, detector_file=N
     else:
         info['detector'] = 'unknown'
         info['detector_metadata'] = detector_metadata_from_filename('unknown')
-    out = {'images': images, 'detection_categories': {'1': 'animal', '2': 'person', '3': 'vehicle'}, 'info': info}
+    return {'images': images, 'detection_categories': {'1': 'animal', '2': 'person', '3': 'vehicle'}, 'info': info}
+
+
+def write_results(results, output_file, relative_path_base=None, detector_file=None, include_max_conf=False):
+    """run_detector_batch.write_results_to_file: same JSON file (ct_utils.write_json with force_str, :210-250)."""
+    out = results_document(results, relative_path_base, detector_file, include_max_conf)
     try:
         os.makedirs(os.path.dirname(output_file), exist_ok=True)
     except Exception:

@@ -217,15 +217,9 @@ def process_videos(detector, input_video_file, output_json_file=None, frame_samp
         except Exception as e:
             print('Video {} failed: {}'.format(v, e))
             images.append(video_results_to_md_format(rel, -1, {'failure': FAILURE_VIDEO_OPEN}))
-    images.sort(key=lambda im: im['file'])  # write_results_to_file: by file, detections by descending confidence (stable)
-    for im in images:
-        if im.get('detections') is not None:
-            im['detections'] = sorted(im['detections'], key=lambda d: d['conf'], reverse=True)
-    out = {'images': images, 'detection_categories': {'1': 'animal', '2': 'person', '3': 'vehicle'},
-           'info': {'detection_completion_time': time.strftime('%Y-%m-%d %H:%M:%S', time.gmtime()), 'format_version': '1.4'}}
-    if detector_file is not None:
-        out['info']['detector'] = os.path.basename(detector_file)
+    # process_video.py:261-265: the records go through run_detector_batch.write_results_to_file
+    from . import run_batch
     if output_json_file is not None:
-        with open(output_json_file, 'w') as f:
-            json.dump(out, f, indent=1)
+        run_batch.write_results(images, output_json_file, relative_path_base=None, detector_file=detector_file)
+    out = run_batch.results_document(images, None, detector_file)
     return out
