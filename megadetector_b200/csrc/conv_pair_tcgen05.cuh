@@ -68,6 +68,10 @@ constexpr int kHaloRows = 18;                       // th + 2
 constexpr int kHaloTw = 8, kHaloTh = 16;
 constexpr uint32_t kHaloBox = kHaloRows * kHaloTw * 128;  // bytes of one {64 ch, 8 px, 18 rows} box
 constexpr int kHaloMaxA = 4;
+#ifndef MDB_HALO_KH_UNROLL
+#define MDB_HALO_KH_UNROLL 3  // 3: the nine taps fully unrolled in the MMA issue loop; 1: the filter-row loop stays a loop
+#endif
+constexpr int kHaloKhUnroll = MDB_HALO_KH_UNROLL;
 // single-box halo (stride 1, the default): ONE {64 ch, 10 px, 18 rows} box per chunk serves all nine taps: the kw shift is a
 // 128-byte (one pixel) offset of the A descriptor's start address, the kh shift one 1280-byte image row; the eight MMA rows of
 // a core-matrix group are the eight pixels of one image row, the stride between groups (SBO) is the 1280-byte row pitch.
@@ -554,6 +558,7 @@ conv_pair_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
       const uint32_t desc_hi = static_cast<uint32_t>(desc_tmpl >> 32);
       const uint32_t desc_lo = static_cast<uint32_t>(desc_tmpl);  // LBO field; the start address is added per use
       const bool mmas = !(kProbes && (p.probe & 2));
+      const bool has_tail = p.tail_k != KC / 16;
       for (int tile = cluster_id; tile < total_tiles; tile += num_clusters, ++tcount) {
         const uint32_t acc = tcount & acc_mask;
         const uint32_t acc_ph = (tcount >> acc_shift) & 1u;
@@ -561,29 +566,47 @@ conv_pair_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
         else mbar_wait_addr_backoff(acc_empty0 + 8u * acc, acc_ph ^ 1u, static_cast<uint32_t>(p.backoff_ns));
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * acc_stride;
+        // The issuing thread's loop is the network's metronome: one dependent instruction costs it ~10 cycles and an N = 80 MMA
+        // lasts 40.  So the nine taps are fully unrolled (their table entries become constant-bank operands), and the
+        // "skip the zero-filled K steps" test sits outside the per-MMA code: one uniform branch per chunk, none per MMA
+        // (a per-MMA `if (k < nk)` cost 9 % of the whole network: profiles/r02_conv_ab_experiments.txt par. 18).
         if (p.halo) {
           const uint32_t a_stage_bytes = p.a_stage_bytes;
           const uint32_t b_region = smem_base + static_cast<uint32_t>(p.a_stages) * a_stage_bytes;
+          const uint32_t a_hi_base = desc_hi & ~0x3FFFu;  // A's high word carries the tap's SBO = its box's image-row pitch
           for (int c = 0; c < p.chunks; ++c) {
             mbar_wait_addr_timed(a_full0 + 8u * as, aph, w_full);
             const uint32_t abase = smem_base + as * a_stage_bytes;
-            const int nk = c == p.chunks - 1 ? p.tail_k : KC / 16;
-#pragma unroll 1
+            const bool tail = has_tail && c == p.chunks - 1;
+#pragma unroll kHaloKhUnroll
             for (int kh = 0; kh < 3; ++kh) {
               mbar_wait_addr_timed(full0 + 8u * s, ph, w_full);
               tc_fence_after();
               if (el) {
+                const uint32_t b_stage = b_region + s * 3u * b_chunk;
+                if (!tail) {
 #pragma unroll
-                for (int kw = 0; kw < 3; ++kw) {
-                  // rows of the tile for this tap: halo rows kh .. kh+15 of the kw-shifted box (8 px = 1024 B per row)
-                  // A's high word carries the tap's SBO = the byte distance between consecutive image rows of its box
-                  const uint32_t a_lo = desc_lo | ((abase + p.tap_off[kh * 3 + kw]) >> 4);
-                  const uint32_t a_hi0 = (desc_hi & ~0x3FFFu) | p.tap_sbo[kh * 3 + kw];
-                  const uint32_t b_lo = desc_lo | ((b_region + (s * 3u + static_cast<uint32_t>(kw)) * b_chunk) >> 4);
-                  if (mmas) {
+                  for (int kw = 0; kw < 3; ++kw) {
+                    const uint32_t a_lo = desc_lo | ((abase + p.tap_off[kh * 3 + kw]) >> 4);
+                    const uint32_t a_hi = a_hi_base | p.tap_sbo[kh * 3 + kw];
+                    const uint32_t b_lo = desc_lo | ((b_stage + static_cast<uint32_t>(kw) * b_chunk) >> 4);
+                    if (mmas) {
 #pragma unroll
-                    for (int k = 0; k < KC / 16; ++k)
-                      if (k < nk) umma2_f16_lo2(d_tmem, a_lo + 2u * k, a_hi0, b_lo + 2u * k, desc_hi, p.idesc, (c | kh | kw | k) != 0 ? 1u : 0u);
+                      for (int k = 0; k < KC / 16; ++k)
+                        umma2_f16_lo2(d_tmem, a_lo + 2u * k, a_hi, b_lo + 2u * k, desc_hi, p.idesc,
+                                      (kh | kw | k) != 0 ? 1u : (c != 0 ? 1u : 0u));
+                    }
+                  }
+                } else {
+#pragma unroll
+                  for (int kw = 0; kw < 3; ++kw) {
+                    const uint32_t a_lo = desc_lo | ((abase + p.tap_off[kh * 3 + kw]) >> 4);
+                    const uint32_t a_hi = a_hi_base | p.tap_sbo[kh * 3 + kw];
+                    const uint32_t b_lo = desc_lo | ((b_stage + static_cast<uint32_t>(kw) * b_chunk) >> 4);
+                    if (mmas) {
+                      for (int k = 0; k < p.tail_k; ++k)
+                        umma2_f16_lo2(d_tmem, a_lo + 2u * k, a_hi, b_lo + 2u * k, desc_hi, p.idesc, (c | kh | kw | k) != 0 ? 1u : 0u);
+                    }
                   }
                 }
                 umma2_commit_mc_addr(empty0 + 8u * s);
@@ -593,7 +616,27 @@ conv_pair_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
             if (el) umma2_commit_mc_addr(a_empty0 + 8u * as);
             if (++as == static_cast<uint32_t>(p.a_stages)) { as = 0; aph ^= 1u; }
           }
+        } else if (!has_tail) {
+          for (int q0 = 0; q0 < p.total_chunks; q0 += p.cps) {
+            const int nch = min(p.cps, p.total_chunks - q0);
+            mbar_wait_addr_timed(full0 + 8u * s, ph, w_full);
+            tc_fence_after();
+            uint32_t a_lo = desc_lo | ((smem_base + s * stage_bytes) >> 4);
+            if (el) {
+              for (int j = 0; j < nch; ++j, a_lo += chunk_bytes >> 4) {
+                if (mmas) {
+#pragma unroll
+                  for (int k = 0; k < KC / 16; ++k)
+                    umma2_f16_lo(d_tmem, a_lo + 2u * k, a_lo + (A_CHUNK >> 4) + 2u * k, desc_hi, p.idesc,
+                                 (q0 | j | k) != 0 ? 1u : 0u);
+                }
+              }
+              umma2_commit_mc_addr(empty0 + 8u * s);
+            }
+            if (++s == S) { s = 0; ph ^= 1u; }
+          }
         } else {
+          // C_in not a multiple of 64: the last chunk of every tap issues only tail_k of its four K steps
           int cc = 0;  // chunk index within the tap at the start of the stage
           for (int q0 = 0; q0 < p.total_chunks; q0 += p.cps) {
             const int nch = min(p.cps, p.total_chunks - q0);
@@ -606,15 +649,15 @@ conv_pair_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
                 const int nk = c2 == p.chunks - 1 ? p.tail_k : KC / 16;
                 if (++c2 == p.chunks) c2 = 0;
                 if (mmas) {
-#pragma unroll
-                  for (int k = 0; k < KC / 16; ++k)
-                    if (k < nk) umma2_f16_lo(d_tmem, a_lo + 2u * k, a_lo + (A_CHUNK >> 4) + 2u * k, desc_hi, p.idesc,
-                                             (q0 | j | k) != 0 ? 1u : 0u);
+                  for (int k = 0; k < nk; ++k)
+                    umma2_f16_lo(d_tmem, a_lo + 2u * k, a_lo + (A_CHUNK >> 4) + 2u * k, desc_hi, p.idesc,
+                                 (q0 | j | k) != 0 ? 1u : 0u);
                 }
               }
               umma2_commit_mc_addr(empty0 + 8u * s);
             }
-            cc = (cc + nch) % p.chunks;
+            cc += nch;  // nch <= 4: a subtract loop, not an integer division, on the issue thread's path
+            while (cc >= p.chunks) cc -= p.chunks;
             if (++s == S) { s = 0; ph ^= 1u; }
           }
         }
