@@ -359,6 +359,7 @@ def main(argv=None):
     ap.add_argument('--resume_from_checkpoint', type=str, default=None,
                     help='checkpoint file to resume from, or "auto" for the latest md_checkpoint*.json next to the output file')
     ap.add_argument('--allow_checkpoint_overwrite', action='store_true')
+    ap.add_argument('--include_max_conf', action='store_true', help='keep max_detection_conf in the output (off by default)')
     args = ap.parse_args(argv)
     output_dir = os.path.dirname(os.path.abspath(args.output_file))
     os.makedirs(output_dir, exist_ok=True)
@@ -388,7 +389,8 @@ def main(argv=None):
     results, times = run_sharded(args.detector_file, files, args.gpus, args.batch_size, args.threshold,
                                  gpu_decode=args.gpu_decode, checkpoint_path=checkpoint_path,
                                  checkpoint_frequency=args.checkpoint_frequency, results=restored)
-    write_results(results, args.output_file, args.image_dir if args.output_relative_filenames else None, args.detector_file)
+    write_results(results, args.output_file, args.image_dir if args.output_relative_filenames else None, args.detector_file,
+                  include_max_conf=args.include_max_conf)
     if checkpoint_path and os.path.isfile(checkpoint_path):
         os.remove(checkpoint_path)
         print('Deleted checkpoint file {}'.format(checkpoint_path))
