@@ -332,7 +332,11 @@ static void conv_launch_pair(ConvOp* op, int n_img, cudaStream_t st) {
   p.dbg = d_dbg;
   // programmatic dependent launch: the next layer's CTAs start (barrier init, TMEM allocation, bias) as SMs free up and wait
   // for this layer's completion before touching activations.  -3 % network time at 8 images, neutral at 64; MDB_CONV_PDL=0: off
-  static const bool pdl = !(getenv("MDB_CONV_PDL") && getenv("MDB_CONV_PDL")[0] == '0');
+  static const bool pdl_on = !(getenv("MDB_CONV_PDL") && getenv("MDB_CONV_PDL")[0] == '0');
+  // ... for launches of up to 16 images (MDB_CONV_PDL_MAX_IMAGES): the pipelined end-to-end path runs 16-image chunks and gains
+  // (e2e 1486 vs 1472 images/s), the 64-image resident pass loses 0.6 % with it (profiles/r02_conv_ab_experiments.txt par. 14, 18)
+  static const int pdl_max_images = getenv("MDB_CONV_PDL_MAX_IMAGES") ? atoi(getenv("MDB_CONV_PDL_MAX_IMAGES")) : 16;
+  const bool pdl = pdl_on && n_img <= pdl_max_images;
   p.pdl = pdl ? 1 : 0;
   if (pdl) {
     cudaLaunchConfig_t cfg = {};
