@@ -19,16 +19,17 @@ static PyObject* g_cat_str[16];  // str(c) for small class ids
 
 static double truncate_d(double x, double f) { return floor(x * f) / f; }
 
-// Python round(x, nd): correctly rounded decimal, half to even -- delegate to float.__round__ (the non-classic modes only)
+// Python round(x, nd) for nd > 0: correctly rounded decimal, half to even -- what float.__round__ does (Objects/floatobject.c
+// double_round): shortest 'f' formatting with nd digits through dtoa, parsed back (the non-classic modes only)
 static int py_round(double x, int nd, double* out) {
-  PyObject* f = PyFloat_FromDouble(x);
-  if (!f) return -1;
-  PyObject* r = PyObject_CallMethod(f, "__round__", "i", nd);
-  Py_DECREF(f);
-  if (!r) return -1;
-  *out = PyFloat_AsDouble(r);
-  Py_DECREF(r);
-  return (*out == -1.0 && PyErr_Occurred()) ? -1 : 0;
+  if (!isfinite(x)) { *out = x; return 0; }
+  char* buf = PyOS_double_to_string(x, 'f', nd, 0, NULL);
+  if (!buf) return -1;
+  const double r = PyOS_string_to_double(buf, NULL, NULL);
+  PyMem_Free(buf);
+  if (r == -1.0 && PyErr_Occurred()) return -1;
+  *out = r;
+  return 0;
 }
 
 // format_detections(det, count, src_h, src_w, use_model_native_classes, classic) -> (list of dicts ascending conf, max_conf)
