@@ -166,6 +166,14 @@ MDB_API int mdb_debug_fetch(mdb_engine* e, int32_t what, int32_t index, void* ho
  * step names (conv names of oracle.yolov5.conv_specs; "model.N.cv12.conv" for the fused C3 entry pair; "upsample.13|17|21";
  * "sppf_pool.11").  This is what lets tests compare every one of the 163 convolutions of pytorch_detector.py:1313 with a
  * PyTorch evaluation of the same layer on the engine's own input.  shape5 = N, H, W, C, is_fp32. */
+/* Parity harness only, no GPU needed: the addressing tables of K2's 3x3 halo main loop (how the TMA boxes of one
+ * 64-channel chunk are laid out in an A stage and where the tcgen05 descriptor of filter tap (kh, kw) starts), so that a test can
+ * model which input pixel every MMA row of every tap reads -- the im2col that cuDNN performs inside the reference's
+ * `model(x)` (pytorch_detector.py:1313).  mode 0: stride 1, one box per kw shift; 1: stride 1, single box; 2: stride 2,
+ * four parity-view boxes.  out64: [0] boxes, [1] bytes per chunk, [2] stage bytes, then per box (4 each) offset, tensor map,
+ * parity view (-1: the tensor itself, else py * 2 + px), dx, dy, width, height from [4]; per tap (9 each) byte offset from [32],
+ * group stride >> 4 from [41]. */
+MDB_API int mdb_debug_halo_layout(int32_t mode, int32_t* out64);
 MDB_API int mdb_debug_set_trace(mdb_engine* e, const char* names);
 MDB_API int mdb_debug_trace_names(mdb_engine* e, char* names_out, size_t cap, int32_t* n_steps);
 MDB_API int mdb_debug_fetch_trace(mdb_engine* e, const char* name, int32_t which, void* host_dst, size_t bytes, int64_t* shape5);

@@ -22,7 +22,7 @@ EXPORTS = [
     'mdb_letterbox_geometry', 'mdb_set_image_size', 'mdb_debug_fetch', 'mdb_last_timing', 'mdb_bench_resident', 'mdb_profile_steps', 'mdb_set_pipeline_split', 'mdb_launch_count', 'mdb_op_letterbox',
     'mdb_op_conv2d', 'mdb_op_nms', 'mdb_alloc_pinned', 'mdb_free_pinned', 'mdb_version',
     'mdb_infer_jpeg_batch', 'mdb_op_decode_jpeg', 'mdb_infer_preprocessed_rp', 'mdb_set_augment',
-    'mdb_debug_set_trace', 'mdb_debug_trace_names', 'mdb_debug_fetch_trace', 'mdb_op_upsample2x', 'mdb_op_sppf_pool', 'mdb_op_decode',
+    'mdb_debug_halo_layout', 'mdb_debug_set_trace', 'mdb_debug_trace_names', 'mdb_debug_fetch_trace', 'mdb_op_upsample2x', 'mdb_op_sppf_pool', 'mdb_op_decode',
 ]
 
 
@@ -120,6 +120,8 @@ def load_library():
     lib.mdb_op_decode_jpeg.restype = C.c_int
     lib.mdb_debug_set_trace.argtypes = [vp, C.c_char_p]
     lib.mdb_debug_set_trace.restype = C.c_int
+    lib.mdb_debug_halo_layout.argtypes = [C.c_int32, P(C.c_int32)]
+    lib.mdb_debug_halo_layout.restype = C.c_int
     lib.mdb_debug_trace_names.argtypes = [vp, vp, C.c_size_t, P(C.c_int32)]
     lib.mdb_debug_trace_names.restype = C.c_int
     lib.mdb_debug_fetch_trace.argtypes = [vp, C.c_char_p, C.c_int32, vp, C.c_size_t, P(C.c_int64)]
@@ -187,6 +189,20 @@ def letterbox_geometry(cfg, h, w):
         raise ValueError('mdb_letterbox_geometry failed ({})'.format(rc))
     return {'new_unpad': (out[0], out[1]), 'top': out[2], 'bottom': out[3], 'left': out[4], 'right': out[5],
             'out_hw': (out[6], out[7]), 'ratio': (rp[0], rp[0]), 'pad': (rp[1], rp[2])}
+
+
+def halo_layout(mode):
+    """Addressing tables of K2's 3x3 halo main loop (pure host arithmetic; mdb_debug_halo_layout): dict of lists."""
+    lib = load_library()
+    o = (C.c_int32 * 64)()
+    rc = lib.mdb_debug_halo_layout(mode, o)
+    if rc != MDB_OK:
+        raise ValueError('mdb_debug_halo_layout({}) failed ({})'.format(mode, rc))
+    n = o[0]
+    return {'n_boxes': n, 'a_tx': o[1], 'a_stage_bytes': o[2], 'box_off': list(o[4:4 + n]), 'box_map': list(o[8:8 + n]),
+            'box_par': list(o[12:12 + n]), 'box_dx': list(o[16:16 + n]), 'box_dy': list(o[20:20 + n]),
+            'box_w': list(o[24:24 + n]), 'box_h': list(o[28:28 + n]), 'tap_off': list(o[32:41]),
+            'tap_sbo': [v << 4 for v in o[41:50]]}
 
 
 class PinnedArray:

@@ -76,6 +76,15 @@ struct ConvDesc {
   int pad_x = -1;  // column padding when it differs from pad (-1: same)
 };
 // opts the conv kernel of the CURRENT device into its full dynamic shared memory (call once per device, after cudaSetDevice)
+// addressing tables of the 3x3 halo main loop (conv_host.cu::halo_layout; mirrored into PairParams by conv_plan)
+struct HaloLayout {
+  int n_boxes;
+  uint32_t a_tx, a_stage_bytes;
+  uint32_t box_off[4];
+  int box_map[4], box_par[4], box_dx[4], box_dy[4], box_w[4], box_h[4];
+  uint32_t tap_off[9], tap_sbo[9];
+};
+HaloLayout halo_layout(int mode);
 void conv_init_device();
 ConvOp* conv_build(const ConvDesc& d, int num_sms);
 void conv_launch(ConvOp* op, int n_img, cudaStream_t st);

@@ -38,6 +38,61 @@ int conv_cin_pad(int cin) {
   return ((cin + 63) / 64) * 64;
 }
 
+HaloLayout halo_layout(int mode) {
+  // mode 0: stride 1, one 8 px x 18 row box per kw shift (the tap's kh shift is a whole 1024-byte image row of its box);
+  // mode 1: stride 1, ONE 10 px x 18 row box: tap (kh, kw) starts kh rows (1280 bytes each) and kw pixels (128 bytes) in;
+  // mode 2: stride 2, one box per parity view (py, px) = in[2r + py][2c + px]: output (y, x), tap (kh, kw) reads
+  //         in[2y + kh - 1][2x + kw - 1], i.e. kh = 0 -> row y - 1 of the odd rows, kh = 1 -> row y of the even rows,
+  //         kh = 2 -> row y of the odd rows (columns alike): boxes of 8|9 px x 16|17 rows starting one row / pixel early
+  //         on the odd views.
+  // Pure host arithmetic (tests/test_capi_host.py models the addressing from these tables without a GPU).
+  HaloLayout L{};
+  auto align1k = [](uint32_t v) { return (v + 1023u) & ~1023u; };
+  if (mode == 0) {
+    L.n_boxes = 3;
+    for (int b = 0; b < 3; ++b) {
+      L.box_off[b] = static_cast<uint32_t>(b) * kHaloBox; L.box_map[b] = 0; L.box_par[b] = -1;
+      L.box_dx[b] = b - 1; L.box_dy[b] = -1; L.box_w[b] = kHaloTw; L.box_h[b] = kHaloRows;
+    }
+    L.a_tx = 3 * kHaloBox;
+    L.a_stage_bytes = 3 * kHaloBox;
+    for (int t = 0; t < 9; ++t) {
+      L.tap_off[t] = static_cast<uint32_t>(t % 3) * kHaloBox + static_cast<uint32_t>(t / 3) * 1024u;
+      L.tap_sbo[t] = 1024u >> 4;
+    }
+  } else if (mode == 1) {
+    L.n_boxes = 1;
+    L.box_off[0] = 0; L.box_map[0] = 0; L.box_par[0] = -1; L.box_dx[0] = -1; L.box_dy[0] = -1;
+    L.box_w[0] = kHaloTw + 2; L.box_h[0] = kHaloRows;
+    L.a_tx = kHalo1Box;
+    L.a_stage_bytes = kHalo1Stage;
+    for (int t = 0; t < 9; ++t) {
+      L.tap_off[t] = static_cast<uint32_t>(t % 3) * 128u + static_cast<uint32_t>(t / 3) * kHalo1Pitch;
+      L.tap_sbo[t] = kHalo1Pitch >> 4;
+    }
+  } else {
+    MDB_REQUIRE(mode == 2, "halo layout mode must be 0, 1 or 2");
+    L.n_boxes = 4;
+    uint32_t off = 0, pitch[4];
+    for (int v = 0; v < 4; ++v) {
+      const int py = v >> 1, px = v & 1;
+      L.box_off[v] = off; L.box_map[v] = v; L.box_par[v] = v; L.box_dx[v] = -px; L.box_dy[v] = -py;
+      L.box_w[v] = kHaloTw + px; L.box_h[v] = kHaloTh + py;
+      pitch[v] = static_cast<uint32_t>(L.box_w[v]) * 128u;
+      L.a_tx += static_cast<uint32_t>(L.box_w[v] * L.box_h[v]) * 128u;
+      off += align1k(static_cast<uint32_t>(L.box_w[v] * L.box_h[v]) * 128u);
+    }
+    L.a_stage_bytes = off;
+    for (int t = 0; t < 9; ++t) {
+      const int kh = t / 3, kx = t % 3;
+      const int v = (kh != 1 ? 2 : 0) | (kx != 1 ? 1 : 0);
+      L.tap_off[t] = L.box_off[v] + (kh == 2 ? pitch[v] : 0u) + (kx == 2 ? 128u : 0u);
+      L.tap_sbo[t] = pitch[v] >> 4;
+    }
+  }
+  return L;
+}
+
 static void pick_tile(int H, int W, int* tw, int* th) {
   // maximise useful rows per 128-row MMA tile; prefer wide tiles (longer contiguous TMA rows)
   double best = -1;
@@ -203,66 +258,31 @@ ConvOp* conv_build(const ConvDesc& d, int num_sms) {
       const double eff = static_cast<double>(Ho) * Wo / (static_cast<double>((Wo + 7) / 8 * 8) * ((Ho + 15) / 16 * 16));
       const bool shape_ok = allow && d.k == 3 && kw == 3 && d.pad == 1 && pad_x == 1 && eff >= 0.85 && q.chunks >= halo_min_chunks;
       const size_t budget = 227 * 1024 - 8192 - 1024;  // static: barriers + the bias vector; alignment slack
-      auto align1k = [](uint32_t v) { return (v + 1023u) & ~1023u; };
       bool use = false;
+      HaloLayout L{};
       if (shape_ok && d.s == 1) {
         // measured (one filter row per weight stage): -26% time at 80 ch, -16% at 160, -9% at 320; single box: another -2..-6 %
         use = true;
+        L = halo_layout(single ? 1 : 0);
         q.a_stages = eas ? std::max(2, std::min(kHaloMaxA, atoi(eas))) : (single ? 3 : 2);
-        if (single) {
-          make_act_tmap(&op->tmA[0], in, kc, kHaloTw + 2, kHaloRows, -1, -1);
-          q.n_boxes = 1;
-          q.box_off[0] = 0; q.box_map[0] = 0; q.box_dx[0] = -1; q.box_dy[0] = -1;
-          q.a_tx = kHalo1Box;
-          q.a_stage_bytes = kHalo1Stage;
-          for (int t = 0; t < 9; ++t) {
-            q.tap_off[t] = static_cast<uint32_t>(t % 3) * 128u + static_cast<uint32_t>(t / 3) * kHalo1Pitch;
-            q.tap_sbo[t] = kHalo1Pitch >> 4;
-          }
-        } else {
-          make_act_tmap(&op->tmA[0], in, kc, kHaloTw, kHaloRows, -1, -1);
-          q.n_boxes = 3;
-          for (int b = 0; b < 3; ++b) {
-            q.box_off[b] = static_cast<uint32_t>(b) * kHaloBox; q.box_map[b] = 0; q.box_dx[b] = b - 1; q.box_dy[b] = -1;
-          }
-          q.a_tx = 3 * kHaloBox;
-          q.a_stage_bytes = 3 * kHaloBox;
-          for (int t = 0; t < 9; ++t) {
-            q.tap_off[t] = static_cast<uint32_t>(t % 3) * kHaloBox + static_cast<uint32_t>(t / 3) * 1024u;
-            q.tap_sbo[t] = 1024u >> 4;
-          }
-        }
-        for (int i = 1; i < 4; ++i) op->tmA[i] = op->tmA[0];
       } else if (shape_ok && d.s == 2 && allow_s2) {
-        // parity view (py, px) = in[2r + py][2c + px]; output (y, x), tap (kh, kw) reads in[2y + kh - 1][2x + kw - 1]:
-        // kh = 0 -> view row y - 1 of the odd rows, kh = 1 -> row y of the even rows, kh = 2 -> row y of the odd rows (columns alike)
-        uint32_t off = 0, tx = 0;
-        uint32_t view_off[4], view_pitch[4];
-        for (int v = 0; v < 4; ++v) {
-          const int bw = kHaloTw + (v & 1), bh = kHaloTh + (v >> 1);
-          view_off[v] = off;
-          view_pitch[v] = static_cast<uint32_t>(bw) * 128u;
-          tx += static_cast<uint32_t>(bw * bh) * 128u;
-          off += align1k(static_cast<uint32_t>(bw * bh) * 128u);
+        L = halo_layout(2);
+        q.a_stages = 2;
+        use = 2 * static_cast<size_t>(L.a_stage_bytes) + 2 * 3 * b_chunk <= budget;  // two A stages + two weight stages must fit
+        if (!use) q.a_stages = 0;
+      }
+      if (use) {
+        q.n_boxes = L.n_boxes;
+        q.a_tx = L.a_tx;
+        q.a_stage_bytes = L.a_stage_bytes;
+        for (int b = 0; b < L.n_boxes; ++b) {
+          q.box_off[b] = L.box_off[b]; q.box_map[b] = L.box_map[b]; q.box_dx[b] = L.box_dx[b]; q.box_dy[b] = L.box_dy[b];
+          const int par = L.box_par[b];
+          make_act_tmap(&op->tmA[L.box_map[b]], in, kc, L.box_w[b], L.box_h[b], par < 0 ? -1 : par >> 1, par < 0 ? -1 : par & 1);
         }
-        use = 2 * static_cast<size_t>(off) + 2 * 3 * b_chunk <= budget;  // two A stages + two weight stages must fit
-        if (use) {
-          q.n_boxes = 4;
-          q.a_tx = tx;
-          q.a_stage_bytes = off;
-          q.a_stages = 2;
-          for (int v = 0; v < 4; ++v) {
-            const int py = v >> 1, px = v & 1;
-            make_act_tmap(&op->tmA[v], in, kc, kHaloTw + px, kHaloTh + py, py, px);
-            q.box_off[v] = view_off[v]; q.box_map[v] = v; q.box_dx[v] = -px; q.box_dy[v] = -py;
-          }
-          for (int t = 0; t < 9; ++t) {
-            const int kh = t / 3, kx = t % 3;
-            const int v = (kh != 1 ? 2 : 0) | (kx != 1 ? 1 : 0);
-            q.tap_off[t] = view_off[v] + (kh == 2 ? view_pitch[v] : 0u) + (kx == 2 ? 128u : 0u);
-            q.tap_sbo[t] = view_pitch[v] >> 4;
-          }
-        }
+        if (L.box_par[0] < 0)
+          for (int i = 1; i < 4; ++i) op->tmA[i] = op->tmA[0];
+        for (int t = 0; t < 9; ++t) { q.tap_off[t] = L.tap_off[t]; q.tap_sbo[t] = L.tap_sbo[t]; }
       }
       if (use) {
         q.halo = 1;

@@ -1631,6 +1631,24 @@ int mdb_debug_set_trace(mdb_engine* e, const char* names) {
   return MDB_OK;
 }
 
+int mdb_debug_halo_layout(int32_t mode, int32_t* out64) {
+  if (!out64 || mode < 0 || mode > 2) return MDB_ERR_ARG;
+  try {
+    const HaloLayout L = halo_layout(mode);
+    int32_t* o = out64;
+    for (int i = 0; i < 64; ++i) o[i] = 0;
+    o[0] = L.n_boxes; o[1] = static_cast<int32_t>(L.a_tx); o[2] = static_cast<int32_t>(L.a_stage_bytes);
+    for (int b = 0; b < 4; ++b) {
+      o[4 + b] = static_cast<int32_t>(L.box_off[b]); o[8 + b] = L.box_map[b]; o[12 + b] = L.box_par[b];
+      o[16 + b] = L.box_dx[b]; o[20 + b] = L.box_dy[b]; o[24 + b] = L.box_w[b]; o[28 + b] = L.box_h[b];
+    }
+    for (int t = 0; t < 9; ++t) { o[32 + t] = static_cast<int32_t>(L.tap_off[t]); o[41 + t] = static_cast<int32_t>(L.tap_sbo[t]); }
+  } catch (...) {
+    return MDB_ERR_ARG;
+  }
+  return MDB_OK;
+}
+
 int mdb_debug_trace_names(mdb_engine* e, char* names_out, size_t cap, int32_t* n_steps) {
   if (!e || !n_steps) return MDB_ERR_ARG;
   if (!e->last_plan) return fail(e, MDB_ERR_STATE, "no batch has been run yet");

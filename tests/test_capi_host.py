@@ -52,3 +52,45 @@ def test_no_gpu_means_loud_failure_not_fallback():
     from megadetector_b200.detector import B200Detector
     with pytest.raises(Exception):
         B200Detector('synthetic://tiny?seed=0', {'max_batch': 1})
+
+
+@pytest.mark.parametrize('mode', [0, 1, 2])
+def test_halo_main_loop_addressing_tables(mode):
+    """K2's 3x3 halo loop (csrc/conv_host.cu::halo_layout): model the shared-memory image the TMA boxes of one chunk leave
+    behind and check that every MMA row of every filter tap -- descriptor start + group * SBO + row * 128 bytes -- reads
+    exactly the input pixel the convolution needs (stride 1: in[y + kh - 1][x + kw - 1]; stride 2: in[2y + kh - 1][2x + kw - 1]
+    through the parity views)."""
+    from megadetector_b200 import _capi
+    L = _capi.halo_layout(mode)
+    stride = 2 if mode == 2 else 1
+    tw, th = 8, 16                       # output tile: 8 px x 16 rows = the 128 MMA rows of one CTA
+    ox0, oy0 = 5 * tw, 3 * th            # some tile origin (in output = view coordinates)
+    smem = {}                            # byte offset of a 128-byte pixel row -> (parity view, view row, view col)
+    total = 0
+    for b in range(L['n_boxes']):
+        assert L['box_off'][b] % 1024 == 0           # every box starts on a swizzle period
+        nbytes = L['box_w'][b] * L['box_h'][b] * 128
+        total += nbytes
+        assert L['box_off'][b] + nbytes <= L['a_stage_bytes']
+        for j in range(L['box_h'][b]):
+            for i in range(L['box_w'][b]):
+                addr = L['box_off'][b] + (j * L['box_w'][b] + i) * 128   # TMA writes the box densely, pixel-major rows
+                assert addr not in smem                                 # boxes do not overlap
+                smem[addr] = (L['box_par'][b], oy0 + L['box_dy'][b] + j, ox0 + L['box_dx'][b] + i)
+    assert total == L['a_tx'] and L['a_stage_bytes'] % 1024 == 0
+    for t in range(9):
+        kh, kw = divmod(t, 3)
+        assert L['tap_off'][t] % 128 == 0 and L['tap_sbo'][t] % 16 == 0
+        for r in range(th):
+            for x in range(tw):
+                m = r * tw + x                                           # MMA row: group m // 8 = image row r, row in group = x
+                addr = L['tap_off'][t] + (m // 8) * L['tap_sbo'][t] + (m % 8) * 128
+                iy, ix = stride * (oy0 + r) + kh - 1, stride * (ox0 + x) + kw - 1
+                if stride == 1:
+                    want = (-1, iy, ix)
+                else:
+                    py, px = iy & 1, ix & 1
+                    want = (py * 2 + px, (iy - py) // 2, (ix - px) // 2)
+                assert smem.get(addr) == want, (mode, kh, kw, r, x)
+    with pytest.raises(ValueError):
+        _capi.halo_layout(3)
